@@ -1,0 +1,741 @@
+// guardx.cu -- kernels and C ABI of libguardx.so (see include/guardx.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//        -Xcompiler -ffp-contract=off,-fPIC -shared guardx.cu -o ../libguardx.so
+// -fmad=false / -ffp-contract=off are REQUIRED (bit-parity contract, gx_math.h).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/guardx.h"
+#include "gx_device.cuh"
+
+#define GX_API extern "C" __attribute__((visibility("default")))
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int gx_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define GX_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return gx_fail(GX_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                               \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+      cudaSetDevice(dev);
+      switched = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------
+struct gx_env {
+  gx_config cfg;
+  gx_params p;
+  GxState s;
+  int device;
+  int sm_count;
+  float* pool;          // [pool_size, lay_dim]
+  int32_t* pool_tries;  // [pool_size]
+  double* stats;        // [8] device
+  uint64_t epoch;       // pool generations so far
+  uint64_t t_global;    // step() calls so far
+  bool have_reset;
+  bool stats_on;
+  // staging for gx_step_host
+  float* stage;  // [n*act_dim | n*obs_dim | n | n | n]
+};
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// Threads per block for one-thread-per-env kernels: small batches are spread
+// over as many SMs as possible (latency-bound regime), large batches use 128.
+static inline int pick_block(const gx_env* e) {
+  const int n = e->p.n;
+  int block = 128;
+  if (n <= e->sm_count * 32 * 4) block = 32;
+  else if (n <= e->sm_count * 64 * 8) block = 64;
+  while (block > 32 && (size_t)block * e->p.obs_dim * sizeof(float) > 48 * 1024) block >>= 1;
+  return block;
+}
+
+// ---------------------------------------------------------------------------
+// layout pool (reset_layout, engine.py:433-444; sample_layout :546-572)
+//
+// One WARP per pool slot.  Candidate `attempt` of slot j is a pure function of
+// (key, j, attempt), so the 32 lanes test 32 consecutive attempts at once and
+// the lowest successful one wins -- the same layout the sequential oracle finds,
+// without the geometric-tail divergence of one thread per slot.
+// ---------------------------------------------------------------------------
+#define GX_MAX_POOL_ATTEMPTS (1u << 16)
+
+__device__ __forceinline__ int gx_class_of(int obj, int nh) {
+  return obj == 0 ? GX_CLS_GOAL : (obj <= nh ? GX_CLS_HAZARD : GX_CLS_ROBOT);
+}
+
+__device__ bool gx_sample_layout(const gx_params& p, uint32_t k0, uint32_t k1, uint32_t slot,
+                                 uint32_t attempt, float (*placed)[2]) {
+  const int nh = p.nh, nobj = nh + 2;
+  for (int o = 0; o < nobj; ++o) {
+    const int cls = gx_class_of(o, nh);
+    bool conflicted = true;
+    float x = -1e30f, y = -1e30f;
+    for (int t = 0; t < p.tries; ++t) {
+      gx_u32x4 r = gx_philox4x32_10(slot, attempt, ((uint32_t)o << 8) | (uint32_t)t, GX_STREAM_LAYOUT, k0, k1);
+      float cx = gx_uniform(r.v[0], p.lo[cls][0], p.hi[cls][0]);
+      float cy = gx_uniform(r.v[1], p.lo[cls][1], p.hi[cls][1]);
+      bool valid = true;
+      for (int q = 0; q < o; ++q) {
+        float dx = cx - placed[q][0], dy = cy - placed[q][1];
+        float dist = gx_sqrt(dx * dx + dy * dy);
+        if (dist < p.keepsum[gx_class_of(q, nh)][cls]) valid = false;
+      }
+      if (valid) { x = cx; y = cy; conflicted = false; }
+    }
+    if (conflicted) return false;  // success can no longer be 1 (engine.py:569)
+    placed[o][0] = x;
+    placed[o][1] = y;
+  }
+  float dx = placed[nobj - 1][0] - placed[0][0], dy = placed[nobj - 1][1] - placed[0][1];
+  return !(gx_sqrt(dx * dx + dy * dy) < p.min_robot_goal);
+}
+
+__global__ void __launch_bounds__(128) gx_pool_kernel(const __grid_constant__ gx_params p, uint32_t k0,
+                                                      uint32_t k1, float* __restrict__ pool,
+                                                      int32_t* __restrict__ tries) {
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= p.pool_size) return;
+  float placed[2 + GX_MAX_HAZARDS][2];
+  for (uint32_t base = 0; base < GX_MAX_POOL_ATTEMPTS; base += 32) {
+    const uint32_t attempt = base + lane;
+    bool ok = gx_sample_layout(p, k0, k1, (uint32_t)slot, attempt, placed);
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) {
+      const int win = __ffs(m) - 1;
+      if (lane == win) {
+        float* out = pool + (size_t)slot * p.lay_dim;
+        const int nobj = p.nh + 2;
+        out[0] = placed[0][0]; out[1] = placed[0][1];
+        out[2] = placed[nobj - 1][0]; out[3] = placed[nobj - 1][1];
+        for (int h = 0; h < p.nh; ++h) { out[4 + 2 * h] = placed[1 + h][0]; out[5 + 2 * h] = placed[1 + h][1]; }
+        tries[slot] = (int32_t)(base + win + 1);
+      }
+      return;
+    }
+  }
+  // acceptance rate ~0: the configuration cannot be laid out (the reference
+  // would fail `assert self.layout_size > self.env_num`, engine.py:444)
+  if (lane == 0) tries[slot] = -1;
+}
+
+// ---------------------------------------------------------------------------
+// placement of one env from a layout row (layout2qpos, engine.py:623-639)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ const float* gx_pick_layout(const gx_params& p, const float* pool,
+                                                       const float* layout, int i, uint64_t t_global,
+                                                       uint32_t stream) {
+  if (layout) return layout + (size_t)i * p.lay_dim;
+  const uint64_t g = p.env_id_offset + (uint64_t)i;
+  gx_u32x4 r = gx_philox4x32_10((uint32_t)g, (uint32_t)t_global, (uint32_t)(t_global >> 32), stream, p.seed_lo, p.seed_hi);
+  const uint32_t idx = gx_randint(r.v[0], (uint32_t)p.pool_size);
+  return pool + (size_t)idx * p.lay_dim;
+}
+
+template <int NH_CT>
+__device__ __forceinline__ void gx_place(const gx_params& p, const GxState& s, int i, const float* lay,
+                                         float& gx_, float& gy_, float4* hz_regs, GxDyn& d) {
+  const int nh = NH_CT ? NH_CT : p.nh;
+  if (NH_CT && ((reinterpret_cast<uintptr_t>(lay) & 15u) == 0) && (NH_CT % 2 == 0)) {
+    const float4* l4 = reinterpret_cast<const float4*>(lay);
+    float4 a = l4[0];
+    gx_ = a.x; gy_ = a.y; d.qx = a.z; d.qy = a.w;
+#pragma unroll
+    for (int k = 0; k < NH_CT / 2; ++k) {
+      hz_regs[k] = l4[1 + k];
+      s.hz[(size_t)k * s.cap + i] = hz_regs[k];
+    }
+  } else {
+    gx_ = lay[0]; gy_ = lay[1]; d.qx = lay[2]; d.qy = lay[3];
+    for (int k = 0; k < s.nh2; ++k) {
+      float4 h;
+      h.x = lay[4 + 4 * k]; h.y = lay[5 + 4 * k];
+      h.z = (2 * k + 1 < nh) ? lay[6 + 4 * k] : 0.0f;
+      h.w = (2 * k + 1 < nh) ? lay[7 + 4 * k] : 0.0f;
+      if (NH_CT) hz_regs[k] = h;
+      s.hz[(size_t)k * s.cap + i] = h;
+    }
+  }
+  s.goal[i] = make_float2(gx_, gy_);
+  d.qth = 0.0f; d.vx = 0.0f; d.vy = 0.0f; d.vw = 0.0f;
+}
+
+template <int NH_CT>
+__device__ __forceinline__ void gx_load_static(const GxState& s, int i, float& gx_, float& gy_, float4* hz_regs) {
+  float2 g = s.goal[i];
+  gx_ = g.x; gy_ = g.y;
+  if (NH_CT) {
+#pragma unroll
+    for (int k = 0; k < (NH_CT + 1) / 2; ++k) hz_regs[k] = s.hz[(size_t)k * s.cap + i];
+  }
+}
+
+extern __shared__ __align__(16) float gx_smem[];
+
+// ---- Engine.reset (engine.py:454-467) -------------------------------------
+template <int NH_CT>
+__global__ void gx_reset_kernel(const __grid_constant__ gx_params p, const GxState s,
+                                const float* __restrict__ pool, const float* __restrict__ layout,
+                                uint64_t t_global, float* __restrict__ obs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wbase = i - lane;
+  if (wbase >= p.n) return;
+  float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
+  float* row = tile + lane * p.obs_dim;
+  if (i < p.n) {
+    const float* lay = gx_pick_layout(p, pool, layout, i, t_global, GX_STREAM_PICK ^ 1u);
+    float4 hz_regs[NH_CT ? (NH_CT + 1) / 2 : 1];
+    float gx_, gy_;
+    GxDyn d;
+    gx_place<NH_CT>(p, s, i, lay, gx_, gy_, hz_regs, d);
+    const float old = s.d2[i].y;  // reset() leaves Engine._done stale (engine.py:463)
+    d.done = (__float_as_uint(old) >> 31) ? 1.0f : 0.0f;
+    d.steps = 0.0f;
+    d.prev_dist = gx_reset_row<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, row);
+    gx_kinematics(d.qth, d.hc, d.hs);  // mjx.forward at the reset pose (engine.py:655): R = I
+    gx_store_dyn(s, i, d);
+    if (s.ep) s.ep[i] = make_float4(0.f, 0.f, 0.f, s.ep[i].w);
+  }
+  const int rows = min(32, p.n - wbase);
+  gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
+}
+
+// ---- episode statistics (ppo_train.py:370-376, 405-411 on the host) --------
+__device__ __forceinline__ void gx_stats_step(const GxState& s, int i, double* stats, float reward,
+                                              float cost, float done) {
+  float4 e = s.ep[i];
+  e.x += reward; e.y += cost; e.z += 1.0f; e.w += cost;
+  if (done > 0.0f) {
+    atomicAdd(stats + 0, 1.0);
+    atomicAdd(stats + 1, (double)e.x);
+    atomicAdd(stats + 2, (double)e.y);
+    atomicAdd(stats + 3, (double)e.z);
+    atomicAdd(stats + 4, (double)e.x * (double)e.x);
+    atomicAdd(stats + 5, (double)e.y * (double)e.y);
+    e.x = 0.f; e.y = 0.f; e.z = 0.f;
+  }
+  s.ep[i] = e;
+}
+
+// total cost / total env-steps: one warp-reduced atomic per warp (all 32 lanes call)
+__device__ __forceinline__ void gx_stats_totals(double* stats, float my_cost, int rows, int lane) {
+  double cd = (double)my_cost;
+  for (int off = 16; off; off >>= 1) cd += __shfl_down_sync(0xffffffffu, cd, off);
+  if (lane == 0) { atomicAdd(stats + 6, cd); atomicAdd(stats + 7, (double)rows); }
+}
+
+// ---- Engine.step (engine.py:469-495) ---------------------------------------
+// qacc (info['obs']['qacc'], engine.py:763-764) is emitted when the pointer is
+// non-NULL (uniform branch); AUX selects the variant that also writes the integer
+// aux row.
+template <int NH_CT, bool AUX, bool STATS>
+__global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxState s,
+                               const float2* __restrict__ action, float* __restrict__ obs,
+                               float* __restrict__ reward, float* __restrict__ done,
+                               float* __restrict__ cost, float* __restrict__ qacc,
+                               int32_t* __restrict__ aux, double* __restrict__ stats) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wbase = i - lane;
+  if (wbase >= p.n) return;
+  float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
+  float* row = tile + lane * p.obs_dim;
+  float my_cost = 0.0f;
+  if (i < p.n) {
+    GxDyn d;
+    gx_load_dyn(s, i, d);
+    float4 hz_regs[NH_CT ? (NH_CT + 1) / 2 : 1];
+    float gx_, gy_;
+    gx_load_static<NH_CT>(s, i, gx_, gy_, hz_regs);
+    const float2 a = action[i];
+    float qa[3];
+    int32_t bins[AUX ? 1 + GX_MAX_HAZARDS : 1];
+    GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a.x, a.y, row,
+                                     qacc ? qa : nullptr, AUX ? bins : nullptr);
+    gx_store_dyn(s, i, d);
+    reward[i] = o.reward;
+    done[i] = o.done;
+    cost[i] = o.cost;
+    my_cost = o.cost;
+    if (qacc) { qacc[3 * (size_t)i] = qa[0]; qacc[3 * (size_t)i + 1] = qa[1]; qacc[3 * (size_t)i + 2] = qa[2]; }
+    if (AUX) {
+      int32_t* ax = aux + (size_t)i * p.aux_dim;
+      ax[0] = o.flags; ax[1] = o.violations;
+      for (int k = 0; k < 1 + p.nh; ++k) ax[2 + k] = bins[k];
+    }
+    if (STATS) gx_stats_step(s, i, stats, o.reward, o.cost, o.done);
+  }
+  const int rows = min(32, p.n - wbase);
+  gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
+  if (STATS) gx_stats_totals(stats, my_cost, rows, lane);
+}
+
+// ---- Engine.reset_done (engine.py:497-505, 702-731) -------------------------
+// Re-place ONE env whose done flag is set.  Lag heading, prev_dist, steps and the
+// done flag itself are deliberately left as they are (the reference returns the
+// un-stepped data and never clears _done).
+template <int NH_CT>
+__device__ __forceinline__ void gx_reset_done_env(const gx_params& p, const GxState& s, int i,
+                                                  const float* lay, GxDyn& d, float& gx_, float& gy_,
+                                                  float4* hz_regs, float* row) {
+  gx_place<NH_CT>(p, s, i, lay, gx_, gy_, hz_regs, d);
+  gx_reset_row<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, row);
+}
+
+template <int NH_CT>
+__global__ void gx_reset_done_kernel(const __grid_constant__ gx_params p, const GxState s,
+                                     const float* __restrict__ pool, const float* __restrict__ layout,
+                                     uint64_t t_global, const float* obs_in, float* obs_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wbase = i - lane;
+  if (wbase >= p.n) return;
+  const int rows = min(32, p.n - wbase);
+  float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
+  float* row = tile + lane * p.obs_dim;
+  const bool inplace = (obs_in == obs_out);
+  bool is_done = false;
+  if (i < p.n) is_done = (__float_as_uint(s.d2[i].y) >> 31) != 0;
+  const unsigned any = __ballot_sync(0xffffffffu, is_done);
+  if (!inplace) {
+    // stage the previous observation rows of this warp (Engine._obs)
+    const int total = rows * p.obs_dim;
+    const float* src = obs_in + (size_t)wbase * p.obs_dim;
+    if (rows == 32 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* t4 = reinterpret_cast<float4*>(tile);
+      for (int k = lane; k < (total >> 2); k += 32) t4[k] = s4[k];
+    } else {
+      for (int k = lane; k < total; k += 32) tile[k] = src[k];
+    }
+    __syncwarp();
+  } else if (!any) {
+    return;
+  }
+  if (is_done) {
+    GxDyn d;
+    gx_load_dyn(s, i, d);
+    float4 hz_regs[NH_CT ? (NH_CT + 1) / 2 : 1];
+    float gx_, gy_;
+    const float* lay = gx_pick_layout(p, pool, layout, i, t_global, GX_STREAM_PICK);
+    gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
+    gx_store_dyn(s, i, d);
+  }
+  if (!inplace) {
+    gx_store_tile(tile, obs_out + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
+  } else if (is_done) {
+    float* dst = obs_out + (size_t)i * p.obs_dim;
+    for (int k = 0; k < p.obs_dim; ++k) dst[k] = row[k];
+  }
+}
+
+// ---- synthetic random-action rollout (trpo/myTest.py:28-49 + reset_done) ----
+// T control steps in ONE launch; dynamic state, goal and hazards stay in
+// registers between steps; HBM sees only the per-step outputs.
+template <int NH_CT, bool STATS>
+__global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxState s,
+                                  const float* __restrict__ pool, int T, uint64_t t0,
+                                  float* __restrict__ obs, float2* __restrict__ act,
+                                  float* __restrict__ reward, float* __restrict__ cost,
+                                  float* __restrict__ done, double* __restrict__ stats) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wbase = i - lane;
+  if (wbase >= p.n) return;
+  const int rows = min(32, p.n - wbase);
+  const bool live = i < p.n;
+  float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
+  float* row = tile + lane * p.obs_dim;
+  GxDyn d;
+  float4 hz_regs[NH_CT ? (NH_CT + 1) / 2 : 1];
+  float gx_ = 0.f, gy_ = 0.f;
+  if (live) {
+    gx_load_dyn(s, i, d);
+    gx_load_static<NH_CT>(s, i, gx_, gy_, hz_regs);
+  }
+  const uint64_t g = p.env_id_offset + (uint64_t)i;
+  const size_t n = (size_t)p.n;
+  for (int t = 0; t < T; ++t) {
+    const uint64_t tg = t0 + (uint64_t)t;
+    float my_cost = 0.0f;
+    if (live) {
+      gx_u32x4 u = gx_philox4x32_10((uint32_t)g, (uint32_t)tg, (uint32_t)(tg >> 32), GX_STREAM_ACTION, p.seed_lo, p.seed_hi);
+      const float a0 = gx_uniform(u.v[0], -1.0f, 1.0f), a1 = gx_uniform(u.v[1], -1.0f, 1.0f);
+      GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a0, a1, row, nullptr, nullptr);
+      if (STATS) gx_stats_step(s, i, stats, o.reward, o.cost, o.done);
+      my_cost = o.cost;
+      if (o.done > 0.0f) {
+        const float* lay = gx_pick_layout(p, pool, nullptr, i, tg + 1, GX_STREAM_PICK);
+        gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
+      }
+      const size_t k = (size_t)t * n + (size_t)i;
+      if (act) act[k] = make_float2(a0, a1);
+      if (reward) reward[k] = o.reward;
+      if (cost) cost[k] = o.cost;
+      if (done) done[k] = o.done;
+    }
+    if (obs) gx_store_tile(tile, obs + ((size_t)t * n + (size_t)wbase) * p.obs_dim, rows, p.obs_dim, lane);
+    if (STATS) gx_stats_totals(stats, my_cost, rows, lane);
+  }
+  if (live) gx_store_dyn(s, i, d);
+}
+
+// ---- state injection / checkpoint -------------------------------------------
+__global__ void gx_get_state_kernel(const __grid_constant__ gx_params p, const GxState s, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  GxDyn d;
+  gx_load_dyn(s, i, d);
+  float* o = out + (size_t)i * p.state_dim;
+  o[0] = d.qx; o[1] = d.qy; o[2] = d.qth; o[3] = d.vx; o[4] = d.vy; o[5] = d.vw;
+  o[6] = d.hc; o[7] = d.hs; o[8] = d.prev_dist; o[9] = d.done; o[10] = d.steps;
+  float2 g = s.goal[i];
+  o[11] = g.x; o[12] = g.y;
+  for (int h = 0; h < p.nh; ++h) {
+    float4 v = s.hz[(size_t)(h >> 1) * s.cap + i];
+    o[13 + 2 * h] = (h & 1) ? v.z : v.x;
+    o[14 + 2 * h] = (h & 1) ? v.w : v.y;
+  }
+}
+
+__global__ void gx_set_state_kernel(const __grid_constant__ gx_params p, const GxState s, const float* in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const float* o = in + (size_t)i * p.state_dim;
+  GxDyn d;
+  d.qx = o[0]; d.qy = o[1]; d.qth = o[2]; d.vx = o[3]; d.vy = o[4]; d.vw = o[5];
+  d.hc = o[6]; d.hs = o[7]; d.prev_dist = o[8]; d.done = o[9]; d.steps = o[10];
+  gx_store_dyn(s, i, d);
+  s.goal[i] = make_float2(o[11], o[12]);
+  for (int k = 0; k < s.nh2; ++k) {
+    float4 v;
+    v.x = o[13 + 4 * k]; v.y = o[14 + 4 * k];
+    v.z = (2 * k + 1 < p.nh) ? o[15 + 4 * k] : 0.0f;
+    v.w = (2 * k + 1 < p.nh) ? o[16 + 4 * k] : 0.0f;
+    s.hz[(size_t)k * s.cap + i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+GX_API int gx_abi_version(void) { return GX_ABI_VERSION; }
+GX_API int gx_config_size(void) { return (int)sizeof(gx_config); }
+GX_API const char* gx_last_error(void) { return g_err; }
+GX_API void gx_default_config(gx_config* cfg) {
+  if (cfg) gx_fill_default_config(cfg);
+}
+
+static size_t tile_bytes(const gx_env* e, int block) { return (size_t)block * e->p.obs_dim * sizeof(float); }
+static bool fast_path(const gx_env* e) { return e->p.nh == 8; }
+
+GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
+  if (!out) return gx_fail(GX_EINVAL, "gx_create: out is NULL");
+  *out = nullptr;
+  gx_params p;
+  memset(&p, 0, sizeof p);
+  if (const char* why = gx_lower_config(h_cfg, &p)) return gx_fail(GX_EINVAL, "gx_create: %s", why);
+  int ndev = 0;
+  GX_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return gx_fail(GX_EINVAL, "gx_create: device %d of %d", device, ndev);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  GX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return gx_fail(GX_ECUDA, "gx_create: device %d is sm_%d%d; libguardx.so is built for sm_100a only", device, prop.major, prop.minor);
+  gx_env* e = new (std::nothrow) gx_env();
+  if (!e) return gx_fail(GX_ENOMEM, "gx_create: host allocation failed");
+  e->cfg = *h_cfg;
+  e->p = p;
+  e->device = device;
+  e->sm_count = prop.multiProcessorCount;
+  e->epoch = 0; e->t_global = 0; e->have_reset = false; e->stats_on = false;
+  e->stage = nullptr;
+  const int cap = div_up(p.n, 32) * 32;
+  GxState& s = e->s;
+  memset(&s, 0, sizeof s);
+  s.cap = cap;
+  s.nh2 = (p.nh + 1) / 2;
+  e->pool = nullptr; e->pool_tries = nullptr; e->stats = nullptr;
+#define GX_ALLOC(ptr, bytes)                                                         \
+  do {                                                                               \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes));                            \
+    if (e_ != cudaSuccess) {                                                         \
+      gx_destroy(e);                                                                 \
+      return gx_fail(e_ == cudaErrorMemoryAllocation ? GX_ENOMEM : GX_ECUDA,         \
+                     "gx_create: cudaMalloc(%zu) failed: %s", (size_t)(bytes), cudaGetErrorString(e_)); \
+    }                                                                                \
+    cudaMemset((ptr), 0, (bytes));                                                   \
+  } while (0)
+  GX_ALLOC(s.d0, sizeof(float4) * cap);
+  GX_ALLOC(s.d1, sizeof(float4) * cap);
+  GX_ALLOC(s.d2, sizeof(float2) * cap);
+  GX_ALLOC(s.goal, sizeof(float2) * cap);
+  GX_ALLOC(s.hz, sizeof(float4) * (size_t)cap * s.nh2);
+  GX_ALLOC(s.ep, sizeof(float4) * cap);
+  GX_ALLOC(e->pool, sizeof(float) * (size_t)p.pool_size * p.lay_dim);
+  GX_ALLOC(e->pool_tries, sizeof(int32_t) * (size_t)p.pool_size);
+  GX_ALLOC(e->stats, sizeof(double) * 8);
+#undef GX_ALLOC
+  // never-forwarded mjx.Data carries the identity xmat that put_data copied in
+  {
+    float4* h = (float4*)malloc(sizeof(float4) * cap);
+    for (int i = 0; i < cap; ++i) h[i] = make_float4(0.f, 0.f, 1.f, 0.f);
+    cudaMemcpy(s.d1, h, sizeof(float4) * cap, cudaMemcpyHostToDevice);
+    free(h);
+  }
+  GX_CUDA(cudaDeviceSynchronize());
+  *out = e;
+  return GX_OK;
+}
+
+GX_API int gx_destroy(gx_env* e) {
+  if (!e) return GX_OK;
+  DeviceGuard guard(e->device);
+  cudaFree(e->s.d0); cudaFree(e->s.d1); cudaFree(e->s.d2); cudaFree(e->s.goal);
+  cudaFree(e->s.hz); cudaFree(e->s.ep);
+  cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage);
+  delete e;
+  return GX_OK;
+}
+
+GX_API int gx_obs_dim(const gx_env* e) { return e ? e->p.obs_dim : GX_EINVAL; }
+GX_API int gx_act_dim(const gx_env* e) { return e ? 2 : GX_EINVAL; }
+GX_API int gx_env_num(const gx_env* e) { return e ? e->p.n : GX_EINVAL; }
+GX_API int gx_pool_size(const gx_env* e) { return e ? e->p.pool_size : GX_EINVAL; }
+GX_API int gx_aux_dim(const gx_env* e) { return e ? e->p.aux_dim : GX_EINVAL; }
+GX_API int gx_state_dim(const gx_env* e) { return e ? e->p.state_dim : GX_EINVAL; }
+
+GX_API int gx_obs_offset(const gx_env* e, uint32_t component) {
+  if (!e) return GX_EINVAL;
+  switch (component) {
+    case GX_OBS_CTRL: return e->p.off_ctrl;
+    case GX_OBS_GOAL_COMPASS: return e->p.off_compass;
+    case GX_OBS_GOAL_LIDAR: return e->p.off_glidar;
+    case GX_OBS_HAZARDS_LIDAR: return e->p.off_hlidar;
+    case GX_OBS_QPOS: return e->p.off_qpos;
+    case GX_OBS_QVEL: return e->p.off_qvel;
+    default: return -1;
+  }
+}
+
+// engine.py:291-297: ctrlrange of the first two actuators, +-inf if not limited
+GX_API int gx_action_bounds(const gx_env* e, float* h_low, float* h_high) {
+  if (!e || !h_low || !h_high) return gx_fail(GX_EINVAL, "gx_action_bounds: NULL argument");
+  for (int i = 0; i < 2; ++i) {
+    h_low[i] = e->p.ctrllimited ? e->p.ctrl_lo : -INFINITY;
+    h_high[i] = e->p.ctrllimited ? e->p.ctrl_hi : INFINITY;
+  }
+  return GX_OK;
+}
+
+#define GX_LAUNCH_CHECK(name)                                                   \
+  do {                                                                          \
+    cudaError_t e_ = cudaGetLastError();                                        \
+    if (e_ != cudaSuccess)                                                      \
+      return gx_fail(GX_ECUDA, "%s launch failed: %s", name, cudaGetErrorString(e_)); \
+  } while (0)
+
+static int gx_generate_pool(gx_env* e, cudaStream_t st) {
+  gx_u32x4 key = gx_philox4x32_10((uint32_t)e->epoch, (uint32_t)(e->epoch >> 32), 0u, GX_STREAM_LAYOUT,
+                                  e->p.seed_lo, e->p.seed_hi);
+  const int block = 128;
+  const int grid = div_up(e->p.pool_size * 32, block);
+  gx_pool_kernel<<<grid, block, 0, st>>>(e->p, key.v[0], key.v[1], e->pool, e->pool_tries);
+  GX_LAUNCH_CHECK("gx_pool_kernel");
+  e->epoch += 1;
+  return GX_OK;
+}
+
+static int gx_reset_impl(gx_env* e, const float* layout, float* obs, cudaStream_t st) {
+  const int block = pick_block(e), grid = div_up(e->p.n, block);
+  const size_t sh = tile_bytes(e, block);
+  if (fast_path(e))
+    gx_reset_kernel<8><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs);
+  else
+    gx_reset_kernel<0><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs);
+  GX_LAUNCH_CHECK("gx_reset_kernel");
+  e->have_reset = true;
+  return GX_OK;
+}
+
+GX_API int gx_reset(gx_env* e, float* obs, void* stream) {
+  if (!e || !obs) return gx_fail(GX_EINVAL, "gx_reset: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = gx_generate_pool(e, st)) return rc;
+  return gx_reset_impl(e, nullptr, obs, st);
+}
+
+GX_API int gx_reset_with_layout(gx_env* e, const float* layout, float* obs, void* stream) {
+  if (!e || !obs || !layout) return gx_fail(GX_EINVAL, "gx_reset_with_layout: NULL argument");
+  DeviceGuard guard(e->device);
+  return gx_reset_impl(e, layout, obs, (cudaStream_t)stream);
+}
+
+template <int NH_CT>
+static void launch_step(gx_env* e, int grid, int block, size_t sh, cudaStream_t st, const float* action,
+                        float* obs, float* reward, float* done, float* cost, float* qacc, int32_t* aux) {
+  const float2* a2 = reinterpret_cast<const float2*>(action);
+#define GX_ST(EX, ST) gx_step_kernel<NH_CT, EX, ST><<<grid, block, sh, st>>>(e->p, e->s, a2, obs, reward, done, cost, qacc, aux, e->stats)
+  if (aux) { if (e->stats_on) GX_ST(true, true); else GX_ST(true, false); }
+  else { if (e->stats_on) GX_ST(false, true); else GX_ST(false, false); }
+#undef GX_ST
+}
+
+GX_API int gx_step(gx_env* e, const float* action, float* obs, float* reward, float* done, float* cost,
+                   float* qacc, int32_t* aux, void* stream) {
+  if (!e || !action || !obs || !reward || !done || !cost) return gx_fail(GX_EINVAL, "gx_step: NULL argument");
+  if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_step: call gx_reset first");
+  if (reinterpret_cast<uintptr_t>(action) & 7u) return gx_fail(GX_EINVAL, "gx_step: action must be 8-byte aligned");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int block = pick_block(e), grid = div_up(e->p.n, block);
+  const size_t sh = tile_bytes(e, block);
+  if (fast_path(e)) launch_step<8>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux);
+  else launch_step<0>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux);
+  GX_LAUNCH_CHECK("gx_step_kernel");
+  e->t_global += 1;
+  return GX_OK;
+}
+
+GX_API int gx_reset_done(gx_env* e, const float* obs_in, float* obs_out, const float* layout, void* stream) {
+  if (!e || !obs_in || !obs_out) return gx_fail(GX_EINVAL, "gx_reset_done: NULL argument");
+  if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_reset_done: call gx_reset first");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int block = pick_block(e), grid = div_up(e->p.n, block);
+  const size_t sh = tile_bytes(e, block);
+  if (fast_path(e))
+    gx_reset_done_kernel<8><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs_in, obs_out);
+  else
+    gx_reset_done_kernel<0><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs_in, obs_out);
+  GX_LAUNCH_CHECK("gx_reset_done_kernel");
+  return GX_OK;
+}
+
+GX_API int gx_get_state(gx_env* e, float* state, void* stream) {
+  if (!e || !state) return gx_fail(GX_EINVAL, "gx_get_state: NULL argument");
+  DeviceGuard guard(e->device);
+  gx_get_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
+  GX_LAUNCH_CHECK("gx_get_state_kernel");
+  return GX_OK;
+}
+
+GX_API int gx_set_state(gx_env* e, const float* state, void* stream) {
+  if (!e || !state) return gx_fail(GX_EINVAL, "gx_set_state: NULL argument");
+  DeviceGuard guard(e->device);
+  gx_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
+  GX_LAUNCH_CHECK("gx_set_state_kernel");
+  e->have_reset = true;
+  return GX_OK;
+}
+
+GX_API int gx_pool_read(gx_env* e, float* pool, int32_t* tries, void* stream) {
+  if (!e) return gx_fail(GX_EINVAL, "gx_pool_read: NULL env");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pool) GX_CUDA(cudaMemcpyAsync(pool, e->pool, sizeof(float) * (size_t)e->p.pool_size * e->p.lay_dim, cudaMemcpyDeviceToDevice, st));
+  if (tries) GX_CUDA(cudaMemcpyAsync(tries, e->pool_tries, sizeof(int32_t) * (size_t)e->p.pool_size, cudaMemcpyDeviceToDevice, st));
+  return GX_OK;
+}
+
+GX_API int gx_rollout(gx_env* e, int32_t T, float* obs, float* act, float* reward, float* cost, float* done,
+                      void* stream) {
+  if (!e || T < 0) return gx_fail(GX_EINVAL, "gx_rollout: bad argument");
+  if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_rollout: call gx_reset first");
+  if (T == 0) return GX_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int block = pick_block(e), grid = div_up(e->p.n, block);
+  const size_t sh = tile_bytes(e, block);
+  float2* a2 = reinterpret_cast<float2*>(act);
+#define GX_RO(NH, ST) gx_rollout_kernel<NH, ST><<<grid, block, sh, st>>>(e->p, e->s, e->pool, T, e->t_global, obs, a2, reward, cost, done, e->stats)
+  if (fast_path(e)) { if (e->stats_on) GX_RO(8, true); else GX_RO(8, false); }
+  else { if (e->stats_on) GX_RO(0, true); else GX_RO(0, false); }
+#undef GX_RO
+  GX_LAUNCH_CHECK("gx_rollout_kernel");
+  e->t_global += (uint64_t)T;
+  return GX_OK;
+}
+
+GX_API int gx_stats_read(gx_env* e, double* out8, void* stream) {
+  if (!e || !out8) return gx_fail(GX_EINVAL, "gx_stats_read: NULL argument");
+  DeviceGuard guard(e->device);
+  GX_CUDA(cudaMemcpyAsync(out8, e->stats, sizeof(double) * 8, cudaMemcpyDefault, (cudaStream_t)stream));
+  return GX_OK;
+}
+
+GX_API int gx_stats_reset(gx_env* e, void* stream) {
+  if (!e) return gx_fail(GX_EINVAL, "gx_stats_reset: NULL env");
+  DeviceGuard guard(e->device);
+  e->stats_on = true;  // the first reset switches accumulation on
+  GX_CUDA(cudaMemsetAsync(e->stats, 0, sizeof(double) * 8, (cudaStream_t)stream));
+  return GX_OK;
+}
+
+GX_API int gx_step_host(gx_env* e, const float* h_action, float* h_obs, float* h_reward, float* h_done,
+                        float* h_cost, int32_t auto_reset_done, void* stream) {
+  if (!e || !h_action || !h_obs || !h_reward || !h_done || !h_cost) return gx_fail(GX_EINVAL, "gx_step_host: NULL argument");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)e->p.n, od = (size_t)e->p.obs_dim;
+  // stage = [obs n*od | reward n | done n | cost n | pad | action 2n]
+  const size_t act_off = ((od + 3) * n + 3) & ~(size_t)3;
+  if (!e->stage) GX_CUDA(cudaMalloc((void**)&e->stage, sizeof(float) * (act_off + 2 * n)));
+  float* d_obs = e->stage;
+  float* d_reward = d_obs + od * n;
+  float* d_done = d_reward + n;
+  float* d_cost = d_done + n;
+  float* d_act = e->stage + act_off;
+  GX_CUDA(cudaMemcpyAsync(d_act, h_action, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, st));
+  if (int rc = gx_step(e, d_act, d_obs, d_reward, d_done, d_cost, nullptr, nullptr, stream)) return rc;
+  if (auto_reset_done)
+    if (int rc = gx_reset_done(e, d_obs, d_obs, nullptr, stream)) return rc;
+  if (h_reward == h_obs + od * n && h_done == h_reward + n && h_cost == h_done + n) {
+    GX_CUDA(cudaMemcpyAsync(h_obs, d_obs, sizeof(float) * (od + 3) * n, cudaMemcpyDeviceToHost, st));
+  } else {
+    GX_CUDA(cudaMemcpyAsync(h_obs, d_obs, sizeof(float) * od * n, cudaMemcpyDeviceToHost, st));
+    GX_CUDA(cudaMemcpyAsync(h_reward, d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    GX_CUDA(cudaMemcpyAsync(h_done, d_done, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    GX_CUDA(cudaMemcpyAsync(h_cost, d_cost, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  }
+  GX_CUDA(cudaStreamSynchronize(st));
+  return GX_OK;
+}
