@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched Goal_Point_8Hazards step on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: one fused
+step + auto-reset launch (gx_step_autoreset) for all envs of the batch with
+random actions already resident in HBM.  Workload (BASELINE.json configs[1]):
+Goal_Point_8Hazards, 4096 envs per GPU, random actions U(-1,1).
+
+One JSON line on stdout (rank 0).  Keys beyond the driver's contract:
+  roofline      dominant kernel (gx_step_kernel) vs the measured HBM peak,
+                348 algorithmic bytes per env-step
+  cpu_baseline  the CPU oracle (C restatement of the reference, OpenMP) timed on
+                this box's host cores on a bounded sample of the same workload
+  e2e           the same metric through Engine.step_host: pinned HOST action in,
+                obs/reward/done/cost out to pinned HOST memory, every step
+  rollout       the fused multi-step kernel (gx_rollout): T steps per launch,
+                state in registers, vs its own 192-byte I/O-only roofline
+  sweep         (N=1 only) step-kernel GB/s at larger batches, to show where the
+                kernel sits against the roofline once launch latency is amortised
+
+L2 policy: every timed step touches a batch whose state, actions and output
+buffers have not been touched for R-1 steps, where R batches x ~1.3 MB exceed the
+126 MB L2 (config.l2 says so); the L2-resident number is reported beside it.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+ALG_BYTES_STEP = 348      # single-step API contract
+ALG_BYTES_ROLLOUT = 192   # multi-step kernel, I/O only
+L2_BYTES = 126e6
+TASK = "Goal_Point_8Hazards"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------- clocks
+class ClockSampler:
+    """SM clock + throttle reasons sampled with NVML while the timed regions run."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.25)   # nvidia-smi -lms 200 cadence: NVML queries take a driver lock
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def workload_config(n, world, how):
+    return {"workload": f"{TASK}, {n} envs per GPU, random-action rollout (a ~ U(-1,1), pre-generated), "
+                        "step + reset_done every step",
+            "envs_per_gpu": n, "total_envs": n * world, "how": how,
+            "parallelism": f"dp{world} (independent env shards, no data-path collective)"}
+
+
+# ------------------------------------------------------------ reference arm
+def oracle_steps_per_sec(n_envs, steps, warmup, threads):
+    """Times gxo_step + gxo_reset_done on preallocated host buffers."""
+    import numpy as np
+    from oracle.oracle import OracleEngine
+    o = OracleEngine({'env_num': n_envs, 'num_steps': 1000, '_seed': 0}, threads=threads)
+    o.reset()
+    L, h = o.L, o.h
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, (64, n_envs, 2)).astype(np.float32)
+    obs = np.empty((n_envs, o.obs_dim), np.float32)
+    rdc = np.empty((3, n_envs), np.float32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    po, pr, pd, pc = p(obs), p(rdc[0]), p(rdc[1]), p(rdc[2])
+    pa = [p(acts[i]) for i in range(64)]
+
+    def run(k):
+        for t in range(k):
+            L.gxo_step(h, pa[t & 63], po, pr, pd, pc, None, None)
+            L.gxo_reset_done(h, po, po, None)
+
+    run(warmup)
+    t0 = time.perf_counter()
+    run(steps)
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from oracle.oracle import lib
+    threads = min(lib().gxo_max_threads(), os.cpu_count() or 1)
+    n = ENVS_PER_GPU * world
+    rate, dt = oracle_steps_per_sec(n, args.steps, max(args.warmup, 3), threads)
+    sample = f"{args.steps} steps x {n} envs, gxo_step + gxo_reset_done, actions pre-generated in host memory"
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(ENVS_PER_GPU, world, "CPU oracle: gxo_step + gxo_reset_done per step, all host threads"),
+        "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                         "sample": sample,
+                         "note": "CPU oracle (C restatement of the reference step, OpenMP); the reference itself "
+                                 "is Python on jax+mujoco, neither installable here"},
+        "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+class Batch:
+    """One 4096-env batch with its own actions and output buffers (all in HBM)."""
+
+    def __init__(self, Engine, torch, n, offset, seed, n_act, pool_size):
+        self.env = Engine({'env_num': n, 'num_steps': 1000, '_seed': seed}, env_id_offset=offset,
+                          pool_size=pool_size)
+        self.env.reset()
+        g = torch.Generator(device='cuda').manual_seed(1234 + offset)
+        self.act = torch.rand(n_act, n, 2, device='cuda', generator=g) * 2 - 1
+        od = self.env.obs_flat_size
+        self.out = torch.empty(n * (od + 3), device='cuda')
+        base = self.out.data_ptr()
+        self.p_obs = C.c_void_p(base)
+        self.p_r = C.c_void_p(base + 4 * n * od)
+        self.p_d = C.c_void_p(base + 4 * n * (od + 1))
+        self.p_c = C.c_void_p(base + 4 * n * (od + 2))
+        self.p_act = [C.c_void_p(self.act[i].data_ptr()) for i in range(n_act)]
+        self.h = self.env._h
+
+
+def time_steps(torch, lib, batches, steps, stream, barrier=None):
+    """K fused step launches, round-robin over the batches; CUDA events on the
+    launching stream, synchronise on both sides."""
+    R = len(batches)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sp = C.c_void_p(stream.cuda_stream)
+    fn = lib.gx_step_autoreset
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for t in range(steps):
+        b = batches[t % R]
+        rc = fn(b.h, b.p_act[(t // R) % len(b.p_act)], b.p_obs, b.p_r, b.p_d, b.p_c, sp)
+        if rc:
+            raise RuntimeError(lib.gx_last_error().decode())
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    if barrier:
+        barrier()
+    return ev0.elapsed_time(ev1) * 1e-3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="guardx", choices=["guardx", "reference"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--no-sweep", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    from guardx_b200 import _abi
+    from guardx_b200.engine import Engine
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    barrier = (lambda: dist.barrier()) if dist else None
+    lib = _abi.load_library()
+    hbm_peak, peak_src = peaks()
+    n = args.envs
+    warmup = max(args.warmup, 3)
+    K = args.steps
+    stream = torch.cuda.current_stream()
+
+    # ---- batches: R independent n-env batches, working set > L2 -------------
+    od = 43
+    per_batch = n * (116 + 4 * (od + 3)) + 8 * n * 8   # state + outputs + 8 action slices
+    R = int(L2_BYTES * 2.0 / per_batch) + 1
+    R = max(2, min(R, 512))
+    pool_size = 16384
+    batches = [Batch(Engine, torch, n, rank * n, seed=k, n_act=8, pool_size=pool_size) for k in range(R)]
+    for b in batches:
+        b.env.stats_reset()   # in-kernel episode statistics on (what ppo_train.py:370-376 does on the host)
+    working_set = R * per_batch
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- value: cold-L2 round-robin --------------------------------------
+    time_steps(torch, lib, batches, warmup, stream)
+    dt = time_steps(torch, lib, batches, K, stream, barrier)
+    # per-epoch statistics all-reduce (replaces mpi_statistics_scalar), inside the job but not the hot loop
+    stats = torch.stack([b.env.stats() for b in batches]).sum(0)
+    if dist:
+        dist.all_reduce(stats)
+        t = torch.tensor([dt], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    value = world * n * K / dt
+    # ---- same loop, one batch only (L2-resident state) --------------------
+    time_steps(torch, lib, batches[:1], warmup, stream)
+    dt_hot = time_steps(torch, lib, batches[:1], K, stream, barrier)
+
+    # ---- e2e: host buffers through Engine.step_host -----------------------
+    h_act = torch.empty(8, n, 2).uniform_(-1, 1).pin_memory()
+    h_out = torch.empty(n * (od + 3)).pin_memory()
+    Ke = max(50, min(K, 1000))
+
+    def e2e_loop(k):
+        for t in range(k):
+            batches[t % R].env.step_host(h_act[t & 7], h_out, auto_reset_done=True)
+        return float(h_out[-1])  # the step's result is read on the host
+
+    e2e_loop(max(3, warmup // 10))
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_loop(Ke)
+    dt_e2e = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([dt_e2e], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_e2e = float(t.item())
+    e2e_value = world * n * Ke / dt_e2e
+
+    # ---- fused rollout kernel ----------------------------------------------
+    T = 256
+    ro_obs = torch.empty(T, n, od, device='cuda')
+    ro_rcd = torch.empty(3, T, n, device='cuda')
+    ro_act = torch.empty(T, n, 2, device='cuda')
+    env0 = batches[0].env
+    pr = lambda t_: C.c_void_p(t_.data_ptr())
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def rollout_once():
+        rc = lib.gx_rollout(env0._h, T, pr(ro_obs), pr(ro_act), pr(ro_rcd[0]), pr(ro_rcd[1]), pr(ro_rcd[2]), sp)
+        assert rc == 0, lib.gx_last_error()
+
+    for _ in range(3):
+        rollout_once()
+    reps = max(3, min(40, K // T + 1))
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    for _ in range(reps):
+        rollout_once()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dt_ro = ev0.elapsed_time(ev1) * 1e-3
+    if dist:
+        t = torch.tensor([dt_ro], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_ro = float(t.item())
+    ro_value = world * n * T * reps / dt_ro
+    clocks = sampler.stop()
+
+    # the dominant kernel's average duration over the timed region (one launch per step)
+    step_us = 1e6 * dt / K
+    achieved = n * ALG_BYTES_STEP / (step_us * 1e-6) / 1e9
+
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        sweep = []
+        for big in (65536, 1 << 20):
+            per = big * (116 + 4 * (od + 3)) + 8 * big * 2
+            Rb = max(2, int(L2_BYTES * 2.0 / per) + 1)
+            bl = [Batch(Engine, torch, big, 0, seed=100 + k, n_act=2, pool_size=pool_size) for k in range(Rb)]
+            time_steps(torch, lib, bl, 5 * Rb, stream)
+            kk = 30 * Rb
+            d = time_steps(torch, lib, bl, kk, stream)
+            gbs = big * ALG_BYTES_STEP * kk / d / 1e9
+            sweep.append({"envs": big, "batches": Rb, "us_per_step": 1e6 * d / kk,
+                          "env_steps_per_s": big * kk / d, "achieved_gbs": gbs, "frac": gbs / hbm_peak})
+            del bl
+            torch.cuda.empty_cache()
+
+    cpu_base = None
+    if rank == 0 and world == 1:
+        from oracle.oracle import lib as olib
+        threads = min(olib().gxo_max_threads(), os.cpu_count() or 1)
+        rate, _ = oracle_steps_per_sec(n, 400, 20, threads)          # calibrate
+        ks = int(max(400, min(12.0 * rate / n, 200000)))             # ~12 s of CPU work
+        rate, d_cpu = oracle_steps_per_sec(n, ks, 20, threads)
+        rate1, d1 = oracle_steps_per_sec(n, max(100, ks // (4 * threads)), 5, 1)
+        cpu_base = {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                    "sample": f"{ks} steps x {n} envs ({d_cpu:.1f} s), gxo_step + gxo_reset_done, host-resident actions",
+                    "single_thread": rate1}
+
+    if rank == 0:
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+            "steps": K, "warmup": warmup, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(n, world, "CUDA: fused step + auto-reset (gx_step_autoreset), one launch "
+                                                     "per step, in-kernel episode statistics"),
+                           l2=f"cold: {R} independent {n}-env batches stepped round-robin, working set "
+                              f"{working_set / 1e6:.0f} MB > 126 MB L2; value_l2_resident is the single-batch loop"),
+            "value_l2_resident": world * n * K / dt_hot,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4,
+                    "d2h_bytes_per_step": n * (od + 3) * 4, "steps": Ke,
+                    "path": "Engine.step_host -> gx_step_host: pinned host action -> H2D -> fused step+auto-reset "
+                            "-> D2H obs|reward|done|cost -> stream sync, every step"},
+            "gpu_launches": K,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "gx_step_kernel<8,false,true,true>",
+                         "alg_bytes_per_env_step": ALG_BYTES_STEP, "envs_per_launch": n,
+                         "us_per_launch": step_us, "peak_source": peak_src,
+                         "note": "launch-/latency-bound at 4096 envs (1.4 MB per launch); see sweep for larger batches"},
+            "rollout": {"value": ro_value, "unit": "env-steps/s", "steps_per_launch": T, "launches": reps,
+                        "alg_bytes_per_env_step": ALG_BYTES_ROLLOUT,
+                        "achieved_gbs": ro_value / world * ALG_BYTES_ROLLOUT / 1e9,
+                        "frac": ro_value / world * ALG_BYTES_ROLLOUT / 1e9 / hbm_peak},
+            "episode_stats": {"episodes": float(stats[0]), "env_steps": float(stats[7]),
+                              "cost_rate": float(stats[6] / max(1.0, float(stats[7])))},
+        }
+        if sweep is not None:
+            line["sweep"] = sweep
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

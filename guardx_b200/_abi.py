@@ -110,6 +110,7 @@ PROTOTYPES = {
     "gx_reset": (_I, [_P, _P, _P]),
     "gx_reset_with_layout": (_I, [_P, _P, _P, _P]),
     "gx_step": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gx_step_autoreset": (_I, [_P, _P, _P, _P, _P, _P, _P]),
     "gx_aux_dim": (_I, [_P]),
     "gx_reset_done": (_I, [_P, _P, _P, _P, _P]),
     "gx_state_dim": (_I, [_P]),
@@ -120,6 +121,7 @@ PROTOTYPES = {
     "gx_stats_read": (_I, [_P, _P, _P]),
     "gx_stats_reset": (_I, [_P, _P]),
     "gx_step_host": (_I, [_P, _P, _P, _P, _P, _P, C.c_int32, _P]),
+    "gx_debug_math": (_I, [_I, _P, _P, _P, _P, _I, _P]),
 }
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

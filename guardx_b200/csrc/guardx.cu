@@ -236,6 +236,18 @@ __global__ void gx_reset_kernel(const __grid_constant__ gx_params p, const GxSta
   gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
 }
 
+// ---- Engine.reset_done (engine.py:497-505, 702-731) -------------------------
+// Re-place ONE env whose done flag is set.  Lag heading, prev_dist, steps and the
+// done flag itself are deliberately left as they are (the reference returns the
+// un-stepped data and never clears _done).
+template <int NH_CT>
+__device__ __forceinline__ void gx_reset_done_env(const gx_params& p, const GxState& s, int i,
+                                                  const float* lay, GxDyn& d, float& gx_, float& gy_,
+                                                  float4* hz_regs, float* row) {
+  gx_place<NH_CT>(p, s, i, lay, gx_, gy_, hz_regs, d);
+  gx_reset_row<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, row);
+}
+
 // ---- episode statistics (ppo_train.py:370-376, 405-411 on the host) --------
 __device__ __forceinline__ void gx_stats_step(const GxState& s, int i, double* stats, float reward,
                                               float cost, float done) {
@@ -264,8 +276,12 @@ __device__ __forceinline__ void gx_stats_totals(double* stats, float my_cost, in
 // qacc (info['obs']['qacc'], engine.py:763-764) is emitted when the pointer is
 // non-NULL (uniform branch); AUX selects the variant that also writes the integer
 // aux row.
-template <int NH_CT, bool AUX, bool STATS>
+// AUTORESET fuses Engine.reset_done into the same launch: reward/done/cost are
+// the step's, the observation row of a done env is its reset observation (what
+// step() followed by reset_done() returns).
+template <int NH_CT, bool AUX, bool STATS, bool AUTORESET>
 __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxState s,
+                               const float* __restrict__ pool, uint64_t t_next,
                                const float2* __restrict__ action, float* __restrict__ obs,
                                float* __restrict__ reward, float* __restrict__ done,
                                float* __restrict__ cost, float* __restrict__ qacc,
@@ -288,6 +304,10 @@ __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxStat
     int32_t bins[AUX ? 1 + GX_MAX_HAZARDS : 1];
     GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a.x, a.y, row,
                                      qacc ? qa : nullptr, AUX ? bins : nullptr);
+    if (AUTORESET && o.done > 0.0f) {
+      const float* lay = gx_pick_layout(p, pool, nullptr, i, t_next, GX_STREAM_PICK);
+      gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
+    }
     gx_store_dyn(s, i, d);
     reward[i] = o.reward;
     done[i] = o.done;
@@ -304,18 +324,6 @@ __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxStat
   const int rows = min(32, p.n - wbase);
   gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
   if (STATS) gx_stats_totals(stats, my_cost, rows, lane);
-}
-
-// ---- Engine.reset_done (engine.py:497-505, 702-731) -------------------------
-// Re-place ONE env whose done flag is set.  Lag heading, prev_dist, steps and the
-// done flag itself are deliberately left as they are (the reference returns the
-// un-stepped data and never clears _done).
-template <int NH_CT>
-__device__ __forceinline__ void gx_reset_done_env(const gx_params& p, const GxState& s, int i,
-                                                  const float* lay, GxDyn& d, float& gx_, float& gy_,
-                                                  float4* hz_regs, float* row) {
-  gx_place<NH_CT>(p, s, i, lay, gx_, gy_, hz_regs, d);
-  gx_reset_row<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, row);
 }
 
 template <int NH_CT>
@@ -611,28 +619,41 @@ GX_API int gx_reset_with_layout(gx_env* e, const float* layout, float* obs, void
 
 template <int NH_CT>
 static void launch_step(gx_env* e, int grid, int block, size_t sh, cudaStream_t st, const float* action,
-                        float* obs, float* reward, float* done, float* cost, float* qacc, int32_t* aux) {
+                        float* obs, float* reward, float* done, float* cost, float* qacc, int32_t* aux,
+                        bool autoreset) {
   const float2* a2 = reinterpret_cast<const float2*>(action);
-#define GX_ST(EX, ST) gx_step_kernel<NH_CT, EX, ST><<<grid, block, sh, st>>>(e->p, e->s, a2, obs, reward, done, cost, qacc, aux, e->stats)
-  if (aux) { if (e->stats_on) GX_ST(true, true); else GX_ST(true, false); }
-  else { if (e->stats_on) GX_ST(false, true); else GX_ST(false, false); }
+#define GX_ST(AX, ST, AR) gx_step_kernel<NH_CT, AX, ST, AR><<<grid, block, sh, st>>>(e->p, e->s, e->pool, e->t_global + 1, a2, obs, reward, done, cost, qacc, aux, e->stats)
+#define GX_ST2(AX, ST) do { if (autoreset) GX_ST(AX, ST, true); else GX_ST(AX, ST, false); } while (0)
+  if (aux) { if (e->stats_on) GX_ST2(true, true); else GX_ST2(true, false); }
+  else { if (e->stats_on) GX_ST2(false, true); else GX_ST2(false, false); }
+#undef GX_ST2
 #undef GX_ST
 }
 
-GX_API int gx_step(gx_env* e, const float* action, float* obs, float* reward, float* done, float* cost,
-                   float* qacc, int32_t* aux, void* stream) {
-  if (!e || !action || !obs || !reward || !done || !cost) return gx_fail(GX_EINVAL, "gx_step: NULL argument");
-  if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_step: call gx_reset first");
-  if (reinterpret_cast<uintptr_t>(action) & 7u) return gx_fail(GX_EINVAL, "gx_step: action must be 8-byte aligned");
+static int gx_step_impl(gx_env* e, const float* action, float* obs, float* reward, float* done, float* cost,
+                        float* qacc, int32_t* aux, void* stream, bool autoreset, const char* who) {
+  if (!e || !action || !obs || !reward || !done || !cost) return gx_fail(GX_EINVAL, "%s: NULL argument", who);
+  if (!e->have_reset) return gx_fail(GX_ESTATE, "%s: call gx_reset first", who);
+  if (reinterpret_cast<uintptr_t>(action) & 7u) return gx_fail(GX_EINVAL, "%s: action must be 8-byte aligned", who);
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
-  if (fast_path(e)) launch_step<8>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux);
-  else launch_step<0>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux);
+  if (fast_path(e)) launch_step<8>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset);
+  else launch_step<0>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset);
   GX_LAUNCH_CHECK("gx_step_kernel");
   e->t_global += 1;
   return GX_OK;
+}
+
+GX_API int gx_step(gx_env* e, const float* action, float* obs, float* reward, float* done, float* cost,
+                   float* qacc, int32_t* aux, void* stream) {
+  return gx_step_impl(e, action, obs, reward, done, cost, qacc, aux, stream, false, "gx_step");
+}
+
+GX_API int gx_step_autoreset(gx_env* e, const float* action, float* obs, float* reward, float* done,
+                             float* cost, void* stream) {
+  return gx_step_impl(e, action, obs, reward, done, cost, nullptr, nullptr, stream, true, "gx_step_autoreset");
 }
 
 GX_API int gx_reset_done(gx_env* e, const float* obs_in, float* obs_out, const float* layout, void* stream) {
@@ -725,9 +746,9 @@ GX_API int gx_step_host(gx_env* e, const float* h_action, float* h_obs, float* h
   float* d_cost = d_done + n;
   float* d_act = e->stage + act_off;
   GX_CUDA(cudaMemcpyAsync(d_act, h_action, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, st));
-  if (int rc = gx_step(e, d_act, d_obs, d_reward, d_done, d_cost, nullptr, nullptr, stream)) return rc;
-  if (auto_reset_done)
-    if (int rc = gx_reset_done(e, d_obs, d_obs, nullptr, stream)) return rc;
+  if (int rc = gx_step_impl(e, d_act, d_obs, d_reward, d_done, d_cost, nullptr, nullptr, stream,
+                            auto_reset_done != 0, "gx_step_host"))
+    return rc;
   if (h_reward == h_obs + od * n && h_done == h_reward + n && h_cost == h_done + n) {
     GX_CUDA(cudaMemcpyAsync(h_obs, d_obs, sizeof(float) * (od + 3) * n, cudaMemcpyDeviceToHost, st));
   } else {
@@ -737,5 +758,29 @@ GX_API int gx_step_host(gx_env* e, const float* h_action, float* h_obs, float* h
     GX_CUDA(cudaMemcpyAsync(h_cost, d_cost, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
   }
   GX_CUDA(cudaStreamSynchronize(st));
+  return GX_OK;
+}
+
+// ---- diagnostics -------------------------------------------------------------
+__global__ void gx_debug_math_kernel(int fn, const float* a, const float* b, float* out, float* out2, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (fn == 0) {
+    float s, c;
+    gx_sincos(a[i], &s, &c);
+    out[i] = s;
+    if (out2) out2[i] = c;
+  } else if (fn == 1) {
+    out[i] = gx_atan2(a[i], b[i]);
+  } else {
+    out[i] = gx_exp(a[i]);
+  }
+}
+
+GX_API int gx_debug_math(int fn, const float* a, const float* b, float* out, float* out2, int n, void* stream) {
+  if (!a || !out || n < 0 || fn < 0 || fn > 2 || (fn == 1 && !b)) return gx_fail(GX_EINVAL, "gx_debug_math: bad argument");
+  if (n == 0) return GX_OK;
+  gx_debug_math_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(fn, a, b, out, out2, n);
+  GX_LAUNCH_CHECK("gx_debug_math_kernel");
   return GX_OK;
 }

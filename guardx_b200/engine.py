@@ -234,6 +234,22 @@ class Engine:
         self._obs, self._reward, self._done, self._info = obs, reward, done, info
         return obs, reward, done, info
 
+    def step_autoreset(self, action):
+        ''' step() and reset_done() fused into one kernel launch: returns
+        (obs after re-placing finished envs, reward, done, info) -- the same
+        tensors `step(a)` followed by `reset_done()` would hand the caller. '''
+        action = self._as_input(action, (self.env_num, self.act_dim))
+        n = self.env_num
+        obs = self._empty(n, self.obs_flat_size)
+        rdc = self._empty(3, n)
+        L = self._lib
+        _abi.check(L, L.gx_step_autoreset(self._h, self._ptr(action), self._ptr(obs), self._ptr(rdc[0]),
+                                          self._ptr(rdc[1]), self._ptr(rdc[2]), self._stream()),
+                   "gx_step_autoreset")
+        info = {'cost': rdc[2]}
+        self._obs, self._reward, self._done, self._info = obs, rdc[0], rdc[1], info
+        return obs, rdc[0], rdc[1], info
+
     def reset_done(self, layout=None):
         ''' Re-place the envs whose last `done` was 1 and return the full
         observation batch with their rows replaced (engine.py:497-505). '''

@@ -168,6 +168,14 @@ int gx_reset_with_layout(gx_env* env, const float* layout, float* obs, void* str
 int gx_step(gx_env* env, const float* action, float* obs, float* reward, float* done,
             float* cost, float* qacc, int32_t* aux, void* stream);
 
+/* Fused gx_step + in-place gx_reset_done in ONE launch ("termination plus
+ * auto-reset", BASELINE.json): reward/done/cost are the step's; the obs row of
+ * an env that finished is its reset observation -- bit-identical to calling
+ * gx_step and then gx_reset_done(obs, obs, NULL).  The reference needs two jitted
+ * calls and a full extra physics step for this (engine.py:497-505, 719-724). */
+int gx_step_autoreset(gx_env* env, const float* action, float* obs, float* reward, float* done,
+                      float* cost, void* stream);
+
 int gx_aux_dim(const gx_env* env); /* 3 + hazards_num */
 enum {
   GX_AUX_GUARD = 1,   /* NaN/Inf in obs -> reward 0, done 1 (engine.py:696-699) */
@@ -215,6 +223,8 @@ int gx_rollout(gx_env* env, int32_t T, float* obs, float* act, float* reward, fl
  *      host-side accumulation of ppo_train.py:370-376 and feeds the NCCL
  *      all-reduce that replaces mpi_statistics_scalar (mpi_tools.py:70-92). */
 int gx_stats_read(gx_env* env, double* out8, void* stream);
+/* zeroes the sums and (first call) switches accumulation on; until then
+ * gx_step / gx_rollout do not touch the statistics buffers at all */
 int gx_stats_reset(gx_env* env, void* stream);
 
 /* ---- host-buffer convenience (the end-to-end path of bench.py): H2D of the
@@ -222,6 +232,13 @@ int gx_stats_reset(gx_env* env, void* stream);
  *      stream synchronise.  Host pointers should be pinned. ----------------- */
 int gx_step_host(gx_env* env, const float* h_action, float* h_obs, float* h_reward,
                  float* h_done, float* h_cost, int32_t auto_reset_done, void* stream);
+
+/* ---- diagnostics: evaluate the shared fp32 math (csrc/gx_math.h) on the
+ *      device, so tests can prove host/device bit-equality of the header.
+ *      fn: 0 sincos(a)->out,out2   1 atan2(a,b)->out   2 exp(a)->out.
+ *      a, b, out, out2: device arrays of n floats (b/out2 may be NULL). ------ */
+int gx_debug_math(int fn, const float* a, const float* b, float* out, float* out2, int n,
+                  void* stream);
 
 #ifdef __cplusplus
 }

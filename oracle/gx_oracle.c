@@ -358,10 +358,12 @@ static void reset_layout(gxo_env* e) {
 #pragma omp parallel for schedule(dynamic, 64) num_threads(e->threads)
   for (int j = 0; j < e->pool_size; ++j) {
     uint32_t attempt = 0;
-    while (!sample_layout(&e->p, key.v[0], key.v[1], (uint32_t)j, attempt,
+    const uint32_t max_attempts = 1u << 16; /* then give up: tries = -1 (engine.py:444 would assert) */
+    while (attempt < max_attempts &&
+           !sample_layout(&e->p, key.v[0], key.v[1], (uint32_t)j, attempt,
                           e->pool + (size_t)j * e->lay_dim))
       ++attempt;
-    e->pool_tries[j] = (int32_t)(attempt + 1);
+    e->pool_tries[j] = attempt < max_attempts ? (int32_t)(attempt + 1) : -1;
   }
   e->epoch += 1;
 }

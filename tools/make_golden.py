@@ -87,11 +87,11 @@ def gen_obs_cases(Engine, shim, config, n_random, rng, tag):
             haz[rng.integers(nh)] = robot + rng.uniform(-0.2, 0.2, 2)
         if k % 7 == 0:
             goal = robot + rng.uniform(-0.45, 0.45, 2)
-        cases.append((robot, cs, goal, haz))
+        cases.append((robot, cs, goal, haz, th))
     # hand-made edges
     one = (np.float32(1.0), np.float32(0.0))
     hz0 = np.tile(np.array([[5.0, 5.0]]), (nh, 1))
-    edge = lambda gx, gy: ((0.0, 0.0), one, (gx, gy), hz0.copy())
+    edge = lambda gx, gy: ((0.0, 0.0), one, (gx, gy), hz0.copy(), 0.0)
     cases += [
         edge(1.0, -1e-8),        # tiny negative angle: angle % 2pi == 2pi in fp32 -> bin == nbins
         edge(1.0, -1e-7),
@@ -106,12 +106,12 @@ def gen_obs_cases(Engine, shim, config, n_random, rng, tag):
     hz_edge = hz0.copy(); hz_edge[0] = [0.3, 0.0]   # dist == hazards_size exactly
     if nh > 1:
         hz_edge[1] = [0.0, 0.1]
-    cases.append(((0.0, 0.0), one, (3.0, 0.0), hz_edge))
+    cases.append(((0.0, 0.0), one, (3.0, 0.0), hz_edge, 0.0))
     out = {k: [] for k in ('robot', 'cs', 'goal', 'hazards', 'qpos', 'qvel', 'ctrl', 'qacc', 'flat', 'cost',
                            'last_robot', 'last_goal', 'last_done', 'reward', 'done', 'reward_nolast',
                            'done_nolast', 'goal_bin_lidar', 'compass')}
-    for robot, cs, goal, haz in cases:
-        qpos = np.r_[robot, rng.uniform(-20, 20)]
+    for robot, cs, goal, haz, th in cases:
+        qpos = np.r_[robot, th]   # self-consistent pose: cs = (cos, sin)(qpos[2])
         qvel = rng.uniform(-3, 3, 3)
         ctrl = rng.normal(size=3)
         qacc = rng.normal(size=3)
