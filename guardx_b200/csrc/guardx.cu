@@ -13,6 +13,7 @@
 
 #include "../../include/guardx.h"
 #include "gx_device.cuh"
+#include "gx_lanes.cuh"
 
 #define GX_API extern "C" __attribute__((visibility("default")))
 
@@ -67,6 +68,7 @@ struct gx_env {
   uint64_t t_global;    // step() calls so far
   bool have_reset;
   bool stats_on;
+  int lanes_max_envs;   // use the 16-lanes-per-env kernels up to this batch size (0 = never)
   // staging for gx_step_host
   float* stage;  // [n*act_dim | n*obs_dim | n | n | n]
 };
@@ -424,6 +426,91 @@ __global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxS
   if (live) gx_store_dyn(s, i, d);
 }
 
+// ---- 16-lanes-per-env variants (small batches; gx_lanes.cuh) ------------------
+template <bool STATS, bool AUTORESET>
+__global__ void __launch_bounds__(128) gx_step_lanes_kernel(
+    const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool, uint64_t t_next,
+    const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
+    float* __restrict__ done, float* __restrict__ cost, float* __restrict__ qacc, double* __restrict__ stats) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & 15;
+  const int env = gtid >> 4;
+  if (((gtid - lane) >> 4) >= p.n) return;  // whole warp past the end
+  const bool live = env < p.n;
+  const int i = live ? env : p.n - 1;
+  const unsigned gmask = gx_grp_mask();
+  GxDyn d;
+  gx_load_dyn(s, i, d);
+  const float2 g = s.goal[i];
+  float gx_ = g.x, gy_ = g.y, ox, oy;
+  gx_load_object(s, i, sub, gx_, gy_, ox, oy);
+  const float2 a = action[i];
+  float qa[3];
+  GxLaneStep r = gx_step_lanes(p, sub, gmask, d, gx_, gy_, ox, oy, a.x, a.y, qacc ? qa : nullptr);
+  if (AUTORESET && r.out.done > 0.0f) {
+    const float* lay = gx_pick_layout(p, pool, nullptr, i, t_next, GX_STREAM_PICK);
+    gx_reset_done_lanes(p, s, i, sub, gmask, live, lay, d, gx_, gy_, ox, oy, r.obs);
+    r.c0 = 0.0f; r.c1 = 0.0f; r.c2 = 0.0f;
+  }
+  if (live) {
+    gx_store_row_lanes(obs + (size_t)i * 43, sub, r.obs, r.c0, r.c1, r.c2, d);
+    gx_store_dyn_lanes(s, i, sub, d);
+    if (sub == 3) reward[i] = r.out.reward;
+    if (sub == 4) done[i] = r.out.done;
+    if (sub == 5) cost[i] = r.out.cost;
+    if (qacc && sub >= 6 && sub <= 8) qacc[3 * (size_t)i + (sub - 6)] = qa[sub - 6];
+    if (STATS && sub == 9) gx_stats_step(s, i, stats, r.out.reward, r.out.cost, r.out.done);
+  }
+  if (STATS) {
+    const int rows = min(2, p.n - ((gtid - lane) >> 4));
+    gx_stats_totals(stats, (live && sub == 0) ? r.out.cost : 0.0f, rows, lane);
+  }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(128) gx_rollout_lanes_kernel(
+    const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool, int T, uint64_t t0,
+    float* __restrict__ obs, float2* __restrict__ act, float* __restrict__ reward, float* __restrict__ cost,
+    float* __restrict__ done, double* __restrict__ stats) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, sub = threadIdx.x & 15;
+  const int env = gtid >> 4;
+  if (((gtid - lane) >> 4) >= p.n) return;
+  const bool live = env < p.n;
+  const int i = live ? env : p.n - 1;
+  const unsigned gmask = gx_grp_mask();
+  GxDyn d;
+  gx_load_dyn(s, i, d);
+  const float2 g = s.goal[i];
+  float gx_ = g.x, gy_ = g.y, ox, oy;
+  gx_load_object(s, i, sub, gx_, gy_, ox, oy);
+  const uint64_t gid = p.env_id_offset + (uint64_t)i;
+  const size_t n = (size_t)p.n;
+  const int rows = min(2, p.n - ((gtid - lane) >> 4));
+  for (int t = 0; t < T; ++t) {
+    const uint64_t tg = t0 + (uint64_t)t;
+    gx_u32x4 u = gx_philox4x32_10((uint32_t)gid, (uint32_t)tg, (uint32_t)(tg >> 32), GX_STREAM_ACTION, p.seed_lo, p.seed_hi);
+    const float a0 = gx_uniform(u.v[0], -1.0f, 1.0f), a1 = gx_uniform(u.v[1], -1.0f, 1.0f);
+    GxLaneStep r = gx_step_lanes(p, sub, gmask, d, gx_, gy_, ox, oy, a0, a1, nullptr);
+    if (STATS && live && sub == 9) gx_stats_step(s, i, stats, r.out.reward, r.out.cost, r.out.done);
+    if (r.out.done > 0.0f) {
+      const float* lay = gx_pick_layout(p, pool, nullptr, i, tg + 1, GX_STREAM_PICK);
+      gx_reset_done_lanes(p, s, i, sub, gmask, live, lay, d, gx_, gy_, ox, oy, r.obs);
+      r.c0 = 0.0f; r.c1 = 0.0f; r.c2 = 0.0f;
+    }
+    if (live) {
+      const size_t k = (size_t)t * n + (size_t)i;
+      if (obs) gx_store_row_lanes(obs + k * 43, sub, r.obs, r.c0, r.c1, r.c2, d);
+      if (act && sub == 2) act[k] = make_float2(a0, a1);
+      if (reward && sub == 3) reward[k] = r.out.reward;
+      if (done && sub == 4) done[k] = r.out.done;
+      if (cost && sub == 5) cost[k] = r.out.cost;
+    }
+    if (STATS) gx_stats_totals(stats, (live && sub == 0) ? r.out.cost : 0.0f, rows, lane);
+  }
+  if (live) gx_store_dyn_lanes(s, i, sub, d);
+}
+
 // ---- state injection / checkpoint -------------------------------------------
 __global__ void gx_get_state_kernel(const __grid_constant__ gx_params p, const GxState s, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -470,6 +557,16 @@ GX_API void gx_default_config(gx_config* cfg) {
   if (cfg) gx_fill_default_config(cfg);
 }
 
+// 16 lanes per env pay off while the batch cannot fill the machine with one
+// thread per env; beyond that the one-thread kernels do less total work.
+static bool lanes_path(const gx_env* e) {
+  const gx_params& p = e->p;
+  return e->lanes_max_envs > 0 && p.n <= e->lanes_max_envs && p.nh == 8 && p.nb == 16 && p.obs_dim == 43 &&
+         p.alias && p.use_exp && p.ctrllimited && p.forcelimited && p.substeps == 1 &&
+         p.off_ctrl == 0 && p.off_compass == 3 && p.off_glidar == 5 && p.off_hlidar == 21 &&
+         p.off_qpos == 37 && p.off_qvel == 40;
+}
+
 static size_t tile_bytes(const gx_env* e, int block) { return (size_t)block * e->p.obs_dim * sizeof(float); }
 static bool fast_path(const gx_env* e) { return e->p.nh == 8; }
 
@@ -495,6 +592,8 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   e->sm_count = prop.multiProcessorCount;
   e->epoch = 0; e->t_global = 0; e->have_reset = false; e->stats_on = false;
   e->stage = nullptr;
+  e->lanes_max_envs = 16384;
+  if (const char* v = getenv("GX_LANES_MAX_ENVS")) e->lanes_max_envs = atoi(v);
   const int cap = div_up(p.n, 32) * 32;
   GxState& s = e->s;
   memset(&s, 0, sizeof s);
@@ -637,6 +736,17 @@ static int gx_step_impl(gx_env* e, const float* action, float* obs, float* rewar
   if (reinterpret_cast<uintptr_t>(action) & 7u) return gx_fail(GX_EINVAL, "%s: action must be 8-byte aligned", who);
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!aux && lanes_path(e)) {
+    const int block = 128, grid = div_up(e->p.n * GX_LPE, block);
+    const float2* a2 = reinterpret_cast<const float2*>(action);
+#define GX_SL(ST, AR) gx_step_lanes_kernel<ST, AR><<<grid, block, 0, st>>>(e->p, e->s, e->pool, e->t_global + 1, a2, obs, reward, done, cost, qacc, e->stats)
+    if (e->stats_on) { if (autoreset) GX_SL(true, true); else GX_SL(true, false); }
+    else { if (autoreset) GX_SL(false, true); else GX_SL(false, false); }
+#undef GX_SL
+    GX_LAUNCH_CHECK("gx_step_lanes_kernel");
+    e->t_global += 1;
+    return GX_OK;
+  }
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
   if (fast_path(e)) launch_step<8>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset);
@@ -707,6 +817,14 @@ GX_API int gx_rollout(gx_env* e, int32_t T, float* obs, float* act, float* rewar
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
   float2* a2 = reinterpret_cast<float2*>(act);
+  if (lanes_path(e)) {
+    const int lb = 128, lg = div_up(e->p.n * GX_LPE, lb);
+    if (e->stats_on) gx_rollout_lanes_kernel<true><<<lg, lb, 0, st>>>(e->p, e->s, e->pool, T, e->t_global, obs, a2, reward, cost, done, e->stats);
+    else gx_rollout_lanes_kernel<false><<<lg, lb, 0, st>>>(e->p, e->s, e->pool, T, e->t_global, obs, a2, reward, cost, done, e->stats);
+    GX_LAUNCH_CHECK("gx_rollout_lanes_kernel");
+    e->t_global += (uint64_t)T;
+    return GX_OK;
+  }
 #define GX_RO(NH, ST) gx_rollout_kernel<NH, ST><<<grid, block, sh, st>>>(e->p, e->s, e->pool, T, e->t_global, obs, a2, reward, cost, done, e->stats)
   if (fast_path(e)) { if (e->stats_on) GX_RO(8, true); else GX_RO(8, false); }
   else { if (e->stats_on) GX_RO(0, true); else GX_RO(0, false); }

@@ -94,17 +94,23 @@ __device__ __forceinline__ void gx_solve_robot_block(float d0, float d1, float m
   x2 = alpha;
 }
 
+// FAST (template flag used by the hot kernels): the launch code has checked that
+// ctrllimited, forcelimited, lidar_alias and the exponential lidar are all on and
+// physics_steps_per_control_step == 1 (the Goal_Point_8Hazards defaults), so those
+// uniform branches disappear at compile time.
+template <bool FAST>
 __device__ __forceinline__ float gx_actuator(const gx_params& p, int i, float ctrl, float v) {
   float u = ctrl;
-  if (p.ctrllimited) u = gx_clip(u, p.ctrl_lo, p.ctrl_hi);
+  if (FAST || p.ctrllimited) u = gx_clip(u, p.ctrl_lo, p.ctrl_hi);
   float act_vel = p.gear[i] * v;
   float force = p.gain * u + p.bias2 * act_vel;
-  if (p.forcelimited) force = gx_clip(force, p.force_lo, p.force_hi);
+  if (FAST || p.forcelimited) force = gx_clip(force, p.force_lo, p.force_hi);
   return p.gear[i] * force;
 }
 
 // One mjx.step for the Point model.  On return (px,py,r00,r10) is the pose
 // snapshot of the forward pass (PRE-step qpos) and d.q*/d.v* are post-step.
+template <bool FAST = false>
 __device__ __forceinline__ void gx_mjx_step_point(const gx_params& p, GxDyn& d, float c0, float c1,
                                                   float c2, float& px, float& py, float& r00,
                                                   float& r10, float* qacc) {
@@ -114,9 +120,9 @@ __device__ __forceinline__ void gx_mjx_step_point(const gx_params& p, GxDyn& d, 
   float m02 = -(p.mc * r10), m12 = p.mc * r00;
   float w2 = d.vw * d.vw;
   float b0 = -(p.mc * r00) * w2, b1 = -(p.mc * r10) * w2;
-  float f0 = (-(p.damp[0] * d.vx) - b0) + gx_actuator(p, 0, c0, d.vx);
-  float f1 = (-(p.damp[1] * d.vy) - b1) + gx_actuator(p, 1, c1, d.vy);
-  float f2 = (-(p.damp[2] * d.vw) - 0.0f) + gx_actuator(p, 2, c2, d.vw);
+  float f0 = (-(p.damp[0] * d.vx) - b0) + gx_actuator<FAST>(p, 0, c0, d.vx);
+  float f1 = (-(p.damp[1] * d.vy) - b1) + gx_actuator<FAST>(p, 1, c1, d.vy);
+  float f2 = (-(p.damp[2] * d.vw) - 0.0f) + gx_actuator<FAST>(p, 2, c2, d.vw);
   if (qacc) gx_solve_robot_block(p.mass, p.mass, p.inertia, m02, m12, f0, f1, f2, qacc[0], qacc[1], qacc[2]);
   float a0, a1, a2;
   gx_solve_robot_block(p.mh0, p.mh1, p.mh2, m02, m12, f0, f1, f2, a0, a1, a2);
@@ -143,6 +149,7 @@ __device__ __forceinline__ void gx_ego(float ox, float oy, float px, float py, f
   ey = dx * (-r10) + dy * r00;
 }
 
+template <bool FAST = false>
 __device__ __forceinline__ GxRay gx_lidar_ray(const gx_params& p, float ex, float ey) {
   GxRay r;
   float dist = gx_sqrt(ex * ex + ey * ey);
@@ -151,7 +158,7 @@ __device__ __forceinline__ GxRay gx_lidar_ray(const gx_params& p, float ex, floa
   float q = gx_div(angle, p.bin_size);
   r.bin = (q >= 0.0f && q < 1.0e9f) ? (int)q : 0;
   float bin_angle = p.bin_size * (float)r.bin;
-  if (p.use_exp) {
+  if (FAST || p.use_exp) {
     r.sensor = gx_exp(p.neg_exp_gain * dist);
   } else {
     r.sensor = gx_div(gx_max(0.0f, p.lidar_max_dist - dist), p.lidar_max_dist);

@@ -85,14 +85,14 @@ GX_HD int gx_notfinite(float x) { return (gx_f2u(x) & 0x7f800000u) == 0x7f800000
 
 /* jnp.maximum / jnp.minimum semantics: NaN in either operand wins. */
 GX_HD float gx_max(float a, float b) {
-  if (a != a) return a;
-  if (b != b) return b;
-  return a > b ? a : b;
+  float m = a > b ? a : b; /* selects, no branches */
+  m = (b != b) ? b : m;
+  return (a != a) ? a : m;
 }
 GX_HD float gx_min(float a, float b) {
-  if (a != a) return a;
-  if (b != b) return b;
-  return a < b ? a : b;
+  float m = a < b ? a : b;
+  m = (b != b) ? b : m;
+  return (a != a) ? a : m;
 }
 /* jnp.clip semantics (NaN stays NaN). */
 GX_HD float gx_clip(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
@@ -152,11 +152,12 @@ GX_HD float gx_atan2(float y, float x) {
    result scaled in two steps so that denormal results round once-ish and
    identically on both sides. */
 GX_HD float gx_exp(float x) {
-  if (x != x) return x;
-  if (x > 88.7228394f) return gx_u2f(0x7f800000u);
-  if (x < -104.0f) return 0.0f;
-  float k = rintf(x * 1.44269502162933350f);
-  float r = gx_fma(k, -0.693147182464599609f, x);
+  /* branch-free: evaluate on the clamped argument, patch the special cases with
+     selects at the end (NaN falls through every comparison and is restored last) */
+  float xc = x < -104.0f ? -104.0f : x;
+  xc = xc > 88.7228394f ? 88.7228394f : xc;
+  float k = rintf(xc * 1.44269502162933350f);
+  float r = gx_fma(k, -0.693147182464599609f, xc);
   r = gx_fma(k, 1.90465421212593356e-9f, r);
   float p = 1.37805939e-3f;
   p = gx_fma(p, r, 8.37312452e-3f);
@@ -165,11 +166,15 @@ GX_HD float gx_exp(float x) {
   p = gx_fma(p, r, 4.99999851e-1f);
   p = gx_fma(p, r, 1.0f);
   p = gx_fma(p, r, 1.0f);
-  int ki = (int)k; /* |k| <= 151 here */
+  float kk = (k == k) ? k : 0.0f; /* NaN -> 0 before the int conversion */
+  int ki = (int)kk;               /* |k| <= 151 here */
   int k1 = ki / 2, k2 = ki - k1;
   float s1 = gx_u2f((uint32_t)(k1 + 127) << 23);
   float s2 = gx_u2f((uint32_t)(k2 + 127) << 23);
-  return (p * s1) * s2;
+  float res = (p * s1) * s2;
+  res = (x > 88.7228394f) ? gx_u2f(0x7f800000u) : res;
+  res = (x < -104.0f) ? 0.0f : res;
+  return (x != x) ? x : res;
 }
 
 #endif /* GX_MATH_H_ */

@@ -42,12 +42,20 @@ def cpu(t):
     return t.detach().cpu().numpy()
 
 
-@pytest.fixture(scope="module")
-def mods():
+@pytest.fixture(scope="module", params=["lanes16", "thread_per_env"])
+def mods(request):
+    """Every test runs twice: with the 16-lanes-per-env kernels (the default up to
+    16384 envs) and with the one-thread-per-env kernels forced for all sizes."""
     _need_gpu()
     from guardx_b200.engine import Engine
     from oracle.oracle import OracleEngine
-    return Engine, OracleEngine
+    old = os.environ.get("GX_LANES_MAX_ENVS")
+    os.environ["GX_LANES_MAX_ENVS"] = "1048576" if request.param == "lanes16" else "0"
+    yield Engine, OracleEngine
+    if old is None:
+        os.environ.pop("GX_LANES_MAX_ENVS", None)
+    else:
+        os.environ["GX_LANES_MAX_ENVS"] = old
 
 
 def make_pair(mods, cfg, threads=8):
