@@ -116,6 +116,8 @@ PROTOTYPES = {
     "gx_state_dim": (_I, [_P]),
     "gx_get_state": (_I, [_P, _P, _P]),
     "gx_set_state": (_I, [_P, _P, _P]),
+    "gx_set_counters": (_I, [_P, C.c_uint64, C.c_uint64, _P]),
+    "gx_get_counters": (_I, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), _P]),
     "gx_pool_read": (_I, [_P, _P, _P, _P]),
     "gx_rollout": (_I, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "gx_stats_read": (_I, [_P, _P, _P]),

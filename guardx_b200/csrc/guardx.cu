@@ -64,8 +64,11 @@ struct gx_env {
   float* pool;          // [pool_size, lay_dim]
   int32_t* pool_tries;  // [pool_size]
   double* stats;        // [8] device
-  uint64_t epoch;       // pool generations so far
-  uint64_t t_global;    // step() calls so far
+  // Device-resident counters, so that every entry point can be captured in a
+  // CUDA graph and replayed: the step count lives per env in the state (d2.zw,
+  // "age"); ctr[1] = epoch (layout pools generated so far), ctr[3] = the
+  // finished-blocks ticket of the pool kernel.
+  unsigned long long* ctr;
   bool have_reset;
   bool stats_on;
   int lanes_max_envs;   // use the 16-lanes-per-env kernels up to this batch size (0 = never)
@@ -84,6 +87,24 @@ static inline int pick_block(const gx_env* e) {
   else if (n <= e->sm_count * 64 * 8) block = 64;
   while (block > 32 && (size_t)block * e->p.obs_dim * sizeof(float) > 48 * 1024) block >>= 1;
   return block;
+}
+
+// ---------------------------------------------------------------------------
+// The pool epoch lives in device memory and is advanced by the LAST block of the
+// pool kernel to finish (a ticket per block), i.e. after every block has taken
+// its read of the old value.  (The step count is per-env state, gx_device.cuh.)
+// No host-side count is baked into a launch, so a captured CUDA graph replays
+// correctly.
+// ---------------------------------------------------------------------------
+enum { GX_CTR_T = 0, GX_CTR_EPOCH = 1, GX_CTR_TICKET = 3 };
+
+__device__ __forceinline__ void gx_tick(unsigned long long* ctr, int slot, unsigned long long inc) {
+  __syncthreads();  // all reads of ctr[slot] by this block are done
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned last = gridDim.x - 1;
+    if (atomicInc(reinterpret_cast<unsigned*>(ctr + GX_CTR_TICKET), last) == last) ctr[slot] += inc;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -127,12 +148,8 @@ __device__ bool gx_sample_layout(const gx_params& p, uint32_t k0, uint32_t k1, u
   return !(gx_sqrt(dx * dx + dy * dy) < p.min_robot_goal);
 }
 
-__global__ void __launch_bounds__(128) gx_pool_kernel(const __grid_constant__ gx_params p, uint32_t k0,
-                                                      uint32_t k1, float* __restrict__ pool,
-                                                      int32_t* __restrict__ tries) {
-  const int lane = threadIdx.x & 31;
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (slot >= p.pool_size) return;
+__device__ void gx_pool_slot(const gx_params& p, uint32_t k0, uint32_t k1, int slot, int lane,
+                             float* __restrict__ pool, int32_t* __restrict__ tries) {
   float placed[2 + GX_MAX_HAZARDS][2];
   for (uint32_t base = 0; base < GX_MAX_POOL_ATTEMPTS; base += 32) {
     const uint32_t attempt = base + lane;
@@ -154,6 +171,19 @@ __global__ void __launch_bounds__(128) gx_pool_kernel(const __grid_constant__ gx
   // acceptance rate ~0: the configuration cannot be laid out (the reference
   // would fail `assert self.layout_size > self.env_num`, engine.py:444)
   if (lane == 0) tries[slot] = -1;
+}
+
+__global__ void __launch_bounds__(128) gx_pool_kernel(const __grid_constant__ gx_params p,
+                                                      unsigned long long* __restrict__ ctr,
+                                                      float* __restrict__ pool, int32_t* __restrict__ tries) {
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // per-epoch key: one Philox call on (epoch, STREAM_LAYOUT) under the seed
+  const unsigned long long epoch = ctr[GX_CTR_EPOCH];
+  const gx_u32x4 key = gx_philox4x32_10((uint32_t)epoch, (uint32_t)(epoch >> 32), 0u, GX_STREAM_LAYOUT,
+                                        p.seed_lo, p.seed_hi);
+  if (slot < p.pool_size) gx_pool_slot(p, key.v[0], key.v[1], slot, lane, pool, tries);
+  gx_tick(ctr, GX_CTR_EPOCH, 1ull);
 }
 
 // ---------------------------------------------------------------------------
@@ -213,7 +243,7 @@ extern __shared__ __align__(16) float gx_smem[];
 template <int NH_CT>
 __global__ void gx_reset_kernel(const __grid_constant__ gx_params p, const GxState s,
                                 const float* __restrict__ pool, const float* __restrict__ layout,
-                                uint64_t t_global, float* __restrict__ obs) {
+                                float* __restrict__ obs) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int wbase = i - lane;
@@ -221,13 +251,12 @@ __global__ void gx_reset_kernel(const __grid_constant__ gx_params p, const GxSta
   float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
   float* row = tile + lane * p.obs_dim;
   if (i < p.n) {
-    const float* lay = gx_pick_layout(p, pool, layout, i, t_global, GX_STREAM_PICK ^ 1u);
+    GxDyn d;
+    gx_load_dyn(s, i, d);  // reset() leaves Engine._done (engine.py:463) and the key stale
+    const float* lay = gx_pick_layout(p, pool, layout, i, d.age, GX_STREAM_PICK ^ 1u);
     float4 hz_regs[NH_CT ? (NH_CT + 1) / 2 : 1];
     float gx_, gy_;
-    GxDyn d;
     gx_place<NH_CT>(p, s, i, lay, gx_, gy_, hz_regs, d);
-    const float old = s.d2[i].y;  // reset() leaves Engine._done stale (engine.py:463)
-    d.done = (__float_as_uint(old) >> 31) ? 1.0f : 0.0f;
     d.steps = 0.0f;
     d.prev_dist = gx_reset_row<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, row);
     gx_kinematics(d.qth, d.hc, d.hs);  // mjx.forward at the reset pose (engine.py:655): R = I
@@ -283,7 +312,7 @@ __device__ __forceinline__ void gx_stats_totals(double* stats, float my_cost, in
 // step() followed by reset_done() returns).
 template <int NH_CT, bool AUX, bool STATS, bool AUTORESET>
 __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxState s,
-                               const float* __restrict__ pool, uint64_t t_next,
+                               const float* __restrict__ pool,
                                const float2* __restrict__ action, float* __restrict__ obs,
                                float* __restrict__ reward, float* __restrict__ done,
                                float* __restrict__ cost, float* __restrict__ qacc,
@@ -307,7 +336,7 @@ __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxStat
     GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a.x, a.y, row,
                                      qacc ? qa : nullptr, AUX ? bins : nullptr);
     if (AUTORESET && o.done > 0.0f) {
-      const float* lay = gx_pick_layout(p, pool, nullptr, i, t_next, GX_STREAM_PICK);
+      const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
       gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
     }
     gx_store_dyn(s, i, d);
@@ -331,7 +360,7 @@ __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxStat
 template <int NH_CT>
 __global__ void gx_reset_done_kernel(const __grid_constant__ gx_params p, const GxState s,
                                      const float* __restrict__ pool, const float* __restrict__ layout,
-                                     uint64_t t_global, const float* obs_in, float* obs_out) {
+                                     const float* obs_in, float* obs_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int wbase = i - lane;
@@ -363,7 +392,7 @@ __global__ void gx_reset_done_kernel(const __grid_constant__ gx_params p, const 
     gx_load_dyn(s, i, d);
     float4 hz_regs[NH_CT ? (NH_CT + 1) / 2 : 1];
     float gx_, gy_;
-    const float* lay = gx_pick_layout(p, pool, layout, i, t_global, GX_STREAM_PICK);
+    const float* lay = gx_pick_layout(p, pool, layout, i, d.age, GX_STREAM_PICK);
     gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
     gx_store_dyn(s, i, d);
   }
@@ -380,7 +409,7 @@ __global__ void gx_reset_done_kernel(const __grid_constant__ gx_params p, const 
 // registers between steps; HBM sees only the per-step outputs.
 template <int NH_CT, bool STATS>
 __global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxState s,
-                                  const float* __restrict__ pool, int T, uint64_t t0,
+                                  const float* __restrict__ pool, int T,
                                   float* __restrict__ obs, float2* __restrict__ act,
                                   float* __restrict__ reward, float* __restrict__ cost,
                                   float* __restrict__ done, double* __restrict__ stats) {
@@ -402,16 +431,16 @@ __global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxS
   const uint64_t g = p.env_id_offset + (uint64_t)i;
   const size_t n = (size_t)p.n;
   for (int t = 0; t < T; ++t) {
-    const uint64_t tg = t0 + (uint64_t)t;
     float my_cost = 0.0f;
     if (live) {
+      const uint64_t tg = d.age;
       gx_u32x4 u = gx_philox4x32_10((uint32_t)g, (uint32_t)tg, (uint32_t)(tg >> 32), GX_STREAM_ACTION, p.seed_lo, p.seed_hi);
       const float a0 = gx_uniform(u.v[0], -1.0f, 1.0f), a1 = gx_uniform(u.v[1], -1.0f, 1.0f);
       GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a0, a1, row, nullptr, nullptr);
       if (STATS) gx_stats_step(s, i, stats, o.reward, o.cost, o.done);
       my_cost = o.cost;
       if (o.done > 0.0f) {
-        const float* lay = gx_pick_layout(p, pool, nullptr, i, tg + 1, GX_STREAM_PICK);
+        const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
         gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
       }
       const size_t k = (size_t)t * n + (size_t)i;
@@ -429,7 +458,7 @@ __global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxS
 // ---- 16-lanes-per-env variants (small batches; gx_lanes.cuh) ------------------
 template <bool STATS, bool AUTORESET>
 __global__ void __launch_bounds__(128) gx_step_lanes_kernel(
-    const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool, uint64_t t_next,
+    const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool,
     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
     float* __restrict__ done, float* __restrict__ cost, float* __restrict__ qacc, double* __restrict__ stats) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -448,7 +477,7 @@ __global__ void __launch_bounds__(128) gx_step_lanes_kernel(
   float qa[3];
   GxLaneStep r = gx_step_lanes(p, sub, gmask, d, gx_, gy_, ox, oy, a.x, a.y, qacc ? qa : nullptr);
   if (AUTORESET && r.out.done > 0.0f) {
-    const float* lay = gx_pick_layout(p, pool, nullptr, i, t_next, GX_STREAM_PICK);
+    const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
     gx_reset_done_lanes(p, s, i, sub, gmask, live, lay, d, gx_, gy_, ox, oy, r.obs);
     r.c0 = 0.0f; r.c1 = 0.0f; r.c2 = 0.0f;
   }
@@ -469,7 +498,7 @@ __global__ void __launch_bounds__(128) gx_step_lanes_kernel(
 
 template <bool STATS>
 __global__ void __launch_bounds__(128) gx_rollout_lanes_kernel(
-    const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool, int T, uint64_t t0,
+    const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool, int T,
     float* __restrict__ obs, float2* __restrict__ act, float* __restrict__ reward, float* __restrict__ cost,
     float* __restrict__ done, double* __restrict__ stats) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -488,13 +517,13 @@ __global__ void __launch_bounds__(128) gx_rollout_lanes_kernel(
   const size_t n = (size_t)p.n;
   const int rows = min(2, p.n - ((gtid - lane) >> 4));
   for (int t = 0; t < T; ++t) {
-    const uint64_t tg = t0 + (uint64_t)t;
+    const uint64_t tg = d.age;
     gx_u32x4 u = gx_philox4x32_10((uint32_t)gid, (uint32_t)tg, (uint32_t)(tg >> 32), GX_STREAM_ACTION, p.seed_lo, p.seed_hi);
     const float a0 = gx_uniform(u.v[0], -1.0f, 1.0f), a1 = gx_uniform(u.v[1], -1.0f, 1.0f);
     GxLaneStep r = gx_step_lanes(p, sub, gmask, d, gx_, gy_, ox, oy, a0, a1, nullptr);
     if (STATS && live && sub == 9) gx_stats_step(s, i, stats, r.out.reward, r.out.cost, r.out.done);
     if (r.out.done > 0.0f) {
-      const float* lay = gx_pick_layout(p, pool, nullptr, i, tg + 1, GX_STREAM_PICK);
+      const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
       gx_reset_done_lanes(p, s, i, sub, gmask, live, lay, d, gx_, gy_, ox, oy, r.obs);
       r.c0 = 0.0f; r.c1 = 0.0f; r.c2 = 0.0f;
     }
@@ -534,6 +563,7 @@ __global__ void gx_set_state_kernel(const __grid_constant__ gx_params p, const G
   if (i >= p.n) return;
   const float* o = in + (size_t)i * p.state_dim;
   GxDyn d;
+  gx_load_dyn(s, i, d);  // keeps the env's age
   d.qx = o[0]; d.qy = o[1]; d.qth = o[2]; d.vx = o[3]; d.vy = o[4]; d.vw = o[5];
   d.hc = o[6]; d.hs = o[7]; d.prev_dist = o[8]; d.done = o[9]; d.steps = o[10];
   gx_store_dyn(s, i, d);
@@ -590,7 +620,7 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   e->p = p;
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
-  e->epoch = 0; e->t_global = 0; e->have_reset = false; e->stats_on = false;
+  e->ctr = nullptr; e->have_reset = false; e->stats_on = false;
   e->stage = nullptr;
   e->lanes_max_envs = 16384;
   if (const char* v = getenv("GX_LANES_MAX_ENVS")) e->lanes_max_envs = atoi(v);
@@ -612,13 +642,14 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   } while (0)
   GX_ALLOC(s.d0, sizeof(float4) * cap);
   GX_ALLOC(s.d1, sizeof(float4) * cap);
-  GX_ALLOC(s.d2, sizeof(float2) * cap);
+  GX_ALLOC(s.d2, sizeof(float4) * cap);
   GX_ALLOC(s.goal, sizeof(float2) * cap);
   GX_ALLOC(s.hz, sizeof(float4) * (size_t)cap * s.nh2);
   GX_ALLOC(s.ep, sizeof(float4) * cap);
   GX_ALLOC(e->pool, sizeof(float) * (size_t)p.pool_size * p.lay_dim);
   GX_ALLOC(e->pool_tries, sizeof(int32_t) * (size_t)p.pool_size);
   GX_ALLOC(e->stats, sizeof(double) * 8);
+  GX_ALLOC(e->ctr, sizeof(unsigned long long) * 4);
 #undef GX_ALLOC
   // never-forwarded mjx.Data carries the identity xmat that put_data copied in
   {
@@ -637,7 +668,7 @@ GX_API int gx_destroy(gx_env* e) {
   DeviceGuard guard(e->device);
   cudaFree(e->s.d0); cudaFree(e->s.d1); cudaFree(e->s.d2); cudaFree(e->s.goal);
   cudaFree(e->s.hz); cudaFree(e->s.ep);
-  cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage);
+  cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage); cudaFree(e->ctr);
   delete e;
   return GX_OK;
 }
@@ -680,13 +711,10 @@ GX_API int gx_action_bounds(const gx_env* e, float* h_low, float* h_high) {
   } while (0)
 
 static int gx_generate_pool(gx_env* e, cudaStream_t st) {
-  gx_u32x4 key = gx_philox4x32_10((uint32_t)e->epoch, (uint32_t)(e->epoch >> 32), 0u, GX_STREAM_LAYOUT,
-                                  e->p.seed_lo, e->p.seed_hi);
   const int block = 128;
   const int grid = div_up(e->p.pool_size * 32, block);
-  gx_pool_kernel<<<grid, block, 0, st>>>(e->p, key.v[0], key.v[1], e->pool, e->pool_tries);
+  gx_pool_kernel<<<grid, block, 0, st>>>(e->p, e->ctr, e->pool, e->pool_tries);
   GX_LAUNCH_CHECK("gx_pool_kernel");
-  e->epoch += 1;
   return GX_OK;
 }
 
@@ -694,9 +722,9 @@ static int gx_reset_impl(gx_env* e, const float* layout, float* obs, cudaStream_
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
   if (fast_path(e))
-    gx_reset_kernel<8><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs);
+    gx_reset_kernel<8><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, obs);
   else
-    gx_reset_kernel<0><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs);
+    gx_reset_kernel<0><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, obs);
   GX_LAUNCH_CHECK("gx_reset_kernel");
   e->have_reset = true;
   return GX_OK;
@@ -721,7 +749,7 @@ static void launch_step(gx_env* e, int grid, int block, size_t sh, cudaStream_t 
                         float* obs, float* reward, float* done, float* cost, float* qacc, int32_t* aux,
                         bool autoreset) {
   const float2* a2 = reinterpret_cast<const float2*>(action);
-#define GX_ST(AX, ST, AR) gx_step_kernel<NH_CT, AX, ST, AR><<<grid, block, sh, st>>>(e->p, e->s, e->pool, e->t_global + 1, a2, obs, reward, done, cost, qacc, aux, e->stats)
+#define GX_ST(AX, ST, AR) gx_step_kernel<NH_CT, AX, ST, AR><<<grid, block, sh, st>>>(e->p, e->s, e->pool, a2, obs, reward, done, cost, qacc, aux, e->stats)
 #define GX_ST2(AX, ST) do { if (autoreset) GX_ST(AX, ST, true); else GX_ST(AX, ST, false); } while (0)
   if (aux) { if (e->stats_on) GX_ST2(true, true); else GX_ST2(true, false); }
   else { if (e->stats_on) GX_ST2(false, true); else GX_ST2(false, false); }
@@ -739,12 +767,11 @@ static int gx_step_impl(gx_env* e, const float* action, float* obs, float* rewar
   if (!aux && lanes_path(e)) {
     const int block = 128, grid = div_up(e->p.n * GX_LPE, block);
     const float2* a2 = reinterpret_cast<const float2*>(action);
-#define GX_SL(ST, AR) gx_step_lanes_kernel<ST, AR><<<grid, block, 0, st>>>(e->p, e->s, e->pool, e->t_global + 1, a2, obs, reward, done, cost, qacc, e->stats)
+#define GX_SL(ST, AR) gx_step_lanes_kernel<ST, AR><<<grid, block, 0, st>>>(e->p, e->s, e->pool, a2, obs, reward, done, cost, qacc, e->stats)
     if (e->stats_on) { if (autoreset) GX_SL(true, true); else GX_SL(true, false); }
     else { if (autoreset) GX_SL(false, true); else GX_SL(false, false); }
 #undef GX_SL
     GX_LAUNCH_CHECK("gx_step_lanes_kernel");
-    e->t_global += 1;
     return GX_OK;
   }
   const int block = pick_block(e), grid = div_up(e->p.n, block);
@@ -752,7 +779,6 @@ static int gx_step_impl(gx_env* e, const float* action, float* obs, float* rewar
   if (fast_path(e)) launch_step<8>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset);
   else launch_step<0>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset);
   GX_LAUNCH_CHECK("gx_step_kernel");
-  e->t_global += 1;
   return GX_OK;
 }
 
@@ -774,9 +800,9 @@ GX_API int gx_reset_done(gx_env* e, const float* obs_in, float* obs_out, const f
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
   if (fast_path(e))
-    gx_reset_done_kernel<8><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs_in, obs_out);
+    gx_reset_done_kernel<8><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, obs_in, obs_out);
   else
-    gx_reset_done_kernel<0><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, e->t_global, obs_in, obs_out);
+    gx_reset_done_kernel<0><<<grid, block, sh, st>>>(e->p, e->s, e->pool, layout, obs_in, obs_out);
   GX_LAUNCH_CHECK("gx_reset_done_kernel");
   return GX_OK;
 }
@@ -795,6 +821,44 @@ GX_API int gx_set_state(gx_env* e, const float* state, void* stream) {
   gx_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
   GX_LAUNCH_CHECK("gx_set_state_kernel");
   e->have_reset = true;
+  return GX_OK;
+}
+
+__global__ void gx_set_age_kernel(const GxState s, int n, unsigned long long age) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 c = s.d2[i];
+  c.z = __uint_as_float((uint32_t)age);
+  c.w = __uint_as_float((uint32_t)(age >> 32));
+  s.d2[i] = c;
+}
+
+GX_API int gx_set_counters(gx_env* e, uint64_t t_global, uint64_t epoch, void* stream) {
+  if (!e) return gx_fail(GX_EINVAL, "gx_set_counters: NULL env");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long h[4] = {0ull, epoch, 0ull, 0ull};
+  GX_CUDA(cudaMemcpyAsync(e->ctr, h, sizeof h, cudaMemcpyHostToDevice, st));
+  gx_set_age_kernel<<<div_up(e->p.n, 128), 128, 0, st>>>(e->s, e->p.n, t_global);
+  GX_LAUNCH_CHECK("gx_set_age_kernel");
+  GX_CUDA(cudaStreamSynchronize(st));  // h is on this stack frame
+  return GX_OK;
+}
+
+GX_API int gx_get_counters(gx_env* e, uint64_t* h_t_global, uint64_t* h_epoch, void* stream) {
+  if (!e) return gx_fail(GX_EINVAL, "gx_get_counters: NULL env");
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long h[4];
+  float4 d2;
+  GX_CUDA(cudaMemcpyAsync(h, e->ctr, sizeof h, cudaMemcpyDeviceToHost, st));
+  GX_CUDA(cudaMemcpyAsync(&d2, e->s.d2, sizeof d2, cudaMemcpyDeviceToHost, st));  // env 0
+  GX_CUDA(cudaStreamSynchronize(st));
+  uint32_t lo, hi;
+  memcpy(&lo, &d2.z, 4);
+  memcpy(&hi, &d2.w, 4);
+  if (h_t_global) *h_t_global = (uint64_t)lo | ((uint64_t)hi << 32);
+  if (h_epoch) *h_epoch = h[GX_CTR_EPOCH];
   return GX_OK;
 }
 
@@ -819,18 +883,16 @@ GX_API int gx_rollout(gx_env* e, int32_t T, float* obs, float* act, float* rewar
   float2* a2 = reinterpret_cast<float2*>(act);
   if (lanes_path(e)) {
     const int lb = 128, lg = div_up(e->p.n * GX_LPE, lb);
-    if (e->stats_on) gx_rollout_lanes_kernel<true><<<lg, lb, 0, st>>>(e->p, e->s, e->pool, T, e->t_global, obs, a2, reward, cost, done, e->stats);
-    else gx_rollout_lanes_kernel<false><<<lg, lb, 0, st>>>(e->p, e->s, e->pool, T, e->t_global, obs, a2, reward, cost, done, e->stats);
+    if (e->stats_on) gx_rollout_lanes_kernel<true><<<lg, lb, 0, st>>>(e->p, e->s, e->pool, T, obs, a2, reward, cost, done, e->stats);
+    else gx_rollout_lanes_kernel<false><<<lg, lb, 0, st>>>(e->p, e->s, e->pool, T, obs, a2, reward, cost, done, e->stats);
     GX_LAUNCH_CHECK("gx_rollout_lanes_kernel");
-    e->t_global += (uint64_t)T;
     return GX_OK;
   }
-#define GX_RO(NH, ST) gx_rollout_kernel<NH, ST><<<grid, block, sh, st>>>(e->p, e->s, e->pool, T, e->t_global, obs, a2, reward, cost, done, e->stats)
+#define GX_RO(NH, ST) gx_rollout_kernel<NH, ST><<<grid, block, sh, st>>>(e->p, e->s, e->pool, T, obs, a2, reward, cost, done, e->stats)
   if (fast_path(e)) { if (e->stats_on) GX_RO(8, true); else GX_RO(8, false); }
   else { if (e->stats_on) GX_RO(0, true); else GX_RO(0, false); }
 #undef GX_RO
   GX_LAUNCH_CHECK("gx_rollout_kernel");
-  e->t_global += (uint64_t)T;
   return GX_OK;
 }
 
@@ -890,13 +952,17 @@ __global__ void gx_debug_math_kernel(int fn, const float* a, const float* b, flo
     if (out2) out2[i] = c;
   } else if (fn == 1) {
     out[i] = gx_atan2(a[i], b[i]);
-  } else {
+  } else if (fn == 2) {
     out[i] = gx_exp(a[i]);
+  } else if (fn == 3) {
+    out[i] = gx_max(a[i], b[i]);
+  } else {
+    out[i] = gx_min(a[i], b[i]);
   }
 }
 
 GX_API int gx_debug_math(int fn, const float* a, const float* b, float* out, float* out2, int n, void* stream) {
-  if (!a || !out || n < 0 || fn < 0 || fn > 2 || (fn == 1 && !b)) return gx_fail(GX_EINVAL, "gx_debug_math: bad argument");
+  if (!a || !out || n < 0 || fn < 0 || fn > 4 || (fn != 0 && fn != 2 && !b)) return gx_fail(GX_EINVAL, "gx_debug_math: bad argument");
   if (n == 0) return GX_OK;
   gx_debug_math_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(fn, a, b, out, out2, n);
   GX_LAUNCH_CHECK("gx_debug_math_kernel");

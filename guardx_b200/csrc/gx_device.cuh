@@ -28,17 +28,23 @@
 //   d0  float4  qpos.x qpos.y qpos.theta qvel.x
 //   d1  float4  qvel.y qvel.theta lag_cos lag_sin    (lag = R[0,0], R[1,0] of the
 //                                                     last forward, engine.py:676)
-//   d2  float2  prev_dist, steps  (sign bit of steps = Engine._done; steps == 0
-//                                  whenever done, engine.py:493, so -0.0f encodes it)
+//   d2  float4  prev_dist, steps, age_lo, age_hi
+//               (sign bit of steps = Engine._done; steps == 0 whenever done,
+//                engine.py:493, so -0.0f encodes it.  age = number of step() calls
+//                this env has seen: the counter that keys its Philox draws.  It is
+//                the same number for every env -- the reference keeps ONE key and
+//                splits it once per step (engine.py:431) -- but it is stored per env
+//                so that no launch carries a host-side count and no kernel needs a
+//                grid-wide counter update: CUDA-graph replay stays correct for free.)
 //   goal float2
 //   hz  float4[nh2][cap]   two hazards per float4, pair-major (coalesced per pair)
 //   ep  float4  ep_ret ep_cost ep_len cum_cost       (only touched when stats on)
-// Dynamic part 40 B, static part 8 + 8*nh B per env.
+// Dynamic part 48 B, static part 8 + 8*nh B per env.
 // ---------------------------------------------------------------------------
 struct GxState {
   float4* d0;
   float4* d1;
-  float2* d2;
+  float4* d2;
   float2* goal;
   float4* hz;
   float4* ep;
@@ -52,23 +58,30 @@ struct GxDyn {
   float prev_dist;                // goal_pos(last_data)
   float steps;                    // Engine._steps
   float done;                     // Engine._done (0/1)
+  uint64_t age;                   // step() calls seen so far (keys the RNG draws)
 };
 
 __device__ __forceinline__ void gx_load_dyn(const GxState& s, int i, GxDyn& d) {
   float4 a = s.d0[i];
   float4 b = s.d1[i];
-  float2 c = s.d2[i];
+  float4 c = s.d2[i];
   d.qx = a.x; d.qy = a.y; d.qth = a.z; d.vx = a.w;
   d.vy = b.x; d.vw = b.y; d.hc = b.z; d.hs = b.w;
   d.prev_dist = c.x;
   d.done = (__float_as_uint(c.y) >> 31) ? 1.0f : 0.0f;
   d.steps = fabsf(c.y);
+  d.age = (uint64_t)__float_as_uint(c.z) | ((uint64_t)__float_as_uint(c.w) << 32);
+}
+
+__device__ __forceinline__ float4 gx_pack_d2(const GxDyn& d) {
+  return make_float4(d.prev_dist, d.done > 0.0f ? -d.steps : d.steps, __uint_as_float((uint32_t)d.age),
+                     __uint_as_float((uint32_t)(d.age >> 32)));
 }
 
 __device__ __forceinline__ void gx_store_dyn(const GxState& s, int i, const GxDyn& d) {
   s.d0[i] = make_float4(d.qx, d.qy, d.qth, d.vx);
   s.d1[i] = make_float4(d.vy, d.vw, d.hc, d.hs);
-  s.d2[i] = make_float2(d.prev_dist, d.done > 0.0f ? -d.steps : d.steps);
+  s.d2[i] = gx_pack_d2(d);
 }
 
 // mjx kinematics of the robot body (quaternion path, A4): R[0,0], R[1,0].
@@ -319,6 +332,7 @@ __device__ __forceinline__ GxStepOut gx_step_env(const gx_params& p, const GxSta
   d.prev_dist = dist;
   d.hc = r00;
   d.hs = r10;
+  d.age += 1;  // update_data splits the key once per step (engine.py:431)
   out.cost = o.cost;
   out.violations = o.violations;
   return out;

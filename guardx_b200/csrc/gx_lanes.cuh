@@ -40,12 +40,12 @@ __device__ __forceinline__ T gx_grp(unsigned gmask, T v, int src) {
 __device__ __forceinline__ float gx_fold_ray(float v, int j, int bin, float sensor, float up, float down) {
   const int bp = (bin + 1) & 15;  // bin in 0..16: (bin+1) % 16
   const int bm = (bin - 1) & 15;  // (bin-1) mod 16, also for bin = 0 and bin = 16
-  float t = gx_max(v, sensor);
-  v = (bin == j) ? t : v;         // bin == 16 never equals j: the out-of-bounds scatter is dropped
-  t = gx_max(v, up);
-  v = (bp == j) ? t : v;
-  t = gx_max(v, down);
-  v = (bm == j) ? t : v;
+  // A contribution that targets another bin is replaced by +0, the neutral
+  // element here: v is always >= +0 or NaN, and max(v, +0) == v bit for bit.
+  // bin == 16 never equals j: the out-of-bounds scatter is dropped (JAX).
+  v = gx_max(v, (bin == j) ? sensor : 0.0f);
+  v = gx_max(v, (bp == j) ? up : 0.0f);
+  v = gx_max(v, (bm == j) ? down : 0.0f);
   return v;
 }
 
@@ -197,6 +197,7 @@ __device__ __forceinline__ GxLaneStep gx_step_lanes(const gx_params& p, int sub,
   d.prev_dist = dist;
   d.hc = r00;
   d.hs = r10;
+  d.age += 1;
   out.cost = r.obs.cost;
   out.violations = r.obs.violations;
   return r;
@@ -206,7 +207,7 @@ __device__ __forceinline__ GxLaneStep gx_step_lanes(const gx_params& p, int sub,
 __device__ __forceinline__ void gx_store_dyn_lanes(const GxState& s, int i, int sub, const GxDyn& d) {
   if (sub == 0) s.d0[i] = make_float4(d.qx, d.qy, d.qth, d.vx);
   if (sub == 1) s.d1[i] = make_float4(d.vy, d.vw, d.hc, d.hs);
-  if (sub == 2) s.d2[i] = make_float2(d.prev_dist, d.done > 0.0f ? -d.steps : d.steps);
+  if (sub == 2) s.d2[i] = gx_pack_d2(d);
 }
 
 #endif  // GX_LANES_CUH_

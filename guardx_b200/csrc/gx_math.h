@@ -83,16 +83,34 @@ GX_HD int gx_isnan(float x) { return x != x; }
 /* true for +-inf and NaN */
 GX_HD int gx_notfinite(float x) { return (gx_f2u(x) & 0x7f800000u) == 0x7f800000u; }
 
-/* jnp.maximum / jnp.minimum semantics: NaN in either operand wins. */
+/* jnp.maximum / jnp.minimum semantics: NaN in either operand wins; zeros are
+   ordered -0 < +0 (IEEE 754-2019 maximum/minimum).  On the device this is ONE
+   instruction (PTX max.NaN.f32 / min.NaN.f32 -> FMNMX.NAN); the host spells the
+   same function out.  Which NaN comes back is unspecified (tests treat all NaNs
+   as equal). */
 GX_HD float gx_max(float a, float b) {
-  float m = a > b ? a : b; /* selects, no branches */
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+#else
+  float m = a > b ? a : b;
+  if (a == b) m = gx_u2f(gx_f2u(a) & gx_f2u(b)); /* (+0,-0) -> +0 */
   m = (b != b) ? b : m;
   return (a != a) ? a : m;
+#endif
 }
 GX_HD float gx_min(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+#else
   float m = a < b ? a : b;
+  if (a == b) m = gx_u2f(gx_f2u(a) | gx_f2u(b)); /* (+0,-0) -> -0 */
   m = (b != b) ? b : m;
   return (a != a) ? a : m;
+#endif
 }
 /* jnp.clip semantics (NaN stays NaN). */
 GX_HD float gx_clip(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }

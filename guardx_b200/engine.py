@@ -292,6 +292,18 @@ class Engine:
         s = self._as_input(state, (self.env_num, self.state_dim))
         _abi.check(self._lib, self._lib.gx_set_state(self._h, self._ptr(s), self._stream()), "gx_set_state")
 
+    def counters(self):
+        """(t_global, epoch): env steps taken and layout pools generated -- the two
+        device-resident counters that key every random draw.  Synchronises."""
+        t, e = C.c_uint64(), C.c_uint64()
+        _abi.check(self._lib, self._lib.gx_get_counters(self._h, C.byref(t), C.byref(e), self._stream()),
+                   "gx_get_counters")
+        return int(t.value), int(e.value)
+
+    def set_counters(self, t_global: int, epoch: int):
+        _abi.check(self._lib, self._lib.gx_set_counters(self._h, t_global, epoch, self._stream()),
+                   "gx_set_counters")
+
     def layout_pool(self):
         pool = self._empty(self.layout_size, self.layout_dim)
         tries = self._empty(self.layout_size, dtype=torch.int32)

@@ -201,6 +201,15 @@ int gx_state_dim(const gx_env* env);
 int gx_get_state(gx_env* env, float* state, void* stream);
 int gx_set_state(gx_env* env, const float* state, void* stream);
 
+/* ---- the two counters that key every random draw: t_global (env steps taken)
+ *      and epoch (layout pools generated).  They live in DEVICE memory and are
+ *      advanced by the kernels themselves, so gx_reset / gx_step* /
+ *      gx_reset_done / gx_rollout never bake a host-side count into a launch and
+ *      can be captured in a CUDA graph and replayed.  These two calls copy them
+ *      and synchronise `stream` (checkpointing, test alignment). ------------- */
+int gx_set_counters(gx_env* env, uint64_t t_global, uint64_t epoch, void* stream);
+int gx_get_counters(gx_env* env, uint64_t* h_t_global, uint64_t* h_epoch, void* stream);
+
 /* ---- layout pool (reset_layout, engine.py:433-444) ------------------------
  * pool: [pool_size, 2*(2+hazards_num)] device floats; tries: [pool_size] int32,
  * the number of candidates each slot consumed (acceptance-rate evidence). */
@@ -235,7 +244,8 @@ int gx_step_host(gx_env* env, const float* h_action, float* h_obs, float* h_rewa
 
 /* ---- diagnostics: evaluate the shared fp32 math (csrc/gx_math.h) on the
  *      device, so tests can prove host/device bit-equality of the header.
- *      fn: 0 sincos(a)->out,out2   1 atan2(a,b)->out   2 exp(a)->out.
+ *      fn: 0 sincos(a)->out,out2   1 atan2(a,b)->out   2 exp(a)->out
+ *          3 max(a,b)->out   4 min(a,b)->out.
  *      a, b, out, out2: device arrays of n floats (b/out2 may be NULL). ------ */
 int gx_debug_math(int fn, const float* a, const float* b, float* out, float* out2, int n,
                   void* stream);

@@ -595,6 +595,8 @@ GXO_API int gxo_stats_reset(gxo_env* e) { memset(e->stats, 0, sizeof e->stats); 
 GXO_API void gxo_v_sincos(const float* x, float* s, float* c, int n) { for (int i = 0; i < n; ++i) gx_sincos(x[i], s + i, c + i); }
 GXO_API void gxo_v_atan2(const float* y, const float* x, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = gx_atan2(y[i], x[i]); }
 GXO_API void gxo_v_exp(const float* x, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = gx_exp(x[i]); }
+GXO_API void gxo_v_max(const float* a, const float* b, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = gx_max(a[i], b[i]); }
+GXO_API void gxo_v_min(const float* a, const float* b, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = gx_min(a[i], b[i]); }
 GXO_API void gxo_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   gx_u32x4 r = gx_philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
   for (int i = 0; i < 4; ++i) out[i] = r.v[i];

@@ -96,6 +96,18 @@ def test_shared_math_is_bit_identical_on_device(mods, oracle_lib):
     oracle_lib.gxo_v_exp(p(xe), p(o), n)
     assert lib.gx_debug_math(2, dp(torch.from_numpy(xe).cuda()), None, dp(o1), None, n, None) == 0
     bits_equal(cpu(o1), o, "exp")
+    # max / min: NaN propagation and signed zeros
+    special = np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1.0, -1.0, 1e-45, -1e-45], np.float32)
+    aa, bb = [v.ravel().copy() for v in np.meshgrid(special, special)]
+    da, db, do_ = torch.from_numpy(aa).cuda(), torch.from_numpy(bb).cuda(), torch.empty(len(aa), device='cuda')
+    ref = np.empty_like(aa)
+    for fn, name in ((3, "gxo_v_max"), (4, "gxo_v_min")):
+        getattr(oracle_lib, name)(p(aa), p(bb), p(ref), len(aa))
+        assert lib.gx_debug_math(fn, dp(da), dp(db), dp(do_), None, len(aa), None) == 0
+        bits_equal(cpu(do_), ref, name)
+    oracle_lib.gxo_v_max(p(x), p(y), p(o), n)
+    assert lib.gx_debug_math(3, dp(dx), dp(dy), dp(o1), None, n, None) == 0
+    bits_equal(cpu(o1), o, "max")
 
 
 # ---------------------------------------------------------------- layout pool
@@ -495,3 +507,48 @@ def test_step_autoreset_equals_step_then_reset_done(mods):
         n_done += int(da.sum().item())
     assert n_done > 2500
     assert torch.equal(a.get_state().view(torch.int32), b.get_state().view(torch.int32))
+
+
+def test_cuda_graph_capture_and_replay(mods):
+    """Counters live in device memory, so a captured graph of fused steps replays
+    correctly: 5 replays of a 6-step graph == 30 direct steps on a twin env."""
+    Engine, _ = mods
+    cfg = {'env_num': 2048, 'num_steps': 9, '_seed': 17}
+    a, b = Engine(dict(cfg)), Engine(dict(cfg))
+    a.reset(); b.reset()
+    acts = torch.rand(6, 2048, 2, device='cuda') * 2 - 1
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        a.step_autoreset(acts[0]); b.step_autoreset(acts[0])   # warm-up outside capture
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        outs = [a.step_autoreset(acts[k]) for k in range(6)]
+    assert a.counters()[0] == 1          # capture does not execute
+    n_done = 0
+    for rep in range(5):
+        g.replay()
+        torch.cuda.synchronize()
+        for k in range(6):
+            o, r, d, info = b.step_autoreset(acts[k])
+            go, gr, gd, gi = outs[k]
+            assert torch.equal(go.view(torch.int32), o.view(torch.int32)), (rep, k)
+            assert torch.equal(gr.view(torch.int32), r.view(torch.int32)) and torch.equal(gd, d)
+            assert torch.equal(gi['cost'].view(torch.int32), info['cost'].view(torch.int32))
+            n_done += int(d.sum().item())
+    assert n_done > 2048
+    assert a.counters() == b.counters() == (31, 1)
+    assert torch.equal(a.get_state().view(torch.int32), b.get_state().view(torch.int32))
+
+
+def test_counters_roundtrip(mods):
+    g, o = make_pair(mods, {'env_num': 64, 'num_steps': 5, '_seed': 33})
+    g.set_counters(1 << 33, 7); o.set_counters(1 << 33, 7)   # > 32-bit step counts key correctly
+    bits_equal(cpu(g.reset()), o.reset(), "reset at epoch 7")
+    assert g.counters() == (1 << 33, 8)
+    rg, ro = g.rollout(30), o.rollout(30)
+    for k in ("obs", "act", "done"):
+        bits_equal(cpu(rg[k]), ro[k], k)
+    assert g.counters() == ((1 << 33) + 30, 8)

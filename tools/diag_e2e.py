@@ -52,3 +52,21 @@ print("graph of 100 steps: us/step", dt / 2000 * 1e6)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ev0.record(); lib.gx_step_autoreset(*args); ev1.record(); torch.cuda.synchronize()
 print("single launch event time us", ev0.elapsed_time(ev1) * 1e3)
+# floor: graph of 100 trivial 1-block kernels
+xa = torch.zeros(32, device='cuda'); xo = torch.zeros(32, device='cuda')
+g2 = torch.cuda.CUDAGraph()
+with torch.cuda.stream(s):
+    lib.gx_debug_math(2, p(xa), None, p(xo), None, 32, sp); torch.cuda.synchronize()
+    with torch.cuda.graph(g2, stream=s):
+        for _ in range(100): lib.gx_debug_math(2, p(xa), None, p(xo), None, 32, sp)
+torch.cuda.synchronize()
+for _ in range(3): g2.replay()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(20): g2.replay()
+torch.cuda.synchronize(); print("graph floor (trivial kernel) us/node", (time.perf_counter() - t0) / 2000 * 1e6)
+# rollout kernel per-step time
+ro = env.rollout(8, want=("obs",)); torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+obs_buf = torch.empty(256, n, od, device='cuda')
+ev0.record(); lib.gx_rollout(env._h, 256, p(obs_buf), None, None, None, None, None); ev1.record(); torch.cuda.synchronize()
+print("rollout kernel us/step (obs only)", ev0.elapsed_time(ev1) * 1e3 / 256)
