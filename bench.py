@@ -187,27 +187,73 @@ class Batch:
         self.h = self.env._h
 
 
-def time_steps(torch, lib, batches, steps, stream, barrier=None):
-    """K fused step launches, round-robin over the batches; CUDA events on the
-    launching stream, synchronise on both sides."""
+def issue_steps(lib, batches, steps, sp, t0=0):
+    """enqueue `steps` fused step launches round-robin over the batches"""
     R = len(batches)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sp = C.c_void_p(stream.cuda_stream)
     fn = lib.gx_step_autoreset
-    if barrier:
-        barrier()
-    torch.cuda.synchronize()
-    ev0.record(stream)
-    for t in range(steps):
+    for t in range(t0, t0 + steps):
         b = batches[t % R]
         rc = fn(b.h, b.p_act[(t // R) % len(b.p_act)], b.p_obs, b.p_r, b.p_d, b.p_c, sp)
         if rc:
             raise RuntimeError(lib.gx_last_error().decode())
+
+
+def time_steps(torch, lib, batches, steps, stream, barrier=None):
+    """K fused step launches issued one by one from Python (stream launches);
+    CUDA events on the launching stream, synchronise on both sides."""
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sp = C.c_void_p(stream.cuda_stream)
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    ev0.record(stream)
+    issue_steps(lib, batches, steps, sp)
     ev1.record(stream)
     torch.cuda.synchronize()
     if barrier:
         barrier()
     return ev0.elapsed_time(ev1) * 1e-3
+
+
+class GraphedSteps:
+    """EXACTLY K fused step launches as CUDA graphs (chunks of <= 2048 kernel
+    nodes).  Legal because every counter the kernels use lives in device memory."""
+
+    def __init__(self, torch, lib, batches, steps, chunk=2048):
+        self.torch = torch
+        self.plan = []
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        sp = C.c_void_p(side.cuda_stream)
+        q, r = divmod(steps, chunk)
+        done = 0
+        with torch.cuda.stream(side):
+            for size, reps in ((chunk, q), (r, 1)):
+                if size == 0 or reps == 0:
+                    continue
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    issue_steps(lib, batches, size, sp, t0=done)
+                self.plan.append((g, reps))
+                done += size * reps
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+    def run(self, stream, barrier=None):
+        torch = self.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if barrier:
+            barrier()
+        torch.cuda.synchronize()
+        ev0.record(stream)
+        for g, reps in self.plan:
+            for _ in range(reps):
+                g.replay()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        return ev0.elapsed_time(ev1) * 1e-3
 
 
 def main():
@@ -230,6 +276,7 @@ def main():
     import numpy as np
     import torch
     from guardx_b200 import _abi
+    from guardx_b200 import distributed as gxd
     from guardx_b200.engine import Engine
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback); use --impl reference for the CPU arm"
@@ -260,20 +307,26 @@ def main():
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- value: cold-L2 round-robin --------------------------------------
-    time_steps(torch, lib, batches, warmup, stream)
-    dt = time_steps(torch, lib, batches, K, stream, barrier)
+    # ---- value: K steps as a CUDA graph, cold-L2 round-robin ---------------
+    time_steps(torch, lib, batches, warmup, stream)                   # warm-up (>= 3 steps)
+    graphed = GraphedSteps(torch, lib, batches, K)
+    graphed.run(stream)                                                # one untimed replay
+    dt = graphed.run(stream, barrier)
     # per-epoch statistics all-reduce (replaces mpi_statistics_scalar), inside the job but not the hot loop
     stats = torch.stack([b.env.stats() for b in batches]).sum(0)
+    gxd.allreduce_stats(stats)   # NCCL all-reduce of the 8-double episode statistics vector
     if dist:
-        dist.all_reduce(stats)
         t = torch.tensor([dt], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     value = world * n * K / dt
-    # ---- same loop, one batch only (L2-resident state) --------------------
-    time_steps(torch, lib, batches[:1], warmup, stream)
-    dt_hot = time_steps(torch, lib, batches[:1], K, stream, barrier)
+    # ---- the same K steps launched one by one from Python (no graph) -------
+    dt_stream = time_steps(torch, lib, batches, K, stream, barrier)
+    # ---- same graph over one batch only (L2-resident state) ----------------
+    graphed_hot = GraphedSteps(torch, lib, batches[:1], K)
+    graphed_hot.run(stream)
+    dt_hot = graphed_hot.run(stream, barrier)
+    del graphed_hot
 
     # ---- e2e: host buffers through Engine.step_host -----------------------
     h_act = torch.empty(8, n, 2).uniform_(-1, 1).pin_memory()
@@ -285,7 +338,7 @@ def main():
             batches[t % R].env.step_host(h_act[t & 7], h_out, auto_reset_done=True)
         return float(h_out[-1])  # the step's result is read on the host
 
-    e2e_loop(max(3, warmup // 10))
+    e2e_loop(R + 3)   # warm-up: every batch's staging buffer exists before the timed region
     if barrier:
         barrier()
     torch.cuda.synchronize()
@@ -342,7 +395,10 @@ def main():
             bl = [Batch(Engine, torch, big, 0, seed=100 + k, n_act=2, pool_size=pool_size) for k in range(Rb)]
             time_steps(torch, lib, bl, 5 * Rb, stream)
             kk = 30 * Rb
-            d = time_steps(torch, lib, bl, kk, stream)
+            gs = GraphedSteps(torch, lib, bl, kk)
+            gs.run(stream)
+            d = gs.run(stream)
+            del gs
             gbs = big * ALG_BYTES_STEP * kk / d / 1e9
             sweep.append({"envs": big, "batches": Rb, "us_per_step": 1e6 * d / kk,
                           "env_steps_per_s": big * kk / d, "achieved_gbs": gbs, "frac": gbs / hbm_peak})
@@ -366,11 +422,13 @@ def main():
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": warmup, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(n, world, "CUDA: fused step + auto-reset (gx_step_autoreset), one launch "
-                                                     "per step, in-kernel episode statistics"),
+            "config": dict(workload_config(n, world, "CUDA: fused step + auto-reset (gx_step_autoreset), one kernel "
+                                                     "launch per step, the K launches replayed as CUDA graphs of <= 2048 "
+                                                     "nodes, in-kernel episode statistics"),
                            l2=f"cold: {R} independent {n}-env batches stepped round-robin, working set "
                               f"{working_set / 1e6:.0f} MB > 126 MB L2; value_l2_resident is the single-batch loop"),
             "value_l2_resident": world * n * K / dt_hot,
+            "value_stream_launch": world * n * K / dt_stream,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4,
                     "d2h_bytes_per_step": n * (od + 3) * 4, "steps": Ke,
@@ -378,16 +436,16 @@ def main():
                             "-> D2H obs|reward|done|cost -> stream sync, every step"},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "gx_step_kernel<8,false,true,true>",
+                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "gx_step_lanes_kernel<true,true>",
                          "alg_bytes_per_env_step": ALG_BYTES_STEP, "envs_per_launch": n,
                          "us_per_launch": step_us, "peak_source": peak_src,
-                         "note": "launch-/latency-bound at 4096 envs (1.4 MB per launch); see sweep for larger batches"},
+                         "note": "latency-bound at 4096 envs (1.4 MB per launch, one dependent chain per env); "
+                                 "see sweep for larger batches"},
             "rollout": {"value": ro_value, "unit": "env-steps/s", "steps_per_launch": T, "launches": reps,
                         "alg_bytes_per_env_step": ALG_BYTES_ROLLOUT,
                         "achieved_gbs": ro_value / world * ALG_BYTES_ROLLOUT / 1e9,
                         "frac": ro_value / world * ALG_BYTES_ROLLOUT / 1e9 / hbm_peak},
-            "episode_stats": {"episodes": float(stats[0]), "env_steps": float(stats[7]),
-                              "cost_rate": float(stats[6] / max(1.0, float(stats[7])))},
+            "episode_stats": gxd.episode_summary(stats.tolist()),
         }
         if sweep is not None:
             line["sweep"] = sweep

@@ -71,6 +71,7 @@ struct gx_env {
   unsigned long long* ctr;
   bool have_reset;
   bool stats_on;
+  unsigned long long stats_age0;  // env age at the last gx_stats_reset
   int lanes_max_envs;   // use the 16-lanes-per-env kernels up to this batch size (0 = never)
   // staging for gx_step_host
   float* stage;  // [n*act_dim | n*obs_dim | n | n | n]
@@ -280,27 +281,51 @@ __device__ __forceinline__ void gx_reset_done_env(const gx_params& p, const GxSt
 }
 
 // ---- episode statistics (ppo_train.py:370-376, 405-411 on the host) --------
-__device__ __forceinline__ void gx_stats_step(const GxState& s, int i, double* stats, float reward,
-                                              float cost, float done) {
+// Per-env accumulators only -- no atomics and no grid-wide reduction in the step
+// (4096 same-address atomics per launch cost more than the step itself).  The
+// sums over envs are taken, deterministically, when the statistics are read.
+__device__ __forceinline__ void gx_stats_step(const GxState& s, int i, float reward, float cost, float done) {
   float4 e = s.ep[i];
   e.x += reward; e.y += cost; e.z += 1.0f; e.w += cost;
   if (done > 0.0f) {
-    atomicAdd(stats + 0, 1.0);
-    atomicAdd(stats + 1, (double)e.x);
-    atomicAdd(stats + 2, (double)e.y);
-    atomicAdd(stats + 3, (double)e.z);
-    atomicAdd(stats + 4, (double)e.x * (double)e.x);
-    atomicAdd(stats + 5, (double)e.y * (double)e.y);
+    float4 f0 = s.fin[i], f1 = s.fin[(size_t)s.cap + i];
+    f0.x += 1.0f; f0.y += e.x; f0.z += e.y; f0.w += e.z;
+    f1.x += e.x * e.x; f1.y += e.y * e.y;
+    s.fin[i] = f0;
+    s.fin[(size_t)s.cap + i] = f1;
     e.x = 0.f; e.y = 0.f; e.z = 0.f;
   }
   s.ep[i] = e;
 }
 
-// total cost / total env-steps: one warp-reduced atomic per warp (all 32 lanes call)
-__device__ __forceinline__ void gx_stats_totals(double* stats, float my_cost, int rows, int lane) {
-  double cd = (double)my_cost;
-  for (int off = 16; off; off >>= 1) cd += __shfl_down_sync(0xffffffffu, cd, off);
-  if (lane == 0) { atomicAdd(stats + 6, cd); atomicAdd(stats + 7, (double)rows); }
+// out[8] = n_episodes, sum_ret, sum_cost, sum_len, sum_ret^2, sum_cost^2,
+// total_cost, total_env_steps.  One block, fixed tree => deterministic.
+__global__ void __launch_bounds__(1024) gx_stats_reduce_kernel(const GxState s, int n, unsigned long long age0,
+                                                                double* __restrict__ out) {
+  __shared__ double sh[8][32];
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float4 f0 = s.fin[i], f1 = s.fin[(size_t)s.cap + i], e = s.ep[i], c = s.d2[i];
+    const unsigned long long age = (unsigned long long)__float_as_uint(c.z) | ((unsigned long long)__float_as_uint(c.w) << 32);
+    acc[0] += f0.x; acc[1] += f0.y; acc[2] += f0.z; acc[3] += f0.w;
+    acc[4] += f1.x; acc[5] += f1.y; acc[6] += e.w; acc[7] += (double)(age - age0);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    double v = acc[k];
+    for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) sh[k][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      double v = lane < (blockDim.x >> 5) ? sh[k][lane] : 0.0;
+      for (int off = 16; off; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+      if (lane == 0) out[k] = v;
+    }
+  }
 }
 
 // ---- Engine.step (engine.py:469-495) ---------------------------------------
@@ -323,7 +348,6 @@ __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxStat
   if (wbase >= p.n) return;
   float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
   float* row = tile + lane * p.obs_dim;
-  float my_cost = 0.0f;
   if (i < p.n) {
     GxDyn d;
     gx_load_dyn(s, i, d);
@@ -343,18 +367,16 @@ __global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxStat
     reward[i] = o.reward;
     done[i] = o.done;
     cost[i] = o.cost;
-    my_cost = o.cost;
     if (qacc) { qacc[3 * (size_t)i] = qa[0]; qacc[3 * (size_t)i + 1] = qa[1]; qacc[3 * (size_t)i + 2] = qa[2]; }
     if (AUX) {
       int32_t* ax = aux + (size_t)i * p.aux_dim;
       ax[0] = o.flags; ax[1] = o.violations;
       for (int k = 0; k < 1 + p.nh; ++k) ax[2 + k] = bins[k];
     }
-    if (STATS) gx_stats_step(s, i, stats, o.reward, o.cost, o.done);
+    if (STATS) gx_stats_step(s, i, o.reward, o.cost, o.done);
   }
   const int rows = min(32, p.n - wbase);
   gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
-  if (STATS) gx_stats_totals(stats, my_cost, rows, lane);
 }
 
 template <int NH_CT>
@@ -431,14 +453,12 @@ __global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxS
   const uint64_t g = p.env_id_offset + (uint64_t)i;
   const size_t n = (size_t)p.n;
   for (int t = 0; t < T; ++t) {
-    float my_cost = 0.0f;
     if (live) {
       const uint64_t tg = d.age;
       gx_u32x4 u = gx_philox4x32_10((uint32_t)g, (uint32_t)tg, (uint32_t)(tg >> 32), GX_STREAM_ACTION, p.seed_lo, p.seed_hi);
       const float a0 = gx_uniform(u.v[0], -1.0f, 1.0f), a1 = gx_uniform(u.v[1], -1.0f, 1.0f);
       GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a0, a1, row, nullptr, nullptr);
-      if (STATS) gx_stats_step(s, i, stats, o.reward, o.cost, o.done);
-      my_cost = o.cost;
+      if (STATS) gx_stats_step(s, i, o.reward, o.cost, o.done);
       if (o.done > 0.0f) {
         const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
         gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
@@ -450,7 +470,6 @@ __global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxS
       if (done) done[k] = o.done;
     }
     if (obs) gx_store_tile(tile, obs + ((size_t)t * n + (size_t)wbase) * p.obs_dim, rows, p.obs_dim, lane);
-    if (STATS) gx_stats_totals(stats, my_cost, rows, lane);
   }
   if (live) gx_store_dyn(s, i, d);
 }
@@ -488,11 +507,7 @@ __global__ void __launch_bounds__(128) gx_step_lanes_kernel(
     if (sub == 4) done[i] = r.out.done;
     if (sub == 5) cost[i] = r.out.cost;
     if (qacc && sub >= 6 && sub <= 8) qacc[3 * (size_t)i + (sub - 6)] = qa[sub - 6];
-    if (STATS && sub == 9) gx_stats_step(s, i, stats, r.out.reward, r.out.cost, r.out.done);
-  }
-  if (STATS) {
-    const int rows = min(2, p.n - ((gtid - lane) >> 4));
-    gx_stats_totals(stats, (live && sub == 0) ? r.out.cost : 0.0f, rows, lane);
+    if (STATS && sub == 9) gx_stats_step(s, i, r.out.reward, r.out.cost, r.out.done);
   }
 }
 
@@ -515,13 +530,12 @@ __global__ void __launch_bounds__(128) gx_rollout_lanes_kernel(
   gx_load_object(s, i, sub, gx_, gy_, ox, oy);
   const uint64_t gid = p.env_id_offset + (uint64_t)i;
   const size_t n = (size_t)p.n;
-  const int rows = min(2, p.n - ((gtid - lane) >> 4));
   for (int t = 0; t < T; ++t) {
     const uint64_t tg = d.age;
     gx_u32x4 u = gx_philox4x32_10((uint32_t)gid, (uint32_t)tg, (uint32_t)(tg >> 32), GX_STREAM_ACTION, p.seed_lo, p.seed_hi);
     const float a0 = gx_uniform(u.v[0], -1.0f, 1.0f), a1 = gx_uniform(u.v[1], -1.0f, 1.0f);
     GxLaneStep r = gx_step_lanes(p, sub, gmask, d, gx_, gy_, ox, oy, a0, a1, nullptr);
-    if (STATS && live && sub == 9) gx_stats_step(s, i, stats, r.out.reward, r.out.cost, r.out.done);
+    if (STATS && live && sub == 9) gx_stats_step(s, i, r.out.reward, r.out.cost, r.out.done);
     if (r.out.done > 0.0f) {
       const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
       gx_reset_done_lanes(p, s, i, sub, gmask, live, lay, d, gx_, gy_, ox, oy, r.obs);
@@ -535,7 +549,6 @@ __global__ void __launch_bounds__(128) gx_rollout_lanes_kernel(
       if (done && sub == 4) done[k] = r.out.done;
       if (cost && sub == 5) cost[k] = r.out.cost;
     }
-    if (STATS) gx_stats_totals(stats, (live && sub == 0) ? r.out.cost : 0.0f, rows, lane);
   }
   if (live) gx_store_dyn_lanes(s, i, sub, d);
 }
@@ -620,7 +633,7 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   e->p = p;
   e->device = device;
   e->sm_count = prop.multiProcessorCount;
-  e->ctr = nullptr; e->have_reset = false; e->stats_on = false;
+  e->ctr = nullptr; e->have_reset = false; e->stats_on = false; e->stats_age0 = 0;
   e->stage = nullptr;
   e->lanes_max_envs = 16384;
   if (const char* v = getenv("GX_LANES_MAX_ENVS")) e->lanes_max_envs = atoi(v);
@@ -646,6 +659,7 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   GX_ALLOC(s.goal, sizeof(float2) * cap);
   GX_ALLOC(s.hz, sizeof(float4) * (size_t)cap * s.nh2);
   GX_ALLOC(s.ep, sizeof(float4) * cap);
+  GX_ALLOC(s.fin, sizeof(float4) * 2 * (size_t)cap);
   GX_ALLOC(e->pool, sizeof(float) * (size_t)p.pool_size * p.lay_dim);
   GX_ALLOC(e->pool_tries, sizeof(int32_t) * (size_t)p.pool_size);
   GX_ALLOC(e->stats, sizeof(double) * 8);
@@ -667,7 +681,7 @@ GX_API int gx_destroy(gx_env* e) {
   if (!e) return GX_OK;
   DeviceGuard guard(e->device);
   cudaFree(e->s.d0); cudaFree(e->s.d1); cudaFree(e->s.d2); cudaFree(e->s.goal);
-  cudaFree(e->s.hz); cudaFree(e->s.ep);
+  cudaFree(e->s.hz); cudaFree(e->s.ep); cudaFree(e->s.fin);
   cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage); cudaFree(e->ctr);
   delete e;
   return GX_OK;
@@ -899,15 +913,24 @@ GX_API int gx_rollout(gx_env* e, int32_t T, float* obs, float* act, float* rewar
 GX_API int gx_stats_read(gx_env* e, double* out8, void* stream) {
   if (!e || !out8) return gx_fail(GX_EINVAL, "gx_stats_read: NULL argument");
   DeviceGuard guard(e->device);
-  GX_CUDA(cudaMemcpyAsync(out8, e->stats, sizeof(double) * 8, cudaMemcpyDefault, (cudaStream_t)stream));
+  cudaStream_t st = (cudaStream_t)stream;
+  gx_stats_reduce_kernel<<<1, 1024, 0, st>>>(e->s, e->p.n, e->stats_age0, e->stats);
+  GX_LAUNCH_CHECK("gx_stats_reduce_kernel");
+  GX_CUDA(cudaMemcpyAsync(out8, e->stats, sizeof(double) * 8, cudaMemcpyDefault, st));
   return GX_OK;
 }
 
 GX_API int gx_stats_reset(gx_env* e, void* stream) {
   if (!e) return gx_fail(GX_EINVAL, "gx_stats_reset: NULL env");
   DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
   e->stats_on = true;  // the first reset switches accumulation on
-  GX_CUDA(cudaMemsetAsync(e->stats, 0, sizeof(double) * 8, (cudaStream_t)stream));
+  GX_CUDA(cudaMemsetAsync(e->s.ep, 0, sizeof(float4) * e->s.cap, st));
+  GX_CUDA(cudaMemsetAsync(e->s.fin, 0, sizeof(float4) * 2 * (size_t)e->s.cap, st));
+  // total_env_steps counts from the env age at this moment (host sync: rare call)
+  uint64_t t = 0;
+  if (int rc = gx_get_counters(e, &t, nullptr, stream)) return rc;
+  e->stats_age0 = t;
   return GX_OK;
 }
 

@@ -39,6 +39,8 @@
 //   goal float2
 //   hz  float4[nh2][cap]   two hazards per float4, pair-major (coalesced per pair)
 //   ep  float4  ep_ret ep_cost ep_len cum_cost       (only touched when stats on)
+//   fin float4[2][cap]  per-env sums over FINISHED episodes: {n, ret, cost, len},
+//               {ret^2, cost^2, -, -}  (read-modify-written only on a done step)
 // Dynamic part 48 B, static part 8 + 8*nh B per env.
 // ---------------------------------------------------------------------------
 struct GxState {
@@ -48,6 +50,7 @@ struct GxState {
   float2* goal;
   float4* hz;
   float4* ep;
+  float4* fin;
   int cap;
   int nh2;  // ceil(nh / 2)
 };

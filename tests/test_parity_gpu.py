@@ -414,11 +414,13 @@ def test_episode_statistics_match_oracle(mods):
     g.stats_reset(); o.stats_reset()
     g.rollout(200); o.rollout(200)
     sg, so = cpu(g.stats()), o.stats()
-    assert sg[0] == so[0] and sg[3] == so[3] and sg[7] == so[7] and so[0] > n
-    np.testing.assert_allclose(sg, so, rtol=1e-9)
+    assert sg[0] == so[0] and sg[3] == so[3] and sg[7] == so[7] and so[0] > n   # counts: exact
+    # sums: per-env fp32 partials reduced in fp64 on the GPU vs serial fp64 in the oracle
+    np.testing.assert_allclose(sg, so, rtol=2e-6)
     a = np.zeros((n, 2), np.float32)
     g.step(torch.from_numpy(a).cuda()); o.step(a)
-    np.testing.assert_allclose(cpu(g.stats()), o.stats(), rtol=1e-9)
+    np.testing.assert_allclose(cpu(g.stats()), o.stats(), rtol=2e-6)
+    assert torch.equal(g.stats(), g.stats())   # deterministic reduction
 
 
 # ------------------------------------------------------- BASELINE full sizes
