@@ -127,7 +127,7 @@ PROTOTYPES = {
 }
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libguardx.so")
+LIB_PATH = os.environ.get("GX_LIB") or os.path.join(_HERE, "libguardx.so")  # GX_LIB: kernel-tuning builds
 _lib = None
 
 

@@ -17,6 +17,13 @@
 
 #define GX_API extern "C" __attribute__((visibility("default")))
 
+// Resident blocks per SM the one-thread-per-env step kernel is compiled for
+// (register cap = 65536 / (128 * this)).  ncu at 2^20 envs: 85 registers -> 5
+// blocks -> 20 warps/SM, issue slots 57 % busy, i.e. occupancy-limited.
+#ifndef GX_STEP_MIN_BLOCKS
+#define GX_STEP_MIN_BLOCKS 8
+#endif
+
 // ---------------------------------------------------------------------------
 // errors
 // ---------------------------------------------------------------------------
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(1024) gx_stats_reduce_kernel(const GxState s, 
 // the step's, the observation row of a done env is its reset observation (what
 // step() followed by reset_done() returns).
 template <int NH_CT, bool AUX, bool STATS, bool AUTORESET>
-__global__ void gx_step_kernel(const __grid_constant__ gx_params p, const GxState s,
+__global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const __grid_constant__ gx_params p, const GxState s,
                                const float* __restrict__ pool,
                                const float2* __restrict__ action, float* __restrict__ obs,
                                float* __restrict__ reward, float* __restrict__ done,
