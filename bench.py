@@ -107,6 +107,15 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def host_threads():
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the
+    oracle's OpenMP regions take an explicit thread count, so that does not bind)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def workload_config(n, world, how):
     return {"workload": f"{TASK}, {n} envs per GPU, random-action rollout (a ~ U(-1,1), pre-generated), "
                         "step + reset_done every step",
@@ -145,8 +154,7 @@ def oracle_steps_per_sec(n_envs, steps, warmup, threads):
 def reference_arm(args, rank, world):
     if rank != 0:
         return
-    from oracle.oracle import lib
-    threads = min(lib().gxo_max_threads(), os.cpu_count() or 1)
+    threads = host_threads()
     n = ENVS_PER_GPU * world
     rate, dt = oracle_steps_per_sec(n, args.steps, max(args.warmup, 3), threads)
     sample = f"{args.steps} steps x {n} envs, gxo_step + gxo_reset_done, actions pre-generated in host memory"
@@ -407,8 +415,7 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1:
-        from oracle.oracle import lib as olib
-        threads = min(olib().gxo_max_threads(), os.cpu_count() or 1)
+        threads = host_threads()
         rate, _ = oracle_steps_per_sec(n, 400, 20, threads)          # calibrate
         ks = int(max(400, min(12.0 * rate / n, 200000)))             # ~12 s of CPU work
         rate, d_cpu = oracle_steps_per_sec(n, ks, 20, threads)

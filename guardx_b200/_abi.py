@@ -77,6 +77,7 @@ class GxConfig(C.Structure):
         ("lidar_max_dist", C.c_double),
         ("lidar_exp_gain", C.c_double),
         ("goal_min_robot_dist", C.c_double),
+        ("opt_timestep", C.c_double),
         ("hazards_num", C.c_int32),
         ("lidar_num_bins", C.c_int32),
         ("lidar_alias", C.c_int32),

@@ -199,6 +199,7 @@ def lower(cfg: dict, env_id_offset: int = 0, pool_size: int = 0) -> _abi.GxConfi
     c.lidar_max_dist = 0.0 if cfg['lidar_max_dist'] is None else float(cfg['lidar_max_dist'])
     c.lidar_exp_gain = float(cfg['lidar_exp_gain'])
     c.goal_min_robot_dist = 3.0  # engine.py:571
+    c.opt_timestep = 0.02  # point.xml:3 (mj_model.opt.timestep is a double)
     c.hazards_num = int(cfg['hazards_num'])
     c.lidar_num_bins = int(cfg['lidar_num_bins'])
     c.lidar_alias = 1 if cfg['lidar_alias'] else 0

@@ -268,6 +268,11 @@ __global__ void gx_reset_kernel(const __grid_constant__ gx_params p, const GxSta
     d.steps = 0.0f;
     d.prev_dist = gx_reset_row<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, row);
     gx_kinematics(d.qth, d.hc, d.hs);  // mjx.forward at the reset pose (engine.py:655): R = I
+    if ((p.off_vel >= 0) | (p.off_acc >= 0)) {  // Engine._data.xpos <- reset pose; _last_data stays
+      float4 h = s.hx[i];
+      h.x = d.qx; h.y = d.qy;
+      s.hx[i] = h;
+    }
     gx_store_dyn(s, i, d);
     if (s.ep) s.ep[i] = make_float4(0.f, 0.f, 0.f, s.ep[i].w);
   }
@@ -576,6 +581,12 @@ __global__ void gx_get_state_kernel(const __grid_constant__ gx_params p, const G
     o[13 + 2 * h] = (h & 1) ? v.z : v.x;
     o[14 + 2 * h] = (h & 1) ? v.w : v.y;
   }
+  float* x = o + 13 + 2 * p.nh;
+  const float4 hx = s.hx[i];
+  const uint32_t hf = s.hf[i];
+  x[0] = hx.x; x[1] = hx.y; x[2] = hx.z; x[3] = hx.w;
+  x[4] = (hf & 1u) ? 1.0f : 0.0f;
+  x[5] = (float)((hf >> 1) & 3u);
 }
 
 __global__ void gx_set_state_kernel(const __grid_constant__ gx_params p, const GxState s, const float* in) {
@@ -595,6 +606,11 @@ __global__ void gx_set_state_kernel(const __grid_constant__ gx_params p, const G
     v.w = (2 * k + 1 < p.nh) ? o[16 + 4 * k] : 0.0f;
     s.hz[(size_t)k * s.cap + i] = v;
   }
+  const float* x = o + 13 + 2 * p.nh;
+  s.hx[i] = make_float4(x[0], x[1], x[2], x[3]);
+  int hist = (int)x[5];
+  hist = hist < 0 ? 0 : (hist > 2 ? 2 : hist);
+  s.hf[i] = (x[4] > 0.0f ? 1u : 0u) | ((uint32_t)hist << 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -667,6 +683,8 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   GX_ALLOC(s.hz, sizeof(float4) * (size_t)cap * s.nh2);
   GX_ALLOC(s.ep, sizeof(float4) * cap);
   GX_ALLOC(s.fin, sizeof(float4) * 2 * (size_t)cap);
+  GX_ALLOC(s.hx, sizeof(float4) * cap);
+  GX_ALLOC(s.hf, sizeof(uint32_t) * cap);
   GX_ALLOC(e->pool, sizeof(float) * (size_t)p.pool_size * p.lay_dim);
   GX_ALLOC(e->pool_tries, sizeof(int32_t) * (size_t)p.pool_size);
   GX_ALLOC(e->stats, sizeof(double) * 8);
@@ -688,7 +706,7 @@ GX_API int gx_destroy(gx_env* e) {
   if (!e) return GX_OK;
   DeviceGuard guard(e->device);
   cudaFree(e->s.d0); cudaFree(e->s.d1); cudaFree(e->s.d2); cudaFree(e->s.goal);
-  cudaFree(e->s.hz); cudaFree(e->s.ep); cudaFree(e->s.fin);
+  cudaFree(e->s.hz); cudaFree(e->s.ep); cudaFree(e->s.fin); cudaFree(e->s.hx); cudaFree(e->s.hf);
   cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage); cudaFree(e->ctr);
   delete e;
   return GX_OK;
@@ -710,6 +728,8 @@ GX_API int gx_obs_offset(const gx_env* e, uint32_t component) {
     case GX_OBS_HAZARDS_LIDAR: return e->p.off_hlidar;
     case GX_OBS_QPOS: return e->p.off_qpos;
     case GX_OBS_QVEL: return e->p.off_qvel;
+    case GX_OBS_ACC: return e->p.off_acc;
+    case GX_OBS_VEL: return e->p.off_vel;
     default: return -1;
   }
 }

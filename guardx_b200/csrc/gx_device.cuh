@@ -39,6 +39,7 @@
 //   goal float2
 //   hz  float4[nh2][cap]   two hazards per float4, pair-major (coalesced per pair)
 //   ep  float4  ep_ret ep_cost ep_len cum_cost       (only touched when stats on)
+//   hx, hf      history read by ego_vel_acc only (observe_vel / observe_acc, default off)
 //   fin float4[2][cap]  per-env sums over FINISHED episodes: {n, ret, cost, len},
 //               {ret^2, cost^2, -, -}  (read-modify-written only on a done step)
 // Dynamic part 48 B, static part 8 + 8*nh B per env.
@@ -51,6 +52,8 @@ struct GxState {
   float4* hz;
   float4* ep;
   float4* fin;
+  float4* hx;     // xpos_xy of Engine._data, xpos_xy of Engine._last_data  (observe_vel/acc only)
+  uint32_t* hf;   // bit 0: Engine._last_done, bits 1-2: history depth       (observe_vel/acc only)
   int cap;
   int nh2;  // ceil(nh / 2)
 };
@@ -230,6 +233,10 @@ __device__ __forceinline__ GxObsOut gx_obs_row(const gx_params& p, const GxState
   GxObsOut o;
   o.bad = 0;
   const int nb = p.nb;
+  // vel / acc default to 0 = obs(data, None, None, None, None) (engine.py:656, 726);
+  // gx_vel_acc overwrites them on a step
+  if (p.off_acc >= 0) { row[p.off_acc] = 0.0f; row[p.off_acc + 1] = 0.0f; }
+  if (p.off_vel >= 0) { row[p.off_vel] = 0.0f; row[p.off_vel + 1] = 0.0f; }
   if (p.off_ctrl >= 0) {
     row[p.off_ctrl + 0] = c0; row[p.off_ctrl + 1] = c1; row[p.off_ctrl + 2] = c2;
     o.bad |= gx_notfinite(c0) | gx_notfinite(c1) | gx_notfinite(c2);
@@ -302,6 +309,39 @@ __device__ __forceinline__ GxObsOut gx_obs_row(const gx_params& p, const GxState
   return o;
 }
 
+// ego_vel_acc (engine.py:902-929): finite-difference velocity / acceleration of
+// the robot xpos in the robot frame, with the done-masking and the None-ness of
+// last_done / last_last_done on the first two steps.  Also performs update_data's
+// history shift for these fields (engine.py:426-430).  Returns the NaN/Inf flag.
+__device__ __forceinline__ int gx_vel_acc(const gx_params& p, const GxState& s, int i, float px, float py,
+                                          float r00, float r10, float last_done, float* row) {
+  const float4 h = s.hx[i];
+  const uint32_t f = s.hf[i];
+  const float last_last_done = (f & 1u) ? 1.0f : 0.0f;
+  const int hist = (int)((f >> 1) & 3u);
+  const float lx = h.x, ly = h.y;  // last_data.xpos (the data this step started from)
+  const float llx = hist >= 2 ? h.z : lx, lly = hist >= 2 ? h.w : ly;
+  float plx = px, ply = py, pllx = px, plly = py;
+  if (hist >= 1) {
+    if (!(last_done > 0.0f)) { plx = lx; ply = ly; }
+    if (hist >= 2) {
+      if (last_last_done + last_done > 0.0f) { pllx = plx; plly = ply; }
+      else { pllx = llx; plly = lly; }
+    }
+  }
+  const float vwx = gx_div(px - plx, p.ctrl_dt), vwy = gx_div(py - ply, p.ctrl_dt);
+  const float lvx = gx_div(plx - pllx, p.ctrl_dt), lvy = gx_div(ply - plly, p.ctrl_dt);
+  const float awx = gx_div(vwx - lvx, p.ctrl_dt), awy = gx_div(vwy - lvy, p.ctrl_dt);
+  const float vx = vwx * r00 + vwy * r10, vy = vwx * (-r10) + vwy * r00;
+  const float ax = awx * r00 + awy * r10, ay = awx * (-r10) + awy * r00;
+  int bad = 0;
+  if (p.off_acc >= 0) { row[p.off_acc] = ax; row[p.off_acc + 1] = ay; bad |= gx_notfinite(ax) | gx_notfinite(ay); }
+  if (p.off_vel >= 0) { row[p.off_vel] = vx; row[p.off_vel + 1] = vy; bad |= gx_notfinite(vx) | gx_notfinite(vy); }
+  s.hx[i] = make_float4(px, py, lx, ly);
+  s.hf[i] = (last_done > 0.0f ? 1u : 0u) | ((uint32_t)(hist < 2 ? hist + 1 : 2) << 1);
+  return bad;
+}
+
 struct GxStepOut {
   float reward, done, cost;
   int flags, violations;
@@ -319,6 +359,7 @@ __device__ __forceinline__ GxStepOut gx_step_env(const gx_params& p, const GxSta
   float px, py, r00, r10;
   for (int k = 0; k < p.substeps; ++k) gx_mjx_step_point(p, d, c0, c1, c2, px, py, r00, r10, qacc);
   GxObsOut o = gx_obs_row<NH_CT>(p, s, i, gx_, gy_, hz_regs, d, c0, c1, c2, px, py, r00, r10, row, aux_bins);
+  if ((p.off_vel >= 0) | (p.off_acc >= 0)) o.bad |= gx_vel_acc(p, s, i, px, py, r00, r10, last_done, row);
   // reward_done (engine.py:787-802)
   float dist = o.dist_goal;
   float last = last_done > 0.0f ? dist : last_dist;

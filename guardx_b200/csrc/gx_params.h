@@ -15,8 +15,9 @@ enum { GX_CLS_GOAL = 0, GX_CLS_HAZARD = 1, GX_CLS_ROBOT = 2 };
 typedef struct gx_params {
   int32_t n, nh, nb, obs_dim;
   int32_t substeps, alias, use_exp, tries;
-  int32_t off_ctrl, off_compass, off_glidar, off_hlidar, off_qpos, off_qvel;
+  int32_t off_ctrl, off_compass, off_glidar, off_hlidar, off_qpos, off_qvel, off_acc, off_vel;
   int32_t lay_dim, state_dim, aux_dim, pool_size;
+  float ctrl_dt;         /* float32(self.dt), divides the finite differences  engine.py:235, 916-923 */
   float num_steps;       /* `self._steps > self.num_steps`, fp32 compare  engine.py:492 */
   float goal_size;       /* engine.py:798 */
   float hazards_size;    /* engine.py:809-810 */
@@ -56,7 +57,6 @@ static inline const char* gx_lower_config(const gx_config* c, gx_params* p) {
     return "lidar_num_bins out of range";
   if (c->physics_steps_per_control_step < 1) return "physics_steps_per_control_step < 1";
   if (c->layout_tries < 1 || c->layout_tries > 255) return "layout_tries out of range";
-  if (c->obs_mask & (GX_OBS_ACC | GX_OBS_VEL)) return "observe_vel / observe_acc not implemented";
   if (c->pool_size < 0) return "pool_size < 0";
   p->n = c->env_num; p->nh = c->hazards_num; p->nb = c->lidar_num_bins;
   p->substeps = c->physics_steps_per_control_step;
@@ -65,18 +65,24 @@ static inline const char* gx_lower_config(const gx_config* c, gx_params* p) {
   p->tries = c->layout_tries;
   int off = 0;
   p->off_ctrl = p->off_compass = p->off_glidar = p->off_hlidar = p->off_qpos = p->off_qvel = -1;
+  p->off_acc = p->off_vel = -1;
+  /* sorted key order (engine.py:775): acc ctrl goal_compass goal_lidar hazards_lidar qpos qvel vel */
+  if (c->obs_mask & GX_OBS_ACC) { p->off_acc = off; off += 2; }
   if (c->obs_mask & GX_OBS_CTRL) { p->off_ctrl = off; off += 3; }
   if (c->obs_mask & GX_OBS_GOAL_COMPASS) { p->off_compass = off; off += 2; }
   if (c->obs_mask & GX_OBS_GOAL_LIDAR) { p->off_glidar = off; off += p->nb; }
   if (c->obs_mask & GX_OBS_HAZARDS_LIDAR) { p->off_hlidar = off; off += p->nb; }
   if (c->obs_mask & GX_OBS_QPOS) { p->off_qpos = off; off += 3; }
   if (c->obs_mask & GX_OBS_QVEL) { p->off_qvel = off; off += 3; }
+  if (c->obs_mask & GX_OBS_VEL) { p->off_vel = off; off += 2; }
   if (off == 0) return "empty observation";
   p->obs_dim = off;
   p->lay_dim = 2 * (2 + p->nh);
-  p->state_dim = 13 + 2 * p->nh;
+  p->state_dim = 19 + 2 * p->nh;
   p->aux_dim = 3 + p->nh;
   p->pool_size = c->pool_size > 0 ? c->pool_size : gx_auto_pool_size(c->env_num);
+  /* self.dt = mj_model.opt.timestep (a double) * physics_steps_per_control_step (engine.py:235) */
+  p->ctrl_dt = (float)(c->opt_timestep * (double)c->physics_steps_per_control_step);
   p->num_steps = (float)c->num_steps;
   p->goal_size = (float)c->goal_size;
   p->hazards_size = (float)c->hazards_size;
@@ -133,6 +139,7 @@ static inline void gx_fill_default_config(gx_config* c) {
   c->robot_keepout = 0.4; c->goal_keepout = 0.5; c->hazards_keepout = 0.4;
   c->goal_size = 0.5; c->hazards_size = 0.3; c->reward_distance = 1.0;
   c->lidar_max_dist = 0.0; c->lidar_exp_gain = 1.0; c->goal_min_robot_dist = 3.0;
+  c->opt_timestep = 0.02;
   c->hazards_num = 8; c->lidar_num_bins = 16; c->lidar_alias = 1;
   c->physics_steps_per_control_step = 1; c->layout_tries = 10; c->pool_size = 0;
   c->obs_mask = GX_OBS_DEFAULT; c->reserved = 0;

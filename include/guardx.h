@@ -110,6 +110,7 @@ typedef struct gx_config {
   double lidar_max_dist;          /* engine.py:150; <= 0 means None (exponential lidar) */
   double lidar_exp_gain;          /* engine.py:151 */
   double goal_min_robot_dist;     /* the literal 3.0 at engine.py:571 */
+  double opt_timestep;            /* mj_model.opt.timestep as a double (point.xml:3); Engine.dt = this * substeps, engine.py:235 */
   int32_t hazards_num;            /* engine.py:195, 1..GX_MAX_HAZARDS */
   int32_t lidar_num_bins;         /* engine.py:148, 1..GX_MAX_LIDAR_BINS */
   int32_t lidar_alias;            /* engine.py:153 */
@@ -196,7 +197,10 @@ int gx_reset_done(gx_env* env, const float* obs_in, float* obs_out, const float*
 /* ---- state injection / checkpoint (no reference counterpart: the reference
  *      state is the mjx.Data pytree held in Engine._data).  One row per env:
  *      qpos[3] qvel[3] lag_cos lag_sin prev_dist prev_done steps goal[2]
- *      hazards[2*hazards_num]; gx_state_dim() floats per row. --------------- */
+ *      hazards[2*hazards_num], then the history that only observe_vel /
+ *      observe_acc read (engine.py:902-929): xpos_xy of Engine._data, xpos_xy of
+ *      Engine._last_data, Engine._last_done, history depth (0,1,2 = how many of
+ *      _last_done/_last_last_done are not None).  gx_state_dim() floats per row. */
 int gx_state_dim(const gx_env* env);
 int gx_get_state(gx_env* env, float* state, void* stream);
 int gx_set_state(gx_env* env, const float* state, void* stream);

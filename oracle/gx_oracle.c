@@ -72,6 +72,10 @@ typedef struct {
   /* Engine-level history (engine.py:426-431, 489-493) */
   float last_dist_goal; /* goal_pos(last_data), i.e. of the forward before the last */
   float done;           /* Engine._done  */
+  /* history only ego_vel_acc reads (engine.py:902-929) */
+  float last_xpos[2];   /* Engine._last_data.xpos[robot] */
+  float last_done;      /* Engine._last_done */
+  int hist;             /* 0: _done is None (no step yet); 1: _last_done is None; 2: neither */
   float steps;          /* Engine._steps (fp32 in the reference, engine.py:463) */
   /* episode accumulators (host side of ppo_train.py:370-376) */
   float ep_ret, ep_cost;
@@ -207,6 +211,33 @@ static int obs_lidar_one(const gx_params* p, const gxo_world* d, const float pos
   return bin;
 }
 
+/* ego_vel_acc (engine.py:902-929).  cur/last/last_last are robot xpos xy of
+   data / last_data / last_last_data; have_last / have_last_last say whether
+   last_done / last_last_done are not None. */
+static void ego_vel_acc(const gx_params* p, const gxo_world* d, const float cur[2], const float last[2],
+                        const float last_last[2], int have_last, int have_last_last, float last_done,
+                        float last_last_done, float vel[2], float acc[2]) {
+  float pl[2] = {cur[0], cur[1]}, pll[2] = {cur[0], cur[1]};
+  if (have_last) {
+    if (!(last_done > 0.0f)) { pl[0] = last[0]; pl[1] = last[1]; }
+    if (have_last_last) {
+      if (last_last_done + last_done > 0.0f) { pll[0] = pl[0]; pll[1] = pl[1]; }
+      else { pll[0] = last_last[0]; pll[1] = last_last[1]; }
+    }
+  }
+  float vw[2], lvw[2], aw[2];
+  for (int k = 0; k < 2; ++k) {
+    vw[k] = gx_div(cur[k] - pl[k], p->ctrl_dt);
+    lvw[k] = gx_div(pl[k] - pll[k], p->ctrl_dt);
+    aw[k] = gx_div(vw[k] - lvw[k], p->ctrl_dt);
+  }
+  /* matmul(vec, robot_mat)[:2]; the z component of the differences is exactly 0 */
+  vel[0] = vw[0] * d->xmat[0][0] + vw[1] * d->xmat[1][0];
+  vel[1] = vw[0] * d->xmat[0][1] + vw[1] * d->xmat[1][1];
+  acc[0] = aw[0] * d->xmat[0][0] + aw[1] * d->xmat[1][0];
+  acc[1] = aw[0] * d->xmat[0][1] + aw[1] * d->xmat[1][1];
+}
+
 /* goal_pos (engine.py:780-785) */
 static float goal_pos(const gxo_world* d) {
   float dx = d->goal[0] - d->xpos[0], dy = d->goal[1] - d->xpos[1];
@@ -214,8 +245,12 @@ static float goal_pos(const gxo_world* d) {
 }
 
 /* Engine.obs (engine.py:738-778): flat concat in sorted key order. */
-static void engine_obs(const gx_params* p, const gxo_world* d, float* obs, int32_t* bins) {
+static void engine_obs(const gx_params* p, const gxo_world* d, float* obs, int32_t* bins,
+                       const float* vel, const float* acc) {
   for (int i = 0; i < p->obs_dim; ++i) obs[i] = 0.0f;
+  /* vel / acc default to 0: obs(data, None, None, None, None) (engine.py:656, 726) */
+  if (p->off_acc >= 0 && acc) { obs[p->off_acc] = acc[0]; obs[p->off_acc + 1] = acc[1]; }
+  if (p->off_vel >= 0 && vel) { obs[p->off_vel] = vel[0]; obs[p->off_vel + 1] = vel[1]; }
   if (p->off_ctrl >= 0)
     for (int i = 0; i < 3; ++i) obs[p->off_ctrl + i] = d->ctrl[i];
   if (p->off_compass >= 0) ego_xy(d, d->goal, obs + p->off_compass);
@@ -267,10 +302,21 @@ static void engine_step_one(const gx_params* p, gxo_world* d, const float* actio
   /* update_data (engine.py:426-431): last_data <- data, last_done <- done */
   float last_dist = d->last_dist_goal; /* goal_pos(last_data) uses last_data.xpos */
   float last_done = d->done;
+  const float last_last_done = d->last_done;
+  const float x_last[2] = {d->xpos[0], d->xpos[1]};           /* last_data <- data */
+  const float x_last_last[2] = {d->last_xpos[0], d->last_xpos[1]}; /* last_last_data <- last_data */
+  const int hist = d->hist;
   /* lax.scan(mjx.step, n) (engine.py:689) */
   for (int k = 0; k < p->substeps; ++k) mjx_step_point(p, d);
   int32_t bins[1 + GX_MAX_HAZARDS];
-  engine_obs(p, d, obs, bins);
+  float vel[2], acc[2];
+  {
+    const float cur[2] = {d->xpos[0], d->xpos[1]};
+    /* obs(): last_last_data = last_data when it is None (engine.py:749-750) */
+    ego_vel_acc(p, d, cur, x_last, hist >= 2 ? x_last_last : x_last, hist >= 1, hist >= 2, last_done,
+                last_last_done, vel, acc);
+  }
+  engine_obs(p, d, obs, bins, vel, acc);
   /* reward_done (engine.py:787-802) */
   float dist = goal_pos(d);
   float last = last_done > 0.0f ? dist : last_dist;
@@ -290,6 +336,9 @@ static void engine_step_one(const gx_params* p, gxo_world* d, const float* actio
   d->steps = dn > 0.0f ? 0.0f : d->steps + 1.0f;
   d->done = dn;
   d->last_dist_goal = dist; /* this data becomes last_data on the next call */
+  d->last_xpos[0] = x_last[0]; d->last_xpos[1] = x_last[1];
+  d->last_done = last_done;
+  d->hist = hist < 2 ? hist + 1 : 2;
   *reward = r; *done = dn; *cost = c;
   if (qacc) { qacc[0] = d->qacc[0]; qacc[1] = d->qacc[1]; qacc[2] = d->qacc[2]; }
   if (aux) {
@@ -389,7 +438,7 @@ static void mjx_reset_one(const gxo_env* e, gxo_world* d, const float* lay, floa
   layout2qpos(e, d, lay);
   for (int i = 0; i < 3; ++i) { d->qvel[i] = 0.0f; d->ctrl[i] = 0.0f; d->qacc[i] = 0.0f; }
   mjx_kinematics(&e->p, d->qpos, d->xpos, d->xmat);
-  engine_obs(&e->p, d, obs, NULL);
+  engine_obs(&e->p, d, obs, NULL, NULL, NULL);
   d->last_dist_goal = goal_pos(d);
 }
 
@@ -401,7 +450,7 @@ static void mjx_reset_done_one(const gxo_env* e, gxo_world* d, const float* lay,
   for (int i = 0; i < 3; ++i) { d->qvel[i] = 0.0f; d->ctrl[i] = 0.0f; }
   gxo_world tmp = *d;
   for (int k = 0; k < e->p.substeps; ++k) mjx_step_point(&e->p, &tmp);
-  engine_obs(&e->p, &tmp, obs, NULL);
+  engine_obs(&e->p, &tmp, obs, NULL, NULL, NULL);
   /* d->xpos / d->xmat / d->last_dist_goal deliberately untouched */
 }
 
@@ -527,6 +576,12 @@ GXO_API int gxo_get_state(gxo_env* e, float* state) {
     s[6] = w->xmat[0][0]; s[7] = w->xmat[1][0]; s[8] = w->last_dist_goal; s[9] = w->done;
     s[10] = w->steps; s[11] = w->goal[0]; s[12] = w->goal[1];
     for (int h = 0; h < e->nh; ++h) { s[13 + 2 * h] = w->hazards[h][0]; s[14 + 2 * h] = w->hazards[h][1]; }
+    float* x = s + 13 + 2 * e->nh;
+    /* the history columns are only kept (and only meaningful) with observe_vel / observe_acc */
+    const int va = e->p.off_vel >= 0 || e->p.off_acc >= 0;
+    x[0] = va ? w->xpos[0] : 0.0f; x[1] = va ? w->xpos[1] : 0.0f;
+    x[2] = va ? w->last_xpos[0] : 0.0f; x[3] = va ? w->last_xpos[1] : 0.0f;
+    x[4] = va ? w->last_done : 0.0f; x[5] = va ? (float)w->hist : 0.0f;
   }
   return GX_OK;
 }
@@ -538,7 +593,9 @@ GXO_API int gxo_set_state(gxo_env* e, const float* state) {
     const float* s = state + (size_t)i * sd;
     for (int k = 0; k < 3; ++k) { w->qpos[k] = s[k]; w->qvel[k] = s[3 + k]; }
     w->xmat[0][0] = s[6]; w->xmat[1][0] = s[7]; w->xmat[0][1] = -s[7]; w->xmat[1][1] = s[6];
-    w->xpos[0] = w->xpos[1] = 0.0f; w->xpos[2] = e->p.body_z;
+    const float* x = s + 13 + 2 * e->nh;
+    w->xpos[0] = x[0]; w->xpos[1] = x[1]; w->xpos[2] = e->p.body_z;
+    w->last_xpos[0] = x[2]; w->last_xpos[1] = x[3]; w->last_done = x[4]; w->hist = (int)x[5];
     w->last_dist_goal = s[8]; w->done = s[9]; w->steps = s[10];
     w->goal[0] = s[11]; w->goal[1] = s[12];
     for (int h = 0; h < e->nh; ++h) { w->hazards[h][0] = s[13 + 2 * h]; w->hazards[h][1] = s[14 + 2 * h]; }
@@ -641,6 +698,17 @@ GXO_API int gxo_piece_reward_done(const gx_config* cfg, const float* robot_xy, c
   float dn = dist < p.goal_size ? 1.0f : 0.0f;
   if (gx_abs(d_dist) > 1.0f) { dn = 1.0f; r = 0.0f; }
   *reward = r; *done = dn;
+  return GX_OK;
+}
+/* ego_vel_acc (engine.py:902-929); have: 0 = last_done None, 1 = last_last_done None, 2 = neither */
+GXO_API int gxo_piece_vel_acc(const gx_config* cfg, const float* xmat9, const float* cur, const float* last,
+                              const float* last_last, int have, float last_done, float last_last_done,
+                              float* vel, float* acc) {
+  gx_params p; memset(&p, 0, sizeof p);
+  if (gx_lower_config(cfg, &p)) return GX_EINVAL;
+  const float x3[3] = {cur[0], cur[1], 0.1f};
+  gxo_world d; world_from_pose(&d, x3, xmat9);
+  ego_vel_acc(&p, &d, cur, last, last_last, have >= 1, have >= 2, last_done, last_last_done, vel, acc);
   return GX_OK;
 }
 /* cost (engine.py:804-811) */

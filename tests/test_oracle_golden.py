@@ -116,6 +116,35 @@ def test_sample_layout_against_reference_source(oracle_lib, golden_dir, tag):
     assert n_ok >= 5
 
 
+def test_ego_vel_acc_against_reference_source(oracle_lib, golden_dir):
+    """engine.py:902-929 incl. the None-ness of last_done / last_last_done on the first
+    two steps, and the sorted-key position of acc (first) and vel (last) in the flat obs."""
+    g = np.load(os.path.join(golden_dir, "refsrc_velacc.npz"))
+    assert [str(k) for k in g['obs_keys']] == ['acc', 'ctrl', 'goal_compass', 'goal_lidar', 'hazards_lidar',
+                                                'qpos', 'qvel', 'vel']
+    cfg = gxconfig.lower(gxconfig.parse({'observe_vel': True, 'observe_acc': True}))
+    n = g['flat'].shape[0]
+    assert g['flat'].shape[1] == 47
+    seen = set()
+    for i in range(n):
+        vel, acc = np.zeros(2, np.float32), np.zeros(2, np.float32)
+        f = lambda k: np.ascontiguousarray(g[k][i], np.float32)
+        have = int(g['have'][i])
+        ll = f('last_last') if have == 2 else f('last')
+        assert oracle_lib.gxo_piece_vel_acc(C.byref(cfg), _p(_xmat9(g['cs'][i])), _p(f('cur')), _p(f('last')), _p(ll),
+                                            have, C.c_float(float(g['last_done'][i])),
+                                            C.c_float(float(g['last_last_done'][i])), _p(vel), _p(acc)) == 0
+        # finite differences divide by dt twice: |acc| ~ 1e2, so the tolerance is relative
+        np.testing.assert_allclose(vel, g['vel'][i], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(acc, g['acc'][i], rtol=2e-5, atol=2e-3)
+        np.testing.assert_array_equal(g['flat'][i][:2], g['acc'][i])
+        np.testing.assert_array_equal(g['flat'][i][-2:], g['vel'][i])
+        if have == 0:
+            assert (vel == 0).all() and (acc == 0).all()
+        seen.add(have)
+    assert seen == {0, 1, 2}
+
+
 def test_default_keys_match_reference(golden_dir):
     with open(os.path.join(golden_dir, "engine_default.json")) as f:
         ref = json.load(f)

@@ -231,7 +231,7 @@ def test_reward_is_zero_after_reset_and_lags_one_step(mods):
     assert (np.abs(cpu(r2)) > 0).any()
     o.step(a); _, r2o, _, _ = o.step(a)
     bits_equal(cpu(r2), r2o, "lagged reward")
-    assert s_before.shape == (32, 13 + 16)
+    assert s_before.shape == (32, 19 + 16)
 
 
 # ----------------------------------------------------------- fused rollout
@@ -282,6 +282,8 @@ VARIANTS = [
     {'observe_ctrl': False, 'observe_qvel': False, 'observe_goal_lidar': False},
     {'observe_hazards': False, 'observe_goal_comp': False, 'hazards_num': 1, 'lidar_num_bins': 1},
     {'hazards_num': 32, 'hazards_keepout': 0.12, 'hazards_size': 0.1, 'lidar_num_bins': 64},
+    {'observe_vel': True, 'observe_acc': True},                                  # ego_vel_acc, engine.py:902-929
+    {'observe_vel': True, 'observe_qpos': False, 'hazards_num': 4, 'physics_steps_per_control_step': 2},
 ]
 
 
@@ -308,6 +310,11 @@ def test_non_default_configs(mods, variant):
     rg, ro = g.rollout(40), o.rollout(40)
     for k in ("obs", "reward", "cost", "done", "act"):
         bits_equal(cpu(rg[k]), ro[k], f"rollout {k}")
+    bits_equal(cpu(g.get_state()), o.get_state(), "state incl. history columns")
+    # reset() leaves the history stale, exactly like the reference (engine.py:454-467)
+    bits_equal(cpu(g.reset()), o.reset(), "second reset")
+    a = rng.uniform(-1, 1, (77, 2)).astype(np.float32)
+    bits_equal(cpu(g.step(torch.from_numpy(a).cuda())[0]), o.step(a)[0], "step after second reset")
 
 
 def test_nan_inf_actions_trip_the_guard(mods):
@@ -372,7 +379,7 @@ def test_golden_reference_source_vectors_through_cuda(mods, golden_dir):
     s = cpu(g.get_state())
     s[:, 0:2] = gold['robot']; s[:, 2] = gold['qpos'][:, 2]; s[:, 3:6] = 0
     s[:, 6] = 1; s[:, 7] = 0; s[:, 8] = 0; s[:, 9] = 1; s[:, 10] = 0
-    s[:, 11:13] = gold['goal']; s[:, 13:] = gold['hazards'].reshape(n, -1)
+    s[:, 11:13] = gold['goal']; s[:, 13:29] = gold['hazards'].reshape(n, -1)
     g.set_state(torch.from_numpy(s).cuda())
     obs, r, d, info = g.step(torch.zeros(n, 2, device='cuda'), want_aux=True)
     obs = cpu(obs)

@@ -141,6 +141,39 @@ def gen_obs_cases(Engine, shim, config, n_random, rng, tag):
     print(path, res['flat'].shape)
 
 
+def gen_velacc_cases(Engine, shim, n, rng):
+    """ego_vel_acc (engine.py:902-929) on random pose histories, for the three None-ness
+    states of (last_done, last_last_done) the Engine goes through on its first steps."""
+    eng = make_engine(Engine, {'observe_vel': True, 'observe_acc': True})
+    nh = eng.hazards_num
+    out = {k: [] for k in ('cs', 'cur', 'last', 'last_last', 'have', 'last_done', 'last_last_done', 'vel', 'acc', 'flat')}
+    z3 = np.zeros(3)
+    for k in range(n):
+        th = rng.uniform(-10, 10)
+        cs = (np.float32(np.cos(th)), np.float32(np.sin(th)))
+        cur = rng.uniform(-2, 2, 2)
+        last = cur - rng.uniform(-0.06, 0.06, 2)
+        ll = last - rng.uniform(-0.06, 0.06, 2)
+        have = k % 3
+        ld, lld = float(rng.random() < 0.25), float(rng.random() < 0.25)
+        goal, haz = rng.uniform(-2, 2, 2), rng.uniform(-2, 2, (nh, 2))
+        mk = lambda xy: fake_data(shim, xy, cs, goal, haz, np.r_[xy, th], z3, z3, z3)
+        data, ldata, lldata = mk(cur), mk(last), mk(ll)
+        W = lambda v: shim._wrap(np.float32(v))
+        a_ld = None if have == 0 else W(ld)
+        a_lld = None if have <= 1 else W(lld)
+        vel, acc = eng.ego_vel_acc(data, ldata, lldata if have == 2 else ldata, a_ld, a_lld)
+        flat, _ = eng.obs(data, ldata, lldata if have == 2 else None, a_ld, a_lld)
+        out['cs'].append(cs); out['cur'].append(cur); out['last'].append(last); out['last_last'].append(ll)
+        out['have'].append(have); out['last_done'].append(ld); out['last_last_done'].append(lld)
+        out['vel'].append(np.asarray(vel)); out['acc'].append(np.asarray(acc)); out['flat'].append(np.asarray(flat))
+    res = {k: np.asarray(v, np.float32) for k, v in out.items()}
+    res['obs_keys'] = np.array(sorted(eng.obs_space_dict.keys()))
+    path = os.path.join(ROOT, 'tests', 'golden', 'refsrc_velacc.npz')
+    np.savez_compressed(path, **res)
+    print(path, res['flat'].shape)
+
+
 def gen_layout_cases(Engine, shim, config, n, tag):
     eng = make_engine(Engine, config)
     import jax
@@ -166,6 +199,7 @@ def main():
                'goal_size': 0.3, 'hazards_size': 0.2, 'reward_distance': 2.0}
     gen_obs_cases(Engine, shim, default, 400, rng, 'default')
     gen_obs_cases(Engine, shim, variant, 200, rng, 'variant')
+    gen_velacc_cases(Engine, shim, 300, rng)
     gen_layout_cases(Engine, shim, default, 600, 'default')
     gen_layout_cases(Engine, shim, {'hazards_num': 5, 'hazards_keepout': 0.25, 'goal_keepout': 0.35,
                                     'robot_keepout': 0.3, 'placements_margin': 0.05,
