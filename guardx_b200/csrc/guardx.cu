@@ -1018,3 +1018,39 @@ GX_API int gx_debug_math(int fn, const float* a, const float* b, float* out, flo
   GX_LAUNCH_CHECK("gx_debug_math_kernel");
   return GX_OK;
 }
+
+// ---- GAE-lambda / rewards-to-go (ppo_train.py:61-113) --------------------------
+// One thread per env walks the T steps backwards; consecutive threads read
+// consecutive envs of the time-major buffers, so every access is coalesced.
+// 12 B read + 8 B written per (t, env): a pure HBM stream.
+__global__ void gx_gae_kernel(const float* __restrict__ reward, const float* __restrict__ value,
+                              const float* __restrict__ done, const float* __restrict__ last_value, int T,
+                              int n, float gamma_f, double gamma, double gl, float* __restrict__ adv,
+                              float* __restrict__ ret) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v_next = last_value ? last_value[i] : 0.0f;
+  double a = 0.0, r = (double)v_next;  // discount_cumsum(rews + [last_val])[:-1]
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t k = (size_t)t * n + i;
+    const float rew = reward[k], v = value[k];
+    const bool closed = done[k] > 0.0f;
+    if (closed) { v_next = 0.0f; a = 0.0; r = 0.0; }
+    const float delta = __fsub_rn(__fadd_rn(rew, __fmul_rn(gamma_f, v_next)), v);
+    a = __dadd_rn((double)delta, __dmul_rn(gl, a));
+    r = __dadd_rn((double)rew, __dmul_rn(gamma, r));
+    adv[k] = (float)a;
+    ret[k] = (float)r;
+    v_next = v;
+  }
+}
+
+GX_API int gx_gae(const float* reward, const float* value, const float* done, const float* last_value,
+                  int32_t T, int32_t n, double gamma, double lam, float* adv, float* ret, void* stream) {
+  if (!reward || !value || !done || !adv || !ret || T < 0 || n < 0) return gx_fail(GX_EINVAL, "gx_gae: bad argument");
+  if (T == 0 || n == 0) return GX_OK;
+  gx_gae_kernel<<<div_up(n, 128), 128, 0, (cudaStream_t)stream>>>(reward, value, done, last_value, T, n,
+                                                                  (float)gamma, gamma, gamma * lam, adv, ret);
+  GX_LAUNCH_CHECK("gx_gae_kernel");
+  return GX_OK;
+}

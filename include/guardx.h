@@ -246,6 +246,20 @@ int gx_stats_reset(gx_env* env, void* stream);
 int gx_step_host(gx_env* env, const float* h_action, float* h_obs, float* h_reward,
                  float* h_done, float* h_cost, int32_t auto_reset_done, void* stream);
 
+/* ---- rollout-side op: GAE-lambda advantages and rewards-to-go
+ *      over a time-major rollout, replacing PPOBufferX.finish_path
+ *      (safe_rl_libX/ppo/ppo_train.py:61-113: a per-env Python loop over
+ *      scipy.signal.lfilter with .cpu() round trips) by one streaming kernel.
+ *      reward, value, done: [T, n] (done[t] = 1 closes a path AFTER step t; the
+ *      reference bootstraps every closed path and the epoch end with 0,
+ *      ppo_train.py:388-409, so V(s_T) = last_value or 0 when NULL).
+ *        delta_t = (r_t + gamma * V_{t+1} * (1 - done_t)) - V_t        (fp32)
+ *        adv_t   = delta_t + gamma*lam * adv_{t+1} * (1 - done_t)      (fp64 scan, as lfilter)
+ *        ret_t   = r_t + gamma * ret_{t+1} * (1 - done_t)              (fp64 scan)
+ *      adv, ret: [T, n] fp32.  No env handle: works on any buffers. ---------- */
+int gx_gae(const float* reward, const float* value, const float* done, const float* last_value,
+           int32_t T, int32_t n, double gamma, double lam, float* adv, float* ret, void* stream);
+
 /* ---- diagnostics: evaluate the shared fp32 math (csrc/gx_math.h) on the
  *      device, so tests can prove host/device bit-equality of the header.
  *      fn: 0 sincos(a)->out,out2   1 atan2(a,b)->out   2 exp(a)->out

@@ -758,3 +758,45 @@ GXO_API int gxo_sample_layout(const gx_config* cfg, uint32_t k0, uint32_t k1, ui
   if (gx_lower_config(cfg, &p)) return GX_EINVAL;
   return sample_layout(&p, k0, k1, slot, attempt, out);
 }
+
+/* ---- PPOBufferX.finish_path (safe_rl_libX/ppo/ppo_train.py:61-113) restated:
+   per env, per path slice [start, end) closed by done (or by the epoch end),
+   deltas in fp32, discount_cumsum as scipy.signal.lfilter does it (fp64 direct
+   form), rewards-to-go over rews + [last_val] with the last element dropped.
+   Time-major [T, n] buffers. */
+static void discount_cumsum_rev(const double* x, int len, double discount, double* y) {
+  double acc = 0.0; /* lfilter([1],[1,-discount], x[::-1])[::-1] */
+  for (int k = len - 1; k >= 0; --k) { acc = x[k] + discount * acc; y[k] = acc; }
+}
+GXO_API int gxo_gae(const float* reward, const float* value, const float* done, const float* last_value,
+                    int T, int n, double gamma, double lam, float* adv, float* ret) {
+  double* x = (double*)malloc(sizeof(double) * (size_t)(T + 1) * 2);
+  double* y = x + (T + 1);
+  const float gf = (float)gamma;
+  for (int i = 0; i < n; ++i) {
+    int start = 0;
+    for (int t = 0; t < T; ++t) {
+      const int closed = done[(size_t)t * n + i] > 0.0f;
+      if (!closed && t != T - 1) continue;
+      const int end = t + 1, len = end - start;
+      const float lv = closed ? 0.0f : (last_value ? last_value[i] : 0.0f);
+      for (int k = 0; k < len; ++k) { /* deltas = rews[:-1] + gamma * vals[1:] - vals[:-1] */
+        const size_t q = (size_t)(start + k) * n + i;
+        const float vn = (k + 1 < len) ? value[q + n] : lv;
+        float g = gf * vn;
+        float d = reward[q] + g;
+        d = d - value[q];
+        x[k] = (double)d;
+      }
+      discount_cumsum_rev(x, len, gamma * lam, y);
+      for (int k = 0; k < len; ++k) adv[(size_t)(start + k) * n + i] = (float)y[k];
+      for (int k = 0; k < len; ++k) x[k] = (double)reward[(size_t)(start + k) * n + i];
+      x[len] = (double)lv;
+      discount_cumsum_rev(x, len + 1, gamma, y);
+      for (int k = 0; k < len; ++k) ret[(size_t)(start + k) * n + i] = (float)y[k];
+      start = end;
+    }
+  }
+  free(x);
+  return GX_OK;
+}
