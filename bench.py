@@ -14,8 +14,10 @@ One JSON line on stdout (rank 0).  Keys beyond the driver's contract:
                 348 algorithmic bytes per env-step
   cpu_baseline  the CPU oracle (C restatement of the reference, OpenMP) timed on
                 this box's host cores on a bounded sample of the same workload
-  e2e           the same metric through Engine.step_host: pinned HOST action in,
-                obs/reward/done/cost out to pinned HOST memory, every step
+  e2e           the same metric with HOST buffers: every step's action from pinned
+                host memory, every step's obs/reward/done/cost to pinned host memory,
+                through gx_rollout_host (chunks pipelined over two streams);
+                e2e.per_step_sync is the blocking one-call-per-step variant
   rollout       the fused multi-step kernel (gx_rollout): T steps per launch,
                 state in registers, vs its own 192-byte I/O-only roofline
   sweep         (N=1 only) step-kernel GB/s at larger batches, to show where the
@@ -43,6 +45,7 @@ ENVS_PER_GPU = 4096
 ALG_BYTES_STEP = 348      # single-step API contract
 ALG_BYTES_ROLLOUT = 192   # multi-step kernel, I/O only
 L2_BYTES = 126e6
+LANES_TRAFFIC_4096 = 626688   # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/)
 TASK = "Goal_Point_8Hazards"
 
 
@@ -357,7 +360,37 @@ def main():
         t = torch.tensor([dt_e2e], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt_e2e = float(t.item())
-    e2e_value = world * n * Ke / dt_e2e
+    e2e_sync_value = world * n * Ke / dt_e2e
+
+    # ---- e2e, pipelined: the same host-buffer steps through gx_rollout_host --
+    # (random actions are known up front, so step t+1 does not wait for step t's
+    # outputs to reach the host: H2D, kernels and D2H of neighbouring chunks overlap)
+    Tp = 512
+    hp_act = torch.empty(Tp, n, 2).uniform_(-1, 1).pin_memory()
+    hp_obs = torch.empty(Tp, n, od).pin_memory()
+    hp_r, hp_d, hp_c = (torch.empty(Tp, n).pin_memory() for _ in range(3))
+    reps_p = max(2, min(40, (K + Tp - 1) // Tp))
+
+    def e2e_pipe(k):
+        acc = 0.0
+        for j in range(k):
+            batches[j % R].env.rollout_host(hp_act, hp_obs, hp_r, hp_d, hp_c)
+            acc += float(hp_r[-1, -1])   # the rollout's result is read on the host
+        return acc
+
+    e2e_pipe(2)
+    if barrier:
+        barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_pipe(reps_p)
+    dt_pipe = time.perf_counter() - t0
+    if dist:
+        t = torch.tensor([dt_pipe], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_pipe = float(t.item())
+    e2e_value = world * n * Tp * reps_p / dt_pipe
+    del hp_obs
 
     # ---- fused rollout kernel ----------------------------------------------
     T = 256
@@ -438,12 +471,21 @@ def main():
             "value_stream_launch": world * n * K / dt_stream,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4,
-                    "d2h_bytes_per_step": n * (od + 3) * 4, "steps": Ke,
-                    "path": "Engine.step_host -> gx_step_host: pinned host action -> H2D -> fused step+auto-reset "
-                            "-> D2H obs|reward|done|cost -> stream sync, every step"},
+                    "d2h_bytes_per_step": n * (od + 3) * 4, "steps": Tp * reps_p,
+                    "path": "Engine.rollout_host -> gx_rollout_host: every step's action comes from pinned host "
+                            "memory (H2D) and every step's obs|reward|done|cost lands in pinned host memory (D2H); "
+                            "chunks of steps are pipelined over a compute and a copy stream; timed on the host "
+                            "clock around the calls, results read on the host",
+                    "per_step_sync": {"value": e2e_sync_value, "steps": Ke,
+                                      "path": "Engine.step_host -> gx_step_host: H2D action -> fused step+auto-reset "
+                                              "-> D2H -> stream sync, one blocking call per step (what a policy in "
+                                              "the loop needs)"}},
             "gpu_launches": K,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "kernel": "gx_step_lanes_kernel<true,true>",
+                         "frac": achieved / hbm_peak, "traffic": LANES_TRAFFIC_4096 if n == 4096 else None,
+                         "traffic_source": "profiles/r1_prof_lanes_4096_summary.txt: dram read 626.7 KB + write 0 KB per "
+                                           "launch under ncu --set full (the 0.9 MB of outputs stay in the 126 MB L2 "
+                                           "within one launch)", "kernel": "gx_step_lanes_kernel<true,true>",
                          "alg_bytes_per_env_step": ALG_BYTES_STEP, "envs_per_launch": n,
                          "us_per_launch": step_us, "peak_source": peak_src,
                          "note": "latency-bound at 4096 envs (1.4 MB per launch, one dependent chain per env); "

@@ -82,6 +82,11 @@ struct gx_env {
   int lanes_max_envs;   // use the 16-lanes-per-env kernels up to this batch size (0 = never)
   // staging for gx_step_host
   float* stage;  // [n*act_dim | n*obs_dim | n | n | n]
+  // gx_rollout_host pipeline: two chunk buffers, a compute and a copy stream
+  float* ring[2];
+  int ring_steps;
+  cudaStream_t rs_compute, rs_copy;
+  cudaEvent_t ev_in, ev_computed[2], ev_copied[2];
 };
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
@@ -708,6 +713,12 @@ GX_API int gx_destroy(gx_env* e) {
   cudaFree(e->s.d0); cudaFree(e->s.d1); cudaFree(e->s.d2); cudaFree(e->s.goal);
   cudaFree(e->s.hz); cudaFree(e->s.ep); cudaFree(e->s.fin); cudaFree(e->s.hx); cudaFree(e->s.hf);
   cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage); cudaFree(e->ctr);
+  if (e->ring_steps) {
+    cudaFree(e->ring[0]); cudaFree(e->ring[1]);
+    cudaStreamDestroy(e->rs_compute); cudaStreamDestroy(e->rs_copy);
+    cudaEventDestroy(e->ev_in);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_computed[k]); cudaEventDestroy(e->ev_copied[k]); }
+  }
   delete e;
   return GX_OK;
 }
@@ -988,6 +999,68 @@ GX_API int gx_step_host(gx_env* e, const float* h_action, float* h_obs, float* h
     GX_CUDA(cudaMemcpyAsync(h_cost, d_cost, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
   }
   GX_CUDA(cudaStreamSynchronize(st));
+  return GX_OK;
+}
+
+// ---- host-buffer rollout, pipelined ------------------------------------------
+// T steps with host-resident actions and host-resident outputs.  The steps are
+// cut into chunks of S; chunk c's actions go up and its S fused step+auto-reset
+// launches run on a compute stream while chunk c-1's outputs drain to the host on
+// a copy stream (two device chunk buffers).  PCIe carries 8 B up and
+// (obs_dim+3)*4 B down per env-step; at 4096 envs the kernels (~5 us/step) hide
+// entirely behind the D2H stream (~14 us/step at 55 GB/s).
+GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h_obs, float* h_reward,
+                           float* h_done, float* h_cost, void* stream) {
+  if (!e || T < 0 || !h_action || !h_obs || !h_reward || !h_done || !h_cost)
+    return gx_fail(GX_EINVAL, "gx_rollout_host: bad argument");
+  if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_rollout_host: call gx_reset first");
+  if (T == 0) return GX_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t user = (cudaStream_t)stream;
+  const size_t n = (size_t)e->p.n, od = (size_t)e->p.obs_dim;
+  const size_t per_step = (od + 3 + 2) * n;  // obs | reward | done | cost | action
+  if (!e->ring_steps) {
+    // ~8 MB of output per chunk keeps the copy engine near its large-transfer rate
+    int S = (int)((8u << 20) / (sizeof(float) * (od + 3) * n));
+    S = S < 1 ? 1 : (S > 64 ? 64 : S);
+    for (int k = 0; k < 2; ++k) GX_CUDA(cudaMalloc((void**)&e->ring[k], sizeof(float) * per_step * S));
+    GX_CUDA(cudaStreamCreateWithFlags(&e->rs_compute, cudaStreamNonBlocking));
+    GX_CUDA(cudaStreamCreateWithFlags(&e->rs_copy, cudaStreamNonBlocking));
+    GX_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+      GX_CUDA(cudaEventCreateWithFlags(&e->ev_computed[k], cudaEventDisableTiming));
+      GX_CUDA(cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming));
+    }
+    e->ring_steps = S;
+  }
+  const int S = e->ring_steps;
+  GX_CUDA(cudaEventRecord(e->ev_in, user));
+  GX_CUDA(cudaStreamWaitEvent(e->rs_compute, e->ev_in, 0));
+  int chunk = 0;
+  for (int t0 = 0; t0 < T; t0 += S, ++chunk) {
+    const int k = chunk & 1, s_now = (T - t0 < S) ? (T - t0) : S;
+    float* d_obs = e->ring[k];
+    float* d_rew = d_obs + od * n * S;
+    float* d_done = d_rew + n * S;
+    float* d_cost = d_done + n * S;
+    float* d_act = d_cost + n * S;
+    if (chunk >= 2) GX_CUDA(cudaStreamWaitEvent(e->rs_compute, e->ev_copied[k], 0));
+    GX_CUDA(cudaMemcpyAsync(d_act, h_action + 2 * n * t0, sizeof(float) * 2 * n * s_now, cudaMemcpyHostToDevice, e->rs_compute));
+    for (int t = 0; t < s_now; ++t)
+      if (int rc = gx_step_impl(e, d_act + 2 * n * t, d_obs + od * n * t, d_rew + n * t, d_done + n * t, d_cost + n * t,
+                                nullptr, nullptr, e->rs_compute, true, "gx_rollout_host"))
+        return rc;
+    GX_CUDA(cudaEventRecord(e->ev_computed[k], e->rs_compute));
+    GX_CUDA(cudaStreamWaitEvent(e->rs_copy, e->ev_computed[k], 0));
+    GX_CUDA(cudaMemcpyAsync(h_obs + od * n * t0, d_obs, sizeof(float) * od * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
+    GX_CUDA(cudaMemcpyAsync(h_reward + n * t0, d_rew, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
+    GX_CUDA(cudaMemcpyAsync(h_done + n * t0, d_done, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
+    GX_CUDA(cudaMemcpyAsync(h_cost + n * t0, d_cost, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
+    GX_CUDA(cudaEventRecord(e->ev_copied[k], e->rs_copy));
+  }
+  // the caller's stream (and the host) see the finished rollout
+  GX_CUDA(cudaStreamWaitEvent(user, e->ev_copied[(chunk - 1) & 1], 0));
+  GX_CUDA(cudaStreamSynchronize(e->rs_copy));
   return GX_OK;
 }
 

@@ -332,6 +332,21 @@ class Engine:
         _abi.check(L, L.gx_step_host(self._h, C.c_void_p(h_action.data_ptr()), p(0), p(n * od), p(n * od + n),
                                      p(n * od + 2 * n), 1 if auto_reset_done else 0, self._stream()), "gx_step_host")
 
+    def rollout_host(self, h_action, h_obs, h_reward, h_done, h_cost):
+        """T pipelined end-to-end steps with HOST buffers (gx_rollout_host): `h_action`
+        pinned [T, N, act_dim]; outputs pinned [T, N, obs_dim] and [T, N].  Same results
+        as T calls of step_host(auto_reset_done=True); returns when they are in host memory."""
+        T = int(h_action.shape[0])
+        n, od = self.env_num, self.obs_flat_size
+        assert tuple(h_action.shape) == (T, n, self.action_space.shape[0]) and h_action.is_contiguous()
+        assert tuple(h_obs.shape) == (T, n, od) and h_obs.is_contiguous()
+        for h in (h_reward, h_done, h_cost):
+            assert tuple(h.shape) == (T, n) and h.is_contiguous()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        L = self._lib
+        _abi.check(L, L.gx_rollout_host(self._h, T, p(h_action), p(h_obs), p(h_reward), p(h_done), p(h_cost),
+                                        self._stream()), "gx_rollout_host")
+
     # ------------------------------------------------------------ lifetime
     def render(self, *a, **k):
         raise NotImplementedError('render() needs a MuJoCo GL viewer (engine.py:1036-1070); out of scope')

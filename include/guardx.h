@@ -246,6 +246,17 @@ int gx_stats_reset(gx_env* env, void* stream);
 int gx_step_host(gx_env* env, const float* h_action, float* h_obs, float* h_reward,
                  float* h_done, float* h_cost, int32_t auto_reset_done, void* stream);
 
+/* ---- host-buffer rollout: T x (gx_step_host with auto_reset_done) for actions
+ *      that are known up front (the random-action rollouts of trpo/myTest.py:31
+ *      and of BASELINE.json's configs), pipelined: while chunk c steps on the
+ *      device, chunk c-1's outputs drain to the host and chunk c+1's actions go
+ *      up.  h_action [T, env_num, act_dim]; h_obs [T, env_num, obs_dim];
+ *      h_reward/h_done/h_cost [T, env_num]; all pinned host memory.  Returns
+ *      after everything has landed in host memory.  Bit-identical to T calls of
+ *      gx_step_host. ------------------------------------------------------- */
+int gx_rollout_host(gx_env* env, int32_t T, const float* h_action, float* h_obs, float* h_reward,
+                    float* h_done, float* h_cost, void* stream);
+
 /* ---- rollout-side op: GAE-lambda advantages and rewards-to-go
  *      over a time-major rollout, replacing PPOBufferX.finish_path
  *      (safe_rl_libX/ppo/ppo_train.py:61-113: a per-env Python loop over

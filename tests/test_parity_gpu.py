@@ -414,6 +414,29 @@ def test_step_host_matches_step(mods):
         assert torch.equal(h_out[n * od + 2 * n:], info['cost'].cpu())
 
 
+@pytest.mark.parametrize("n,T", [(1000, 37), (4096, 70), (70000, 5)])
+def test_rollout_host_matches_step_host(mods, n, T):
+    """The pipelined host rollout (chunked, two streams) == T synchronous host steps,
+    including a ragged last chunk and a second call reusing the ring."""
+    Engine, _ = mods
+    cfg = {'env_num': n, 'num_steps': 20, '_seed': 9}
+    a, b = Engine(dict(cfg)), Engine(dict(cfg))
+    a.reset(); b.reset()
+    od = a.obs_flat_size
+    h_out = torch.empty(n * (od + 3)).pin_memory()
+    for rep in range(2):
+        h_act = torch.empty(T, n, 2).uniform_(-1, 1).pin_memory()
+        h_obs = torch.empty(T, n, od).pin_memory()
+        h_r, h_d, h_c = (torch.empty(T, n).pin_memory() for _ in range(3))
+        a.rollout_host(h_act, h_obs, h_r, h_d, h_c)
+        for t in range(T):
+            b.step_host(h_act[t], h_out, auto_reset_done=True)
+            assert torch.equal(h_out[:n * od].view(n, od), h_obs[t]), (rep, t)
+            assert torch.equal(h_out[n * od:n * od + n], h_r[t])
+            assert torch.equal(h_out[n * od + n:n * od + 2 * n], h_d[t])
+            assert torch.equal(h_out[n * od + 2 * n:], h_c[t])
+
+
 def test_episode_statistics_match_oracle(mods):
     n = 300
     g, o = make_pair(mods, {'env_num': n, 'num_steps': 30, '_seed': 12})
