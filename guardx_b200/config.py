@@ -92,7 +92,9 @@ DEFAULT = {
 }
 
 # robots this build has dynamics for -> GX_ROBOT_*
-_ROBOTS = {'xmls/point.xml': _abi.GX_ROBOT_POINT}
+_ROBOTS = {'xmls/point.xml': _abi.GX_ROBOT_POINT, 'xmls/ant.xml': _abi.GX_ROBOT_ART,
+           'xmls/walker.xml': _abi.GX_ROBOT_ART, 'xmls/swimmer.xml': _abi.GX_ROBOT_ART}
+_TASK_ROBOT = {'Point': 'xmls/point.xml', 'Ant': 'xmls/ant.xml', 'Walker': 'xmls/walker.xml', 'Swimmer': 'xmls/swimmer.xml'}
 
 
 def parse(config: dict) -> dict:
@@ -106,10 +108,13 @@ def parse(config: dict) -> dict:
 
 def configuration(task: str) -> dict:
     """The runnable subset of safe_rl_env_config.configuration_list."""
-    if task in ("Goal_Point_8Hazards", "Goal_Point_8Hazards_noconti"):
-        # safe_rl_env_config.py:59-82
+    # safe_rl_env_config.py:59-82 (Point), :111-136 (Swimmer), :195-221 (Ant), :254-280 (Walker):
+    # the four entries differ only in robot_base
+    name = task[:-len("_noconti")] if task.endswith("_noconti") else task
+    parts = name.split("_")
+    if len(parts) == 3 and parts[0] == "Goal" and parts[2] == "8Hazards" and parts[1] in _TASK_ROBOT:
         return {
-            'robot_base': 'xmls/point.xml',
+            'robot_base': _TASK_ROBOT[parts[1]],
             'task': 'goal',
             'goal_size': 0.5,
             'observe_goal_comp': True,
@@ -121,9 +126,20 @@ def configuration(task: str) -> dict:
             'hazards_size': 0.3,
         }
     raise NotImplementedError(
-        f"task {task!r}: only Goal_Point_8Hazards is built so far "
-        "(Swimmer/Ant/Walker/Doggo need the general MJX pipeline; the Push/Chase/Defense/"
-        "Ghost entries are rejected by the reference Engine itself, engine.py:326-328)")
+        f"task {task!r}: built so far are Goal_{{Point,Swimmer,Ant,Walker}}_8Hazards "
+        "(Doggo needs a free-joint root; the Push/Chase/Defense/Ghost entries are rejected by "
+        "the reference Engine itself, engine.py:326-328)")
+
+
+def compiled_model(cfg: dict):
+    """The MuJoCo model World.build() would emit for this config (world.py:104-333), compiled
+    by guardx_b200.mjcf -- None for the Point, whose constants are closed-form (point_model)."""
+    if _ROBOTS.get(cfg['robot_base']) != _abi.GX_ROBOT_ART:
+        return None
+    from . import mjcf, robots
+    spec = mjcf.add_world_geoms(robots.robot_spec(cfg['robot_base']), cfg['goal_size'], cfg['hazards_size'],
+                                cfg['hazards_num'])
+    return mjcf.compile_spec(spec)
 
 
 def obs_mask_of(cfg: dict) -> int:
@@ -168,7 +184,7 @@ def point_model() -> _abi.GxPointModel:
     return pm
 
 
-def lower(cfg: dict, env_id_offset: int = 0, pool_size: int = 0) -> _abi.GxConfig:
+def lower(cfg: dict, env_id_offset: int = 0, pool_size: int = 0, model=None) -> _abi.GxConfig:
     """Parsed Engine config -> gx_config.  Raises for what the reference itself
     cannot run (SURVEY.md Appendix A quirks marked "don't")."""
     if cfg['robot_base'] not in _ROBOTS:
@@ -200,6 +216,12 @@ def lower(cfg: dict, env_id_offset: int = 0, pool_size: int = 0) -> _abi.GxConfi
     c.lidar_exp_gain = float(cfg['lidar_exp_gain'])
     c.goal_min_robot_dist = 3.0  # engine.py:571
     c.opt_timestep = 0.02  # point.xml:3 (mj_model.opt.timestep is a double)
+    if c.robot == _abi.GX_ROBOT_ART:
+        if model is None:
+            model = compiled_model(cfg)
+        nv_robot = int(model.nv) - 2 - 2 * int(cfg['hazards_num'])
+        c.opt_timestep = float(model.opt['timestep'])
+        c.art_nu, c.art_nv = int(model.nu), nv_robot
     c.hazards_num = int(cfg['hazards_num'])
     c.lidar_num_bins = int(cfg['lidar_num_bins'])
     c.lidar_alias = 1 if cfg['lidar_alias'] else 0

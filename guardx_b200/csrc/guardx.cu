@@ -14,6 +14,7 @@
 #include "../../include/guardx.h"
 #include "gx_device.cuh"
 #include "gx_lanes.cuh"
+#include "gx_art.cuh"
 
 #define GX_API extern "C" __attribute__((visibility("default")))
 
@@ -82,6 +83,10 @@ struct gx_env {
   int lanes_max_envs;   // use the 16-lanes-per-env kernels up to this batch size (0 = never)
   // staging for gx_step_host
   float* stage;  // [n*act_dim | n*obs_dim | n | n | n]
+  // articulated robots (GX_ROBOT_ART): host + device copy of the model, joint-state SoA
+  GxArtModel* art_host;
+  GxArtDev art;
+  int art_shape;  // 1 ant-like (4 legs x 2 dofs), 2 walker-like (2 x 5), 3 swimmer-like (1 x 2)
   // gx_rollout_host pipeline: two chunk buffers, a compute and a copy stream
   float* ring[2];
   int ring_steps;
@@ -618,6 +623,8 @@ __global__ void gx_set_state_kernel(const __grid_constant__ gx_params p, const G
   s.hf[i] = (x[4] > 0.0f ? 1u : 0u) | ((uint32_t)hist << 1);
 }
 
+#include "gx_art_kernels.cuh"
+
 // ---------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------
@@ -641,9 +648,29 @@ static bool lanes_path(const gx_env* e) {
 static size_t tile_bytes(const gx_env* e, int block) { return (size_t)block * e->p.obs_dim * sizeof(float); }
 static bool fast_path(const gx_env* e) { return e->p.nh == 8; }
 
-GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
+static int gx_art_shape_of(const GxArtModel* m) {
+  int kmax = 0, nbmax = 0;
+  for (int l = 0; l < m->nleg; ++l) { kmax = m->leg[l].nk > kmax ? m->leg[l].nk : kmax; nbmax = m->leg[l].nb > nbmax ? m->leg[l].nb : nbmax; }
+  if (m->nleg == 4 && kmax <= 2 && nbmax <= 3) return 1;
+  if (m->nleg == 2 && kmax <= 5 && nbmax <= 3) return 2;
+  if (m->nleg == 1 && kmax <= 2 && nbmax <= 2) return 3;
+  return 0;
+}
+
+static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int device, gx_env** out) {
   if (!out) return gx_fail(GX_EINVAL, "gx_create: out is NULL");
   *out = nullptr;
+  if (h_cfg && (h_cfg->robot == GX_ROBOT_ART) != (h_model != nullptr))
+    return gx_fail(GX_EINVAL, "gx_create: GX_ROBOT_ART needs gx_create_art with a model (and only it)");
+  if (h_model) {
+    int nvr = 3;
+    if (h_model->nleg < 1 || h_model->nleg > GX_ART_MAXLEG) return gx_fail(GX_EINVAL, "gx_create_art: nleg out of range");
+    for (int l = 0; l < h_model->nleg; ++l) nvr += h_model->leg[l].nk;
+    if (nvr != h_model->nv || h_cfg->art_nv != h_model->nv || h_cfg->art_nu != h_model->nu)
+      return gx_fail(GX_EINVAL, "gx_create_art: nv / nu of the model and the config disagree");
+    if (!gx_art_shape_of(h_model))
+      return gx_fail(GX_EINVAL, "gx_create_art: no kernel instance for this robot shape (legs x dofs x bodies)");
+  }
   gx_params p;
   memset(&p, 0, sizeof p);
   if (const char* why = gx_lower_config(h_cfg, &p)) return gx_fail(GX_EINVAL, "gx_create: %s", why);
@@ -663,6 +690,7 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   e->sm_count = prop.multiProcessorCount;
   e->ctr = nullptr; e->have_reset = false; e->stats_on = false; e->stats_age0 = 0;
   e->stage = nullptr;
+  e->art_host = nullptr; e->art.m = nullptr; e->art.aq = nullptr; e->art.nv = 0; e->art.nu = 0; e->art_shape = 0;
   e->lanes_max_envs = 16384;
   if (const char* v = getenv("GX_LANES_MAX_ENVS")) e->lanes_max_envs = atoi(v);
   const int cap = div_up(p.n, 32) * 32;
@@ -694,6 +722,16 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   GX_ALLOC(e->pool_tries, sizeof(int32_t) * (size_t)p.pool_size);
   GX_ALLOC(e->stats, sizeof(double) * 8);
   GX_ALLOC(e->ctr, sizeof(unsigned long long) * 4);
+  if (h_model) {
+    e->art_host = new (std::nothrow) GxArtModel(*h_model);
+    e->art_shape = gx_art_shape_of(h_model);
+    e->art.nv = h_model->nv; e->art.nu = h_model->nu;
+    GxArtModel* dm = nullptr;
+    GX_ALLOC(dm, sizeof(GxArtModel));
+    cudaMemcpy(dm, h_model, sizeof(GxArtModel), cudaMemcpyHostToDevice);
+    e->art.m = dm;
+    GX_ALLOC(e->art.aq, sizeof(float) * 3 * (size_t)h_model->nv * cap);
+  }
 #undef GX_ALLOC
   // never-forwarded mjx.Data carries the identity xmat that put_data copied in
   {
@@ -707,12 +745,19 @@ GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) {
   return GX_OK;
 }
 
+GX_API int gx_create(const gx_config* h_cfg, int device, gx_env** out) { return gx_create_impl(h_cfg, nullptr, device, out); }
+GX_API int gx_create_art(const gx_config* h_cfg, const GxArtModel* h_model, int device, gx_env** out) {
+  if (!h_model) return gx_fail(GX_EINVAL, "gx_create_art: model is NULL");
+  return gx_create_impl(h_cfg, h_model, device, out);
+}
+
 GX_API int gx_destroy(gx_env* e) {
   if (!e) return GX_OK;
   DeviceGuard guard(e->device);
   cudaFree(e->s.d0); cudaFree(e->s.d1); cudaFree(e->s.d2); cudaFree(e->s.goal);
   cudaFree(e->s.hz); cudaFree(e->s.ep); cudaFree(e->s.fin); cudaFree(e->s.hx); cudaFree(e->s.hf);
   cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage); cudaFree(e->ctr);
+  cudaFree((void*)e->art.m); cudaFree(e->art.aq); delete e->art_host;
   if (e->ring_steps) {
     cudaFree(e->ring[0]); cudaFree(e->ring[1]);
     cudaStreamDestroy(e->rs_compute); cudaStreamDestroy(e->rs_copy);
@@ -724,7 +769,7 @@ GX_API int gx_destroy(gx_env* e) {
 }
 
 GX_API int gx_obs_dim(const gx_env* e) { return e ? e->p.obs_dim : GX_EINVAL; }
-GX_API int gx_act_dim(const gx_env* e) { return e ? 2 : GX_EINVAL; }
+GX_API int gx_act_dim(const gx_env* e) { return e ? (e->art_host ? e->art.nu : 2) : GX_EINVAL; }
 GX_API int gx_env_num(const gx_env* e) { return e ? e->p.n : GX_EINVAL; }
 GX_API int gx_pool_size(const gx_env* e) { return e ? e->p.pool_size : GX_EINVAL; }
 GX_API int gx_aux_dim(const gx_env* e) { return e ? e->p.aux_dim : GX_EINVAL; }
@@ -748,6 +793,17 @@ GX_API int gx_obs_offset(const gx_env* e, uint32_t component) {
 // engine.py:291-297: ctrlrange of the first two actuators, +-inf if not limited
 GX_API int gx_action_bounds(const gx_env* e, float* h_low, float* h_high) {
   if (!e || !h_low || !h_high) return gx_fail(GX_EINVAL, "gx_action_bounds: NULL argument");
+  if (e->art_host) {
+    const GxArtModel* m = e->art_host;
+    auto put = [&](const GxArtDof& d) {
+      if (d.act < 0) return;
+      h_low[d.act] = d.ctrllimited ? d.ctrl_lo : -INFINITY;
+      h_high[d.act] = d.ctrllimited ? d.ctrl_hi : INFINITY;
+    };
+    for (int r = 0; r < 3; ++r) put(m->root.dof[r]);
+    for (int l = 0; l < m->nleg; ++l) for (int k = 0; k < m->leg[l].nk; ++k) put(m->leg[l].dof[k]);
+    return GX_OK;
+  }
   for (int i = 0; i < 2; ++i) {
     h_low[i] = e->p.ctrllimited ? e->p.ctrl_lo : -INFINITY;
     h_high[i] = e->p.ctrllimited ? e->p.ctrl_hi : INFINITY;
@@ -770,7 +826,42 @@ static int gx_generate_pool(gx_env* e, cudaStream_t st) {
   return GX_OK;
 }
 
+// ---- articulated robots: one launcher for reset / step / reset_done ----------
+template <int MODE, bool AR>
+static int gx_art_launch(gx_env* e, cudaStream_t st, const float* layout, const float* action, const float* obs_in,
+                         float* obs, float* act_out, float* reward, float* done, float* cost, float* qacc) {
+  const int n = e->p.n, block = 128;
+#define GX_ART_GO(L, NL, K, NB)                                                                              \
+  do {                                                                                                       \
+    const int grid = div_up(n * (L), block);                                                                 \
+    const size_t sh = (size_t)(block / (L)) * e->p.obs_dim * sizeof(float);                                  \
+    gx_art_kernel<L, NL, K, NB, MODE, AR><<<grid, block, sh, st>>>(e->p, e->s, e->art, e->pool, layout,     \
+                                                                       action, obs_in, obs, act_out, reward, \
+                                                                       done, cost, qacc, e->stats_on ? 1 : 0); \
+  } while (0)
+  switch (e->art_shape) {
+    case 1: GX_ART_GO(4, 4, 2, 3); break;
+    case 2: GX_ART_GO(2, 2, 5, 3); break;
+    case 3: GX_ART_GO(1, 1, 2, 2); break;
+    default: return gx_fail(GX_EINVAL, "gx_art_launch: no kernel for this robot shape");
+  }
+#undef GX_ART_GO
+  GX_LAUNCH_CHECK("gx_art_kernel");
+  return GX_OK;
+}
+
+static int gx_art_step(gx_env* e, cudaStream_t st, const float* action, float* obs, float* act_out, float* reward,
+                       float* done, float* cost, float* qacc, bool autoreset) {
+  return autoreset ? gx_art_launch<GX_ART_STEP, true>(e, st, nullptr, action, nullptr, obs, act_out, reward, done, cost, qacc)
+                   : gx_art_launch<GX_ART_STEP, false>(e, st, nullptr, action, nullptr, obs, act_out, reward, done, cost, qacc);
+}
+
 static int gx_reset_impl(gx_env* e, const float* layout, float* obs, cudaStream_t st) {
+  if (e->art_host) {
+    if (int rc = gx_art_launch<GX_ART_RESET, false>(e, st, layout, nullptr, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr)) return rc;
+    e->have_reset = true;
+    return GX_OK;
+  }
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
   if (fast_path(e))
@@ -816,6 +907,10 @@ static int gx_step_impl(gx_env* e, const float* action, float* obs, float* rewar
   if (reinterpret_cast<uintptr_t>(action) & 7u) return gx_fail(GX_EINVAL, "%s: action must be 8-byte aligned", who);
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->art_host) {
+    if (aux) return gx_fail(GX_EINVAL, "%s: the aux row is not built for articulated robots", who);
+    return gx_art_step(e, st, action, obs, nullptr, reward, done, cost, qacc, autoreset);
+  }
   if (!aux && lanes_path(e)) {
     const int block = 128, grid = div_up(e->p.n * GX_LPE, block);
     const float2* a2 = reinterpret_cast<const float2*>(action);
@@ -849,6 +944,8 @@ GX_API int gx_reset_done(gx_env* e, const float* obs_in, float* obs_out, const f
   if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_reset_done: call gx_reset first");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->art_host)
+    return gx_art_launch<GX_ART_RESET_DONE, false>(e, st, layout, nullptr, obs_in, obs_out, nullptr, nullptr, nullptr, nullptr, nullptr);
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
   if (fast_path(e))
@@ -862,7 +959,8 @@ GX_API int gx_reset_done(gx_env* e, const float* obs_in, float* obs_out, const f
 GX_API int gx_get_state(gx_env* e, float* state, void* stream) {
   if (!e || !state) return gx_fail(GX_EINVAL, "gx_get_state: NULL argument");
   DeviceGuard guard(e->device);
-  gx_get_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
+  if (e->art_host) gx_art_get_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, e->art, state);
+  else gx_get_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
   GX_LAUNCH_CHECK("gx_get_state_kernel");
   return GX_OK;
 }
@@ -870,7 +968,8 @@ GX_API int gx_get_state(gx_env* e, float* state, void* stream) {
 GX_API int gx_set_state(gx_env* e, const float* state, void* stream) {
   if (!e || !state) return gx_fail(GX_EINVAL, "gx_set_state: NULL argument");
   DeviceGuard guard(e->device);
-  gx_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
+  if (e->art_host) gx_art_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, e->art, state);
+  else gx_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
   GX_LAUNCH_CHECK("gx_set_state_kernel");
   e->have_reset = true;
   return GX_OK;
@@ -930,6 +1029,17 @@ GX_API int gx_rollout(gx_env* e, int32_t T, float* obs, float* act, float* rewar
   if (T == 0) return GX_OK;
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->art_host) {
+    // one fused step + auto-reset launch per control step, actions drawn in-kernel (the
+    // per-step work of a legged robot dwarfs the launch, unlike the Point's)
+    if (!obs || !reward || !cost || !done) return gx_fail(GX_EINVAL, "gx_rollout: articulated robots need obs, reward, cost and done buffers");
+    const size_t n = (size_t)e->p.n;
+    for (int t = 0; t < T; ++t)
+      if (int rc = gx_art_step(e, st, nullptr, obs + (size_t)t * n * e->p.obs_dim, act ? act + (size_t)t * n * e->art.nu : nullptr,
+                               reward + t * n, done + t * n, cost + t * n, nullptr, true))
+        return rc;
+    return GX_OK;
+  }
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
   float2* a2 = reinterpret_cast<float2*>(act);
@@ -979,14 +1089,15 @@ GX_API int gx_step_host(gx_env* e, const float* h_action, float* h_obs, float* h
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)e->p.n, od = (size_t)e->p.obs_dim;
   // stage = [obs n*od | reward n | done n | cost n | pad | action 2n]
+  const size_t ad = (size_t)gx_act_dim(e);
   const size_t act_off = ((od + 3) * n + 3) & ~(size_t)3;
-  if (!e->stage) GX_CUDA(cudaMalloc((void**)&e->stage, sizeof(float) * (act_off + 2 * n)));
+  if (!e->stage) GX_CUDA(cudaMalloc((void**)&e->stage, sizeof(float) * (act_off + ad * n)));
   float* d_obs = e->stage;
   float* d_reward = d_obs + od * n;
   float* d_done = d_reward + n;
   float* d_cost = d_done + n;
   float* d_act = e->stage + act_off;
-  GX_CUDA(cudaMemcpyAsync(d_act, h_action, sizeof(float) * 2 * n, cudaMemcpyHostToDevice, st));
+  GX_CUDA(cudaMemcpyAsync(d_act, h_action, sizeof(float) * ad * n, cudaMemcpyHostToDevice, st));
   if (int rc = gx_step_impl(e, d_act, d_obs, d_reward, d_done, d_cost, nullptr, nullptr, stream,
                             auto_reset_done != 0, "gx_step_host"))
     return rc;
@@ -1018,7 +1129,8 @@ GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h
   DeviceGuard guard(e->device);
   cudaStream_t user = (cudaStream_t)stream;
   const size_t n = (size_t)e->p.n, od = (size_t)e->p.obs_dim;
-  const size_t per_step = (od + 3 + 2) * n;  // obs | reward | done | cost | action
+  const size_t ad = (size_t)gx_act_dim(e);
+  const size_t per_step = (od + 3 + ad) * n;  // obs | reward | done | cost | action
   if (!e->ring_steps) {
     // ~8 MB of output per chunk keeps the copy engine near its large-transfer rate
     int S = (int)((8u << 20) / (sizeof(float) * (od + 3) * n));
@@ -1045,9 +1157,9 @@ GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h
     float* d_cost = d_done + n * S;
     float* d_act = d_cost + n * S;
     if (chunk >= 2) GX_CUDA(cudaStreamWaitEvent(e->rs_compute, e->ev_copied[k], 0));
-    GX_CUDA(cudaMemcpyAsync(d_act, h_action + 2 * n * t0, sizeof(float) * 2 * n * s_now, cudaMemcpyHostToDevice, e->rs_compute));
+    GX_CUDA(cudaMemcpyAsync(d_act, h_action + ad * n * t0, sizeof(float) * ad * n * s_now, cudaMemcpyHostToDevice, e->rs_compute));
     for (int t = 0; t < s_now; ++t)
-      if (int rc = gx_step_impl(e, d_act + 2 * n * t, d_obs + od * n * t, d_rew + n * t, d_done + n * t, d_cost + n * t,
+      if (int rc = gx_step_impl(e, d_act + ad * n * t, d_obs + od * n * t, d_rew + n * t, d_done + n * t, d_cost + n * t,
                                 nullptr, nullptr, e->rs_compute, true, "gx_rollout_host"))
         return rc;
     GX_CUDA(cudaEventRecord(e->ev_computed[k], e->rs_compute));

@@ -1,0 +1,390 @@
+// gx_art_kernels.cuh -- Engine.reset / step / reset_done for articulated robots
+// (included by guardx.cu after the Point kernels; shares GxState's env-level arrays,
+// the layout pool, the Philox streams and the lidar / reward / cost device functions).
+//
+// Thread mapping: LANES consecutive threads per env (lane l owns leg l, gx_art.cuh),
+// 32/LANES envs per warp; the warp's observation rows are assembled in a shared-memory
+// tile and leave as coalesced 128-bit stores.  The joint state lives in one SoA array
+//   aq[(which * nv + dof) * cap + env],  which = 0 qpos, 1 qvel, 2 qacc_warmstart.
+#ifndef GX_ART_KERNELS_CUH_
+#define GX_ART_KERNELS_CUH_
+
+#include "gx_art.cuh"
+
+enum { GX_ART_RESET = 0, GX_ART_STEP = 1, GX_ART_RESET_DONE = 2 };
+
+template <int LANES>
+__device__ __forceinline__ unsigned gx_art_mask() {
+  if (LANES == 32) return 0xffffffffu;
+  const unsigned lw = threadIdx.x & 31u;
+  return ((1u << LANES) - 1u) << (lw & ~(unsigned)(LANES - 1));
+}
+
+__device__ __forceinline__ void gx_art_hazard(const GxState& s, const float* lay, int i, int h, float& hx, float& hy) {
+  if (lay) { hx = lay[4 + 2 * h]; hy = lay[5 + 2 * h]; return; }
+  const float4 v = s.hz[(size_t)(h >> 1) * s.cap + i];
+  hx = (h & 1) ? v.z : v.x;
+  hy = (h & 1) ? v.w : v.y;
+}
+
+struct GxArtObs { float dist_goal, cost; int bad; };
+
+// Observation row of one env, written by its LANES lanes into `row` (shared memory):
+// geometry from the pose snapshot (engine.py:754-758, 817-900), qpos / qvel = (q, v) given
+// (post-step values on a step, engine.py:759-762), ctrl = the unclipped action.
+template <int LANES, int NLEG, int K, int NB>
+__device__ __forceinline__ GxArtObs gx_art_obs_row(const gx_params& p, const GxState& s, const GxArtModel& m, int i,
+                                                   int lane, unsigned mask, const float* lay, float gx_, float gy_,
+                                                   const GxArtSnap& sn, const float* cr, const float (*cl)[K],
+                                                   const float* qr, const float* vr, const float (*ql)[K],
+                                                   const float (*vl)[K], float* row) {
+  constexpr int LPL = NLEG / LANES;
+  GxArtObs o;
+  int bad = 0;
+  const int nb = p.nb;
+  // zero both lidars cooperatively
+  if (p.off_glidar >= 0) for (int k = lane; k < nb; k += LANES) row[p.off_glidar + k] = 0.0f;
+  if (p.off_hlidar >= 0) for (int k = lane; k < nb; k += LANES) row[p.off_hlidar + k] = 0.0f;
+  // root entries: lane 0; leg entries: owning lane
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int a = m.root.dof[r].act;
+      if (p.off_ctrl >= 0 && a >= 0) { row[p.off_ctrl + a] = cr[r]; bad |= gx_notfinite(cr[r]); }
+      if (p.off_qpos >= 0) { row[p.off_qpos + m.root_qadr + r] = qr[r]; bad |= gx_notfinite(qr[r]); }
+      if (p.off_qvel >= 0) { row[p.off_qvel + m.root_qadr + r] = vr[r]; bad |= gx_notfinite(vr[r]); }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LPL; ++j) {
+    const int leg = j * LANES + lane;
+    const GxArtSeg& sg = m.leg[leg];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k < sg.nk) {
+        const int a = sg.dof[k].act, idx = m.leg_qadr[leg] + k;
+        if (p.off_ctrl >= 0 && a >= 0) { row[p.off_ctrl + a] = cl[j][k]; bad |= gx_notfinite(cl[j][k]); }
+        if (p.off_qpos >= 0) { row[p.off_qpos + idx] = ql[j][k]; bad |= gx_notfinite(ql[j][k]); }
+        if (p.off_qvel >= 0) { row[p.off_qvel + idx] = vl[j][k]; bad |= gx_notfinite(vl[j][k]); }
+      }
+    }
+  }
+  float gex, gey;
+  gx_ego(gx_, gy_, sn.px, sn.py, sn.r00, sn.r10, gex, gey);
+  {
+    const float dx = gx_ - sn.px, dy = gy_ - sn.py;
+    o.dist_goal = gx_sqrt(dx * dx + dy * dy);
+  }
+  __syncwarp(mask);
+  if (lane == 0) {
+    if (p.off_compass >= 0) { row[p.off_compass] = gex; row[p.off_compass + 1] = gey; bad |= gx_notfinite(gex) | gx_notfinite(gey); }
+    if (p.off_glidar >= 0) bad |= gx_lidar_scatter(p, gx_lidar_ray(p, gex, gey), row + p.off_glidar);
+  }
+  // hazards: lane l takes hazards l, l + LANES, ...; the scatters into the shared row are
+  // serialised lane by lane (all updates are max, so the order cannot change the result)
+  float cost = 0.0f;
+#pragma unroll 1
+  for (int ph = 0; ph < LANES; ++ph) {
+    if (lane == ph) {
+      for (int h = lane; h < p.nh; h += LANES) {
+        float hx, hy, ex, ey;
+        gx_art_hazard(s, lay, i, h, hx, hy);
+        gx_ego(hx, hy, sn.px, sn.py, sn.r00, sn.r10, ex, ey);
+        if (p.off_hlidar >= 0) bad |= gx_lidar_scatter(p, gx_lidar_ray(p, ex, ey), row + p.off_hlidar);
+        const float dx = hx - sn.px, dy = hy - sn.py;
+        const float dist = gx_sqrt(dx * dx + dy * dy);
+        cost = cost + (p.hazards_size - gx_min(dist, p.hazards_size));
+      }
+    }
+    __syncwarp(mask);
+  }
+  o.cost = gx_art_sum<LANES>(cost, mask);
+  o.bad = gx_art_or<LANES>(bad, mask);
+  return o;
+}
+
+// a_t ~ U(-1,1) for actuator a of env g at step `age` (the synthetic rollouts of
+// BASELINE.json; same stream as the Point kernels: word 3 = GX_STREAM_ACTION + block)
+__device__ __forceinline__ float gx_art_synth_action(const gx_params& p, uint64_t g, uint64_t age, int a) {
+  gx_u32x4 u = gx_philox4x32_10((uint32_t)g, (uint32_t)age, (uint32_t)(age >> 32), GX_STREAM_ACTION + (uint32_t)(a >> 2),
+                                p.seed_lo, p.seed_hi);
+  return gx_uniform(u.v[a & 3], -1.0f, 1.0f);
+}
+
+template <int LANES, int NLEG, int K, int NB, int MODE, bool AUTORESET>
+__global__ void __launch_bounds__(128) gx_art_kernel(const __grid_constant__ gx_params p, const GxState s,
+                                                     const GxArtDev a, const float* __restrict__ pool,
+                                                     const float* __restrict__ layout,
+                                                     const float* __restrict__ action, const float* obs_in,
+                                                     float* obs, float* __restrict__ act_out,
+                                                     float* __restrict__ reward, float* __restrict__ done,
+                                                     float* __restrict__ cost, float* __restrict__ qacc_out, int stats_on) {
+  constexpr int LPL = NLEG / LANES;
+  constexpr int EPW = 32 / LANES;
+  const int lw = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = lw % LANES, ew = lw / LANES;
+  const int wbase = (int)(((size_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / LANES);
+  if (wbase >= p.n) return;
+  const int rows = min(EPW, p.n - wbase);
+  const int env = wbase + ew;
+  const bool live = env < p.n;
+  const int i = live ? env : p.n - 1;
+  const unsigned mask = gx_art_mask<LANES>();
+  const GxArtModel& m = *a.m;
+  const int nv = a.nv, nu = a.nu;
+  const size_t cap = (size_t)s.cap;
+  float* tile = gx_smem + (size_t)warp * EPW * p.obs_dim;
+  float* row = tile + (size_t)ew * p.obs_dim;
+
+  // ---- env-level state
+  const float4 c2 = s.d2[i];
+  float prev_dist = c2.x;
+  float was_done = (__float_as_uint(c2.y) >> 31) ? 1.0f : 0.0f;
+  float steps = fabsf(c2.y);
+  uint64_t age = (uint64_t)__float_as_uint(c2.z) | ((uint64_t)__float_as_uint(c2.w) << 32);
+
+  if (MODE == GX_ART_RESET_DONE) {
+    // rows of envs that are not done pass through (Engine._obs); done envs overwrite theirs below
+    if (obs_in != obs) {
+      const int total = rows * p.obs_dim;
+      const float* src = obs_in + (size_t)wbase * p.obs_dim;
+      float* dst = obs + (size_t)wbase * p.obs_dim;
+      for (int k = lw; k < total; k += 32) dst[k] = src[k];
+      __syncwarp();
+    }
+    if (!(was_done > 0.0f) || !live) return;
+  }
+
+  // ---- joint state
+  GxArtLane<LANES, NLEG, K, NB> st;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const size_t d = (size_t)(m.root_qadr + r);
+    st.qr[r] = a.aq[d * cap + i];
+    st.vr[r] = a.aq[(nv + d) * cap + i];
+    st.wr[r] = a.aq[(2 * nv + d) * cap + i];
+  }
+#pragma unroll
+  for (int j = 0; j < LPL; ++j) {
+    const int leg = j * LANES + lane;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const bool on = k < m.leg[leg].nk;
+      const size_t d = (size_t)(m.leg_qadr[leg] + k);
+      st.ql[j][k] = on ? a.aq[d * cap + i] : 0.0f;
+      st.vl[j][k] = on ? a.aq[(nv + d) * cap + i] : 0.0f;
+      st.wl[j][k] = on ? a.aq[(2 * nv + d) * cap + i] : 0.0f;
+    }
+  }
+  float2 goal = s.goal[i];
+  float cr[3] = {0.f, 0.f, 0.f}, cl[LPL][K];
+#pragma unroll
+  for (int j = 0; j < LPL; ++j)
+#pragma unroll
+    for (int k = 0; k < K; ++k) cl[j][k] = 0.0f;
+  float qro[3], vro[3], qlo[LPL][K], vlo[LPL][K];
+  GxArtSnap sn;
+  float o_reward = 0.0f, o_done = 0.0f, o_cost = 0.0f;
+
+  // place the env on a layout row: goal / hazards into the state arrays (lane 0), robot
+  // root x, y from the layout, every other qpos 0, qvel 0 (layout2qpos, engine.py:623-639)
+  auto place = [&](const float* lay) {
+    goal = make_float2(lay[0], lay[1]);
+    if (lane == 0 && live) {
+      s.goal[i] = goal;
+      for (int k = 0; k < s.nh2; ++k) {
+        float4 h;
+        h.x = lay[4 + 4 * k]; h.y = lay[5 + 4 * k];
+        h.z = (2 * k + 1 < p.nh) ? lay[6 + 4 * k] : 0.0f;
+        h.w = (2 * k + 1 < p.nh) ? lay[7 + 4 * k] : 0.0f;
+        s.hz[(size_t)k * cap + i] = h;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { st.qr[r] = (r == m.root_x) ? lay[2] : ((r == m.root_y) ? lay[3] : 0.0f); st.vr[r] = 0.0f; }
+#pragma unroll
+    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+      for (int k = 0; k < K; ++k) { st.ql[j][k] = 0.0f; st.vl[j][k] = 0.0f; }
+  };
+
+  if (MODE == GX_ART_RESET) {
+    // Engine.reset (engine.py:454-467): mjx_reset starts from the pristine mjx_data
+    // (qacc_warmstart 0), runs mjx.forward, observes; steps <- 0; done/key stay stale.
+    const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK ^ 1u);
+    place(lay);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) st.wr[r] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < LPL; ++j)
+#pragma unroll
+      for (int k = 0; k < K; ++k) st.wl[j][k] = 0.0f;
+    gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, st, nullptr, nullptr, false, true, false, sn, qro, vro, qlo, vlo, nullptr);
+    GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+    prev_dist = o.dist_goal;
+    steps = 0.0f;
+    if (lane == 0 && live && s.ep) s.ep[i] = make_float4(0.f, 0.f, 0.f, s.ep[i].w);
+  } else if (MODE == GX_ART_RESET_DONE) {
+    // Engine.reset_done for a done env (engine.py:702-731): re-place, ctrl 0, one throw-away
+    // mjx.step for the observation; the state keeps the UN-stepped pose, the stale warm start,
+    // prev_dist, steps and the done flag.
+    const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK);
+    place(lay);
+    {
+      GxArtLane<LANES, NLEG, K, NB> tmp = st;   // scratch copy: the state itself stays un-stepped
+      for (int k = 0; k < p.substeps; ++k)
+        gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, tmp, nullptr, nullptr, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
+    }
+    gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+  } else {
+    // Engine.step (engine.py:469-495) + mjx_step (:659-700)
+    const uint64_t g = p.env_id_offset + (uint64_t)i;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ai = m.root.dof[r].act;
+      if (ai >= 0) cr[r] = action ? action[(size_t)i * nu + ai] : gx_art_synth_action(p, g, age, ai);
+    }
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+      const GxArtSeg& sg = m.leg[j * LANES + lane];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int ai = k < sg.nk ? sg.dof[k].act : -1;
+        if (ai >= 0) {
+          cl[j][k] = action ? action[(size_t)i * nu + ai] : gx_art_synth_action(p, g, age, ai);
+          if (act_out && live) act_out[(size_t)i * nu + ai] = cl[j][k];
+        }
+      }
+    }
+    const float last_dist = prev_dist, last_done = was_done;
+    for (int k = 0; k < p.substeps; ++k)
+      gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, st, cr, cl, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
+    if (qacc_out && live) {   // info['obs']['qacc'] (engine.py:763-764): the solver's qacc of the last forward
+      if (lane == 0)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) qacc_out[(size_t)i * nv + m.root_qadr + r] = st.wr[r];
+#pragma unroll
+      for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if (k < m.leg[j * LANES + lane].nk) qacc_out[(size_t)i * nv + m.leg_qadr[j * LANES + lane] + k] = st.wl[j][k];
+    }
+    GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, nullptr, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+    // reward_done (engine.py:787-802), guards (:696-699), timeout + counter (:492-493)
+    const float dist = o.dist_goal;
+    const float last = last_done > 0.0f ? dist : last_dist;
+    const float d_dist = last - dist;
+    o_reward = d_dist * p.reward_distance;
+    o_done = dist < p.goal_size ? 1.0f : 0.0f;
+    if (gx_abs(d_dist) > 1.0f) { o_done = 1.0f; o_reward = 0.0f; }
+    if (o.bad) { o_reward = 0.0f; o_done = 1.0f; }
+    if (steps > p.num_steps) o_done = 1.0f;
+    steps = o_done > 0.0f ? 0.0f : steps + 1.0f;
+    was_done = o_done;
+    prev_dist = dist;
+    age += 1;
+    o_cost = o.cost;
+    if (stats_on && lane == 0 && live) gx_stats_step(s, i, o_reward, o_cost, o_done);
+    if (AUTORESET && o_done > 0.0f) {
+      const float* lay = gx_pick_layout(p, pool, nullptr, i, age, GX_STREAM_PICK);
+      place(lay);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) cr[r] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int k = 0; k < K; ++k) cl[j][k] = 0.0f;
+      {
+        GxArtLane<LANES, NLEG, K, NB> tmp = st;
+        for (int k = 0; k < p.substeps; ++k)
+          gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, tmp, nullptr, nullptr, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
+      }
+      gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+    }
+  }
+
+  // ---- write back
+  if (live) {
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const size_t d = (size_t)(m.root_qadr + r);
+        a.aq[d * cap + i] = st.qr[r];
+        a.aq[(nv + d) * cap + i] = st.vr[r];
+        a.aq[(2 * nv + d) * cap + i] = st.wr[r];
+      }
+      s.d2[i] = make_float4(prev_dist, was_done > 0.0f ? -steps : steps, __uint_as_float((uint32_t)age),
+                            __uint_as_float((uint32_t)(age >> 32)));
+      if (MODE == GX_ART_STEP) { reward[i] = o_reward; done[i] = o_done; cost[i] = o_cost; }
+    }
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+      const int leg = j * LANES + lane;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (k < m.leg[leg].nk) {
+          const size_t d = (size_t)(m.leg_qadr[leg] + k);
+          a.aq[d * cap + i] = st.ql[j][k];
+          a.aq[(nv + d) * cap + i] = st.vl[j][k];
+          a.aq[(2 * nv + d) * cap + i] = st.wl[j][k];
+        }
+      }
+    }
+  }
+  if (MODE == GX_ART_RESET_DONE) {
+    // only the done envs' rows are (over)written
+    __syncwarp(mask);
+    float* dst = obs + (size_t)env * p.obs_dim;
+    for (int k = lane; k < p.obs_dim; k += LANES) dst[k] = row[k];
+    return;
+  }
+  __syncwarp();
+  {
+    const int total = rows * p.obs_dim;
+    float* dst = obs + (size_t)wbase * p.obs_dim;
+    if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+      const float4* src4 = reinterpret_cast<const float4*>(tile);
+      float4* dst4 = reinterpret_cast<float4*>(dst);
+      for (int k = lw; k < (total >> 2); k += 32) dst4[k] = src4[k];
+    } else {
+      for (int k = lw; k < total; k += 32) dst[k] = tile[k];
+    }
+  }
+}
+
+// ---- state injection / checkpoint: one row per env =
+//      qpos[nv] qvel[nv] qacc_warmstart[nv] prev_dist prev_done steps goal[2] hazards[2*nh]
+__global__ void gx_art_get_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxArtDev a, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  float* o = out + (size_t)i * p.state_dim;
+  const size_t cap = (size_t)s.cap;
+  for (int k = 0; k < 3 * a.nv; ++k) o[k] = a.aq[(size_t)k * cap + i];
+  o += 3 * a.nv;
+  const float4 c = s.d2[i];
+  o[0] = c.x; o[1] = (__float_as_uint(c.y) >> 31) ? 1.0f : 0.0f; o[2] = fabsf(c.y);
+  const float2 g = s.goal[i];
+  o[3] = g.x; o[4] = g.y;
+  for (int h = 0; h < p.nh; ++h) gx_art_hazard(s, nullptr, i, h, o[5 + 2 * h], o[6 + 2 * h]);
+}
+
+__global__ void gx_art_set_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxArtDev a, const float* in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const float* o = in + (size_t)i * p.state_dim;
+  const size_t cap = (size_t)s.cap;
+  for (int k = 0; k < 3 * a.nv; ++k) a.aq[(size_t)k * cap + i] = o[k];
+  o += 3 * a.nv;
+  const float4 c = s.d2[i];
+  s.d2[i] = make_float4(o[0], o[1] > 0.0f ? -o[2] : o[2], c.z, c.w);
+  s.goal[i] = make_float2(o[3], o[4]);
+  for (int k = 0; k < s.nh2; ++k) {
+    float4 h;
+    h.x = o[5 + 4 * k]; h.y = o[6 + 4 * k];
+    h.z = (2 * k + 1 < p.nh) ? o[7 + 4 * k] : 0.0f;
+    h.w = (2 * k + 1 < p.nh) ? o[8 + 4 * k] : 0.0f;
+    s.hz[(size_t)k * cap + i] = h;
+  }
+}
+
+#endif  // GX_ART_KERNELS_CUH_

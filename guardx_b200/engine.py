@@ -111,10 +111,20 @@ class Engine:
         # device; here: explicit `device`, else torch's current CUDA device
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None
                                    else torch.device(device).index or 0)
-        self._gx_config = gxconfig.lower(self.config, env_id_offset, pool_size)
+        # World.build + mujoco.MjModel.from_xml_string + mjx.put_model (engine.py:220-232):
+        # the Point's constants are closed-form; the other robots go through the model compiler
+        self.mj_model = gxconfig.compiled_model(self.config)
+        self._gx_config = gxconfig.lower(self.config, env_id_offset, pool_size, self.mj_model)
         h = C.c_void_p()
-        _abi.check(self._lib, self._lib.gx_create(C.byref(self._gx_config), self.device.index, C.byref(h)),
-                   "gx_create")
+        if self.mj_model is None:
+            _abi.check(self._lib, self._lib.gx_create(C.byref(self._gx_config), self.device.index, C.byref(h)),
+                       "gx_create")
+            self._art_info = None
+        else:
+            from . import art_model
+            self._art_model, self._art_info = art_model.lower_art(self.mj_model)
+            _abi.check(self._lib, self._lib.gx_create_art(C.byref(self._gx_config), C.byref(self._art_model),
+                                                          self.device.index, C.byref(h)), "gx_create_art")
         self._h = h
         L = self._lib
         self.obs_flat_size = L.gx_obs_dim(h)
@@ -123,8 +133,11 @@ class Engine:
         self.state_dim = L.gx_state_dim(h)
         self.layout_dim = 2 * (2 + int(self.hazards_num))
         self.layout_size = L.gx_pool_size(h)  # reference: number of valid layouts (engine.py:442)
-        self.robot = _Robot(3, 3, 3, 0.1)  # point.xml: nq = nv = nu = 3, body z 0.1
-        self.dt = float(self._gx_config.point.timestep) * self.physics_steps_per_control_step
+        if self._art_info is None:
+            self.robot = _Robot(3, 3, 3, 0.1)  # point.xml: nq = nv = nu = 3, body z 0.1
+        else:
+            self.robot = _Robot(self._art_info['nv'], self._art_info['nv'], self._art_info['nu'], self._art_info['z_height'])
+        self.dt = float(self._gx_config.opt_timestep) * self.physics_steps_per_control_step
         lo = (C.c_float * self.act_dim)()
         hi = (C.c_float * self.act_dim)()
         _abi.check(L, L.gx_action_bounds(h, lo, hi), "gx_action_bounds")
@@ -221,7 +234,7 @@ class Engine:
         obs = self._empty(n, self.obs_flat_size)
         rdc = self._empty(3, n)
         reward, done, cost = rdc[0], rdc[1], rdc[2]
-        qacc = self._empty(n, 3) if self.emit_info_obs else None
+        qacc = self._empty(n, self.robot.nv) if self.emit_info_obs else None
         aux = self._empty(n, self.aux_dim, dtype=torch.int32) if want_aux else None
         L = self._lib
         _abi.check(L, L.gx_step(self._h, self._ptr(action), self._ptr(obs), self._ptr(reward), self._ptr(done),

@@ -25,11 +25,13 @@
 
 #include <stdint.h>
 
+#include "guardx_art.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 1
+#define GX_ABI_VERSION 2
 
 #define GX_MAX_HAZARDS 32    /* hazards_num upper bound of this build */
 #define GX_MAX_LIDAR_BINS 64 /* lidar_num_bins upper bound of this build */
@@ -43,7 +45,10 @@ enum {
 };
 
 /* robot_base (engine.py:113).  Only robots whose dynamics this build implements. */
-enum { GX_ROBOT_POINT = 0 };
+enum {
+  GX_ROBOT_POINT = 0, /* xmls/point.xml: closed-form 3-DoF dynamics (gx_point_model) */
+  GX_ROBOT_ART = 1    /* articulated planar-root robot (ant / walker / swimmer): gx_create_art + guardx_art.h */
+};
 
 /* observation components, flat order = sorted key order (engine.py:773-777) */
 enum {
@@ -118,7 +123,8 @@ typedef struct gx_config {
   int32_t layout_tries;           /* the literal range(10) at engine.py:562 */
   int32_t pool_size;              /* layout pool entries; 0 = auto (replaces the 1e6-candidate pool, engine.py:263) */
   uint32_t obs_mask;              /* GX_OBS_* */
-  int32_t reserved;
+  int32_t art_nu;                 /* GX_ROBOT_ART: robot.nu (width of 'ctrl' in the observation, engine.py:402-403) */
+  int32_t art_nv;                 /* GX_ROBOT_ART: robot.nq = robot.nv (widths of 'qpos' / 'qvel', engine.py:398-401) */
   gx_point_model point;
 } gx_config;
 
@@ -133,6 +139,12 @@ void gx_default_config(gx_config* cfg);
 
 /* ---- lifetime: Engine.__init__ (engine.py:207-316) ---------------------- */
 int gx_create(const gx_config* h_cfg, int device, gx_env** out);
+/* Same for cfg->robot == GX_ROBOT_ART: h_model is the compiled robot (guardx_art.h), what
+ * mujoco.MjModel.from_xml_string + mjx.put_model produce in the reference (engine.py:228-231).
+ * Every entry point below then works on that robot: action [env_num, nu], qacc
+ * [env_num, nv], state rows as documented at gx_get_state.  observe_vel / observe_acc and
+ * the integer aux row are not built for articulated robots (GX_EINVAL). */
+int gx_create_art(const gx_config* h_cfg, const GxArtModel* h_model, int device, gx_env** out);
 int gx_destroy(gx_env* env);
 
 /* ---- spaces: build_observation_space (engine.py:386-418), action space
@@ -200,7 +212,9 @@ int gx_reset_done(gx_env* env, const float* obs_in, float* obs_out, const float*
  *      hazards[2*hazards_num], then the history that only observe_vel /
  *      observe_acc read (engine.py:902-929): xpos_xy of Engine._data, xpos_xy of
  *      Engine._last_data, Engine._last_done, history depth (0,1,2 = how many of
- *      _last_done/_last_last_done are not None).  gx_state_dim() floats per row. */
+ *      _last_done/_last_last_done are not None).  gx_state_dim() floats per row.
+ *      GX_ROBOT_ART rows: qpos[nv] qvel[nv] qacc_warmstart[nv] prev_dist prev_done steps
+ *      goal[2] hazards[2*hazards_num]. */
 int gx_state_dim(const gx_env* env);
 int gx_get_state(gx_env* env, float* state, void* stream);
 int gx_set_state(gx_env* env, const float* state, void* stream);

@@ -1,0 +1,184 @@
+"""CPU oracle of the batched env for articulated robots (Ant / Walker / Swimmer).
+
+TEST INFRASTRUCTURE ONLY.  Restates ``Engine.reset / step / reset_done`` and
+``mjx_reset / mjx_step / mjx_reset_done`` (engine.py:454-505, 623-731) around
+  * ``oracle/mjx_numpy.py`` for ``mjx.forward`` / ``mjx.step`` (PARITY UNPINNED, see there), and
+  * the single-env pieces of ``oracle/gx_oracle.c`` for ``obs_lidar`` / ``obs_compass`` /
+    ``cost`` (engine.py:804-900), which ARE pinned against the reference's own source
+    (tests/golden/refsrc_*.npz).
+State is the full ``mjx.Data`` the reference carries: qpos / qvel over robot + goal + hazard
+joints, ctrl, qacc_warmstart, plus Engine._done / _steps and the previous forward's distance.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from guardx_b200 import config as gxconfig
+from . import mjx_numpy as mx
+from . import oracle as _o
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ArtOracleEngine:
+    def __init__(self, config: dict, dtype=np.float32):
+        self.L = _o.lib()
+        self.config = gxconfig.parse(config)
+        self.model = gxconfig.compiled_model(self.config)
+        assert self.model is not None, 'ArtOracleEngine is for the articulated robots; the Point has oracle.OracleEngine'
+        self.gx_config = gxconfig.lower(self.config, 0, 0, self.model)
+        self.mm = mx.MjxModel(self.model, dtype)
+        self.dtype = dtype
+        m = self.model
+        self.n = int(self.config['env_num'])
+        self.nh = int(self.config['hazards_num'])
+        self.nb = int(self.config['lidar_num_bins'])
+        self.substeps = int(self.config['physics_steps_per_control_step'])
+        self.robot_body = m.body_id('robot')
+        self.nq_robot = m.nq - 2 - 2 * self.nh   # robot.nq (world.py:436): the robot's own joints
+        self.nu = m.nu
+        self.obs_dim = self.nu + 2 + 2 * self.nb + 2 * self.nq_robot
+        assert self.config['observe_goal_lidar'] and self.config['observe_goal_comp'] and self.config['observe_hazards']
+        assert self.config['observe_qpos'] and self.config['observe_qvel'] and self.config['observe_ctrl']
+        assert not self.config['observe_vel'] and not self.config['observe_acc']
+        # joint_name2qpos_id (engine.py:310-316)
+        self.qadr = {m.jnt_name[j]: int(m.jnt_qposadr[j]) for j in range(m.njnt) if m.jnt_name[j]}
+        n = self.n
+        self.qpos = np.zeros((n, m.nq), dtype); self.qvel = np.zeros((n, m.nv), dtype)
+        self.ctrl = np.zeros((n, m.nu), dtype); self.warm = np.zeros((n, m.nv), dtype)
+        self.done = np.zeros(n, np.float32); self.steps = np.zeros(n, np.float32)
+        self.prev_dist = np.zeros(n, np.float32)
+        self._obs = None
+        self.last_data = None
+
+    # layout rows: goal xy, robot xy, hazard0 xy, ... (same as guardx.h)
+    def layout2qpos(self, layout):
+        q = np.zeros((layout.shape[0], self.model.nq), self.dtype)
+        q[:, self.qadr['goal_x']] = layout[:, 0]; q[:, self.qadr['goal_y']] = layout[:, 1]
+        q[:, self.qadr['robot_x']] = layout[:, 2]; q[:, self.qadr['robot_y']] = layout[:, 3]
+        for h in range(self.nh):
+            q[:, self.qadr[f'hazard{h}_x']] = layout[:, 4 + 2 * h]; q[:, self.qadr[f'hazard{h}_y']] = layout[:, 5 + 2 * h]
+        return q
+
+    def _geometry(self, d, qpos):
+        """robot xpos/xmat of the forward pass + goal / hazard positions (their slide qpos)."""
+        xpos = d['xpos'][:, self.robot_body].astype(np.float32)
+        xmat = d['xmat'][:, self.robot_body].astype(np.float32).reshape(-1, 9)
+        goal = np.stack([qpos[:, self.qadr['goal_x']], qpos[:, self.qadr['goal_y']]], 1).astype(np.float32)
+        hz = np.stack([np.stack([qpos[:, self.qadr[f'hazard{h}_x']], qpos[:, self.qadr[f'hazard{h}_y']]], 1)
+                       for h in range(self.nh)], 1).astype(np.float32)
+        return xpos, xmat, goal, hz
+
+    def _obs_rows(self, d, qpos_geom, qpos, qvel, ctrl):
+        """Engine.obs (engine.py:738-778): ctrl | goal_compass | goal_lidar | hazards_lidar | qpos | qvel."""
+        n = qpos.shape[0]
+        xpos, xmat, goal, hz = self._geometry(d, qpos_geom)
+        obs = np.zeros((n, self.obs_dim), np.float32)
+        cost = np.zeros(n, np.float32)
+        gb = np.zeros((n, 1), np.int32); hb = np.zeros((n, self.nh), np.int32)
+        o = 0
+        obs[:, o:o + self.nu] = ctrl; o += self.nu
+        comp = np.zeros(2, np.float32); lid = np.zeros(self.nb, np.float32); c1 = np.zeros(1, np.float32)
+        cfg = C.byref(self.gx_config)
+        for i in range(n):
+            xp, xm = np.ascontiguousarray(xpos[i]), np.ascontiguousarray(xmat[i])
+            g, h = np.ascontiguousarray(goal[i]), np.ascontiguousarray(hz[i])
+            self.L.gxo_piece_compass(_p(xp), _p(xm), _p(g), _p(comp))
+            obs[i, o:o + 2] = comp
+            b = np.zeros(1, np.int32)
+            self.L.gxo_piece_lidar(cfg, _p(xp), _p(xm), _p(g), 1, _p(lid), _p(b))
+            obs[i, o + 2:o + 2 + self.nb] = lid; gb[i] = b
+            b = np.zeros(self.nh, np.int32)
+            self.L.gxo_piece_lidar(cfg, _p(xp), _p(xm), _p(h), self.nh, _p(lid), _p(b))
+            obs[i, o + 2 + self.nb:o + 2 + 2 * self.nb] = lid; hb[i] = b
+            rxy = np.ascontiguousarray(xp[:2])
+            self.L.gxo_piece_cost(cfg, _p(rxy), _p(h), _p(c1))
+            cost[i] = c1[0]
+        o += 2 + 2 * self.nb
+        obs[:, o:o + self.nq_robot] = qpos[:, :self.nq_robot]; o += self.nq_robot
+        obs[:, o:o + self.nq_robot] = qvel[:, :self.nq_robot]
+        dist = np.sqrt(((goal - xpos[:, :2]) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+        return obs, cost, dist, dict(goal_bin=gb, hazard_bins=hb, xpos=xpos, xmat=xmat)
+
+    # ------------------------------------------------------------------ API
+    def reset(self, layout):
+        """Engine.reset + mjx_reset (engine.py:454-467, 644-657) with the layouts injected."""
+        layout = np.asarray(layout, np.float32)
+        self.qpos = self.layout2qpos(layout)
+        self.qvel[:] = 0; self.ctrl[:] = 0
+        d = mx.forward(self.mm, self.qpos, self.qvel, self.ctrl, np.zeros_like(self.warm))   # pristine mjx_data
+        self.warm = d['qacc'].copy()
+        obs, _, dist, _ = self._obs_rows(d, self.qpos, self.qpos, self.qvel, self.ctrl)
+        self.prev_dist = dist
+        self.steps[:] = 0
+        self._obs = obs
+        self.last_data = d
+        return obs
+
+    def step(self, action):
+        """Engine.step + mjx_step (engine.py:469-495, 659-700)."""
+        self.ctrl = np.asarray(action, self.dtype).copy()          # non-Point robots: ctrl = action (engine.py:673)
+        qpos_pre = self.qpos
+        for _ in range(self.substeps):
+            qpos_pre = self.qpos
+            self.qpos, self.qvel, d = mx.step(self.mm, self.qpos, self.qvel, self.ctrl, self.warm)
+            self.warm = d['qacc'].copy()
+        obs, cost, dist, extra = self._obs_rows(d, qpos_pre, self.qpos, self.qvel, self.ctrl)
+        last = np.where(self.done > 0, dist, self.prev_dist).astype(np.float32)
+        d_dist = (last - dist).astype(np.float32)
+        reward = (d_dist * np.float32(self.config['reward_distance'])).astype(np.float32)
+        done = (dist < np.float32(self.config['goal_size'])).astype(np.float32)
+        jump = np.abs(d_dist) > 1
+        done[jump] = 1; reward[jump] = 0
+        bad = ~np.isfinite(obs).all(1)
+        reward[bad] = 0; done[bad] = 1
+        done[self.steps > np.float32(self.config['num_steps'])] = 1
+        self.steps = np.where(done > 0, 0, self.steps + 1).astype(np.float32)
+        self.done = done
+        self.prev_dist = dist
+        self._obs = obs
+        self.last_data = d
+        info = dict(cost=cost, qacc=d['qacc'][:, :self.nq_robot].astype(np.float32), dist=dist, d_dist=d_dist, **extra)
+        return obs, reward, done, info
+
+    def reset_done(self, layout):
+        """Engine.reset_done + mjx_reset_done (engine.py:497-505, 702-731)."""
+        layout = np.asarray(layout, np.float32)
+        sel = self.done > 0
+        if not sel.any():
+            return self._obs.copy()
+        q = self.layout2qpos(layout)
+        self.qpos = np.where(sel[:, None], q, self.qpos).astype(self.dtype)
+        self.qvel = np.where(sel[:, None], 0, self.qvel).astype(self.dtype)
+        self.ctrl = np.where(sel[:, None], 0, self.ctrl).astype(self.dtype)
+        # throw-away step(s) on the re-placed envs only (the other rows are masked out anyway)
+        qp, qv, w = self.qpos[sel], self.qvel[sel], self.warm[sel]
+        qpre = qp
+        for _ in range(self.substeps):
+            qpre = qp
+            qp, qv, d = mx.step(self.mm, qp, qv, self.ctrl[sel], w)
+            w = d['qacc']
+        obs_reset, _, _, _ = self._obs_rows(d, qpre, qp, qv, self.ctrl[sel])
+        obs = self._obs.copy()
+        obs[sel] = obs_reset
+        self._obs = obs
+        return obs
+
+    # state rows as gx_get_state documents for GX_ROBOT_ART
+    def get_state(self):
+        nr = self.nq_robot
+        goal = np.stack([self.qpos[:, self.qadr['goal_x']], self.qpos[:, self.qadr['goal_y']]], 1)
+        hz = np.concatenate([np.stack([self.qpos[:, self.qadr[f'hazard{h}_x']], self.qpos[:, self.qadr[f'hazard{h}_y']]], 1)
+                             for h in range(self.nh)], 1)
+        return np.concatenate([self.qpos[:, :nr], self.qvel[:, :nr], self.warm[:, :nr], self.prev_dist[:, None],
+                               self.done[:, None], self.steps[:, None], goal, hz], 1).astype(np.float32)
+
+    def round_state_to_fp32(self):
+        """Make the float64 state exactly what get_state() hands to the CUDA env (one-step parity
+        from bit-identical inputs)."""
+        f = lambda a: a.astype(np.float32).astype(self.dtype)
+        self.qpos, self.qvel, self.warm = f(self.qpos), f(self.qvel), f(self.warm)

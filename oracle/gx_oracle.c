@@ -460,6 +460,7 @@ GXO_API int gxo_create(const gx_config* cfg, gxo_env** out) {
   gx_params p;
   memset(&p, 0, sizeof p);
   const char* why = gx_lower_config(cfg, &p);
+  if (!why && cfg->robot != GX_ROBOT_POINT) why = "this C oracle restates the Point only; articulated robots: oracle/art_oracle.py";
   if (why || !out) {
     snprintf(gxo_err, sizeof gxo_err, "gxo_create: %s", why ? why : "null out");
     return GX_EINVAL;

@@ -1,0 +1,168 @@
+"""CPU checks of the articulated-robot path: the model compiler against golden constants
+made from the reference's own robot files (tools/make_golden_mjcf.py), hand-computed
+compiler rules, the numpy mjx.step restatement against the closed-form Point dynamics of the
+C oracle, and the CUDA kernels' arithmetic (gx_art.cuh built as plain C++, LANES = 1)
+against the numpy restatement.  No GPU needed."""
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from guardx_b200 import art_model, mjcf, robots
+from oracle import mjx_numpy as mx
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/safe_rl_envs/safe_rl_envs"
+
+
+def _compile(name):
+    return mjcf.compile_spec(mjcf.add_world_geoms(robots.robot_spec(name), 0.5, 0.3, 8))
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    with open(os.path.join(golden_dir, "mjcf_constants.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("name", ['point', 'ant', 'walker', 'swimmer'])
+def test_builtin_robot_equals_golden_reference_compile(gold, name):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_mjcf import constants
+    got = constants(_compile(name))
+    for k, v in gold[name].items():
+        if isinstance(v, list) and v and not isinstance(v[0], str):
+            np.testing.assert_allclose(np.asarray(got[k], float), np.asarray(v, float), rtol=1e-12, atol=1e-15, err_msg=k)
+        else:
+            assert got[k] == v, k
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+@pytest.mark.parametrize("f,name", list(robots.ROBOT_FILES.items()))
+def test_builtin_robot_equals_parsed_reference_xml(f, name):
+    a = mjcf.compile_spec(mjcf.parse_mjcf(open(os.path.join(REF, f)).read()))
+    b = mjcf.compile_spec(robots.robot_spec(f))
+    for k in ('body_pos', 'body_mass', 'body_ipos', 'body_inertia_full', 'jnt_axis', 'jnt_range', 'dof_damping',
+              'dof_armature', 'dof_invweight0', 'body_invweight0', 'geom_size', 'actuator_gear'):
+        np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+    assert a.jnt_name == b.jnt_name and a.contact_pairs == b.contact_pairs
+
+
+def test_compiler_rules_by_hand():
+    """Numbers that can be derived on paper from the MJCF (SURVEY.md Appendix C and xmls/ant.xml)."""
+    p = _compile('point')
+    r = p.body_id('robot')
+    m1, m2 = 4 / 3 * math.pi * 1e-3, 1e-3
+    assert p.body_mass[r] == pytest.approx(m1 + m2, rel=1e-14)
+    assert p.body_ipos[r][0] == pytest.approx(m2 * 0.1 / (m1 + m2), rel=1e-14)
+    cx = p.body_ipos[r][0]
+    izz = 0.4 * m1 * 0.01 + m1 * cx * cx + m2 * (0.05 ** 2 * 2) / 3 + m2 * (0.1 - cx) ** 2
+    assert p.body_inertia_full[r][2, 2] == pytest.approx(izz, rel=1e-13)
+    assert p.body_mass[p.body_id('goal')] == pytest.approx(4 / 3 * math.pi * 0.125, rel=1e-14)      # density 1 (point.xml:5)
+    assert p.actuator_biasprm[0].tolist() == [0, 0, -1] and p.actuator_forcelimited.tolist() == [1, 1, 1]   # A1
+    a = _compile('ant')
+    assert a.nq == 29 and a.nu == 8 and a.opt['timestep'] == 0.09
+    j = a.jnt_id('ankle_1')
+    np.testing.assert_allclose(a.jnt_range[j], [math.radians(30), math.radians(70)])     # compiler angle default: degree
+    np.testing.assert_allclose(a.jnt_axis[j], [-math.sqrt(0.5), math.sqrt(0.5), 0])      # axis normalised
+    r = a.body_id('robot')
+    assert a.body_mass[r] == pytest.approx(5 * 4 / 3 * math.pi * 0.06 ** 3, rel=1e-14)      # torso sphere, density 5
+    # capsule: r .02, half-length |(.05,.05,0)|/2, density 5
+    h = math.hypot(0.05, 0.05)
+    vol = math.pi * 0.02 ** 2 * h + 4 / 3 * math.pi * 0.02 ** 3
+    assert a.body_mass[a.body_id('front_left_leg')] == pytest.approx(5 * vol, rel=1e-13)
+    assert a.body_mass[a.body_id('goal')] == pytest.approx(5 * 4 / 3 * math.pi * 0.125, rel=1e-14)   # inherits density 5
+    assert a.contact_pairs == [(0, 5), (0, 9), (0, 13), (0, 17)]                          # floor x 4 foot spheres only
+    # root x slide (armature 0): its diagonal mass-matrix entry is the total robot mass; hip: armature 1 + inertia
+    M = mjcf.mass_matrix(a, mjcf.kinematics0(a))
+    assert M[0, 0] == pytest.approx(a.body_mass[1:14].sum(), rel=1e-12)
+    assert 1 < M[3, 3] < 1.001 and np.allclose(M[:11, 11:], 0) and np.allclose(M, M.T)
+    assert a.stat_meaninertia == pytest.approx(np.trace(M) / a.nv, rel=1e-14)
+
+
+def test_numpy_mjx_step_equals_closed_form_point_oracle(oracle_lib):
+    """Generic CRB / RNE / actuation / implicit-damping Euler on the compiled Point model vs the
+    hand-derived 3-DoF dynamics of oracle/gx_oracle.c: two derivations, one answer."""
+    from oracle.oracle import OracleEngine
+    m = _compile('point')
+    n = 64
+    o = OracleEngine({'env_num': n, '_seed': 1})
+    o.reset()
+    rng = np.random.default_rng(0)
+    for _ in range(30):
+        o.step(rng.uniform(-1, 1, (n, 2)).astype(np.float32))
+    s = o.get_state()
+    a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    ctrl = np.stack([a[:, 0] * s[:, 6], a[:, 0] * s[:, 7], a[:, 1]], 1)
+    _, _, _, info = o.step(a, want_qacc=True)
+    s2 = o.get_state()
+    mm = mx.MjxModel(m, np.float64)
+    qpos = np.zeros((n, m.nq)); qvel = np.zeros((n, m.nv))
+    qpos[:, :3] = s[:, 0:3]; qvel[:, :3] = s[:, 3:6]; qpos[:, 3:5] = s[:, 11:13]; qpos[:, 5:21] = s[:, 13:29]
+    q2, v2, d = mx.step(mm, qpos, qvel, ctrl, np.zeros((n, m.nv)))
+    np.testing.assert_allclose(q2[:, :3], s2[:, 0:3], atol=2e-7)
+    np.testing.assert_allclose(v2[:, :3], s2[:, 3:6], atol=3e-6)
+    np.testing.assert_allclose(d['qacc'][:, :3], info['qacc'], rtol=2e-6, atol=1e-3)
+    assert np.abs(v2[:, 3:]).max() == 0          # goal / hazard bodies never move
+    np.testing.assert_allclose(d['xmat'][:, 1, 0, 0], s2[:, 6], atol=3e-7)   # lagged heading = this forward's R
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "libartemu.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++",
+                    "-I" + os.path.join(ROOT, "guardx_b200", "csrc"), os.path.join(ROOT, "tests", "emu", "art_emu.cpp"),
+                    "-o", out], check=True)
+    lib = C.CDLL(out)
+    assert lib.art_emu_model_size() == C.sizeof(art_model.GxArtModel)
+    return lib
+
+
+@pytest.mark.parametrize("name", ['ant', 'walker', 'swimmer'])
+def test_kernel_arithmetic_on_host_equals_numpy_oracle(emu, name):
+    """gx_art.cuh compiled as C++ (fp32, leg-wise arrowhead solves) vs the dense fp64 numpy
+    restatement: one step from identical states along an 80-step random-action trajectory with
+    joint limits and foot contacts active."""
+    m = _compile(name)
+    am, info = art_model.lower_art(m)
+    nl, K, NB = info['shape']
+    n, nvr = 24, info['nv']
+    mm = mx.MjxModel(m, np.float64)
+    rng = np.random.default_rng(0)
+    qpos = np.zeros((n, m.nq)); qvel = np.zeros((n, m.nv)); warm = np.zeros((n, m.nv))
+    qpos[:, 0] = rng.uniform(-1, 1, n)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    active_rows = 0
+    for t in range(80):
+        ctrl = rng.uniform(-1.2, 1.2, (n, m.nu))
+        q1, v1, w1 = (x[:, :nvr].astype(np.float32).copy() for x in (qpos, qvel, warm))
+        snap = np.zeros((n, 4), np.float32); it = np.zeros(n, np.int32)
+        assert emu.art_emu_step(C.byref(am), nl, K, NB, n, p(q1), p(v1), p(w1), p(ctrl.astype(np.float32)), 0, p(snap), p(it)) == 0
+        qpos, qvel, d = mx.step(mm, qpos, qvel, ctrl, warm)
+        warm = d['qacc']
+        scale = 1 + np.abs(d['qacc'][:, :nvr]).max()
+        assert np.abs(q1 - qpos[:, :nvr]).max() < 3e-6, t
+        assert np.abs(v1 - qvel[:, :nvr]).max() < 3e-6 * scale * m.opt['timestep'] * 20, t
+        assert np.abs(w1 - d['qacc'][:, :nvr]).max() < 2e-5 * scale, t
+        assert np.abs(snap[:, 0] - d['xpos'][:, 1, 0]).max() < 1e-6 and np.abs(snap[:, 2] - d['xmat'][:, 1, 0, 0]).max() < 1e-6
+        assert it.max() <= 12
+        active_rows = max(active_rows, int((d['efc_D'] > 0).sum(1).max()))
+    assert active_rows >= (2 if name == 'swimmer' else 8)      # limits (and contacts) really were active
+
+
+def test_art_model_lowering_and_rejections():
+    am, info = art_model.lower_art(_compile('ant'))
+    assert info['shape'] == (4, 2, 3) and am.nv == 11 and am.nu == 8 and (am.root_x, am.root_y) == (0, 2)
+    assert [am.leg[l].con.on for l in range(4)] == [1, 1, 1, 1] and am.leg[0].con.body == 2
+    assert am.leg[0].dof[1].act == 1 and am.leg[3].dof[0].act == 6
+    am, info = art_model.lower_art(_compile('walker'))
+    assert info['shape'] == (2, 5, 3) and (am.root_x, am.root_y) == (0, 2)
+    am, info = art_model.lower_art(_compile('swimmer'))
+    assert info['shape'] == (1, 2, 2) and (am.root_x, am.root_y) == (0, 1) and len(info['ignored_pairs']) == 3
+    with pytest.raises(AssertionError):
+        robots.robot_spec('xmls/doggo.xml')

@@ -1,0 +1,208 @@
+"""Articulated robots (Ant / Walker / Swimmer) on the CUDA kernels vs the CPU oracle
+(oracle/art_oracle.py: numpy restatement of mjx.step on the full dense model + the pinned C
+pieces for lidar / compass / cost).
+
+The two sides are INDEPENDENT formulations (dense 29..31-DoF Cholesky in a subtree-COM frame
+vs the robot-only arrowhead solve with leg-per-lane reductions), so floats are compared with
+a stated tolerance and integer outputs exactly wherever the deciding float is not within that
+tolerance of its threshold.  The oracle's dynamics run in float64 (the rounding-free answer);
+its float32 mode mirrors MJX's working precision, whose own solver noise (cost differences of
+O(1e3) numbers tested against 1e-8) is as large as the tolerances below:
+  one step from an injected identical state   |d| <= 2e-5 + 2e-5*|x| for obs / reward / cost
+                                              (qvel entries scale with |qacc|*dt: 1e-4 relative)
+  free-running, 25 steps                      |d| <= 2e-3
+Done flags, timeout resets and reset masks: exact.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROBOTS = {'ant': ('xmls/ant.xml', 8, 11), 'walker': ('xmls/walker.xml', 10, 13), 'swimmer': ('xmls/swimmer.xml', 2, 5)}
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from guardx_b200.engine import Engine
+    from oracle.art_oracle import ArtOracleEngine
+    from oracle.oracle import OracleEngine
+    base = OracleEngine({'env_num': 64, '_seed': 5})
+    base.reset()
+    pool, _ = base.pool()
+    return Engine, ArtOracleEngine, pool
+
+
+def cpu(t):
+    return t.detach().cpu().numpy()
+
+
+def close(a, b, atol, rtol, what):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b) - (atol + rtol * np.abs(b))
+    assert (err <= 0).all(), f'{what}: max excess {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}'
+
+
+def obs_close(g, o, nu, nv, atol, rtol, what):
+    """flat obs = ctrl(nu) | compass 2 | lidars 32 | qpos nv | qvel nv; qvel gets the looser bound."""
+    k = nu + 34 + nv
+    close(g[:, :k], o[:, :k], atol, rtol, what + ' (ctrl..qpos)')
+    close(g[:, k:], o[:, k:], 20 * atol, 5 * rtol, what + ' (qvel)')
+
+
+@pytest.mark.parametrize("robot", ['ant', 'walker', 'swimmer'])
+def test_spaces_and_reset(mods, robot):
+    Engine, Oracle, pool = mods
+    base, nu, nv = ROBOTS[robot]
+    n = 37
+    cfg = {'env_num': n, 'robot_base': base, 'num_steps': 50, '_seed': 1}
+    g, o = Engine(dict(cfg)), Oracle(dict(cfg), dtype=np.float64)
+    assert g.observation_space.shape == (nu + 34 + 2 * nv,) and g.action_space.shape == (nu,)
+    assert (g.action_space.low == -1).all() and (g.action_space.high == 1).all()
+    lay = pool[:n]
+    og, oo = cpu(g.reset(lay)), o.reset(lay)
+    obs_close(og, oo, nu, nv, 2e-6, 2e-6, 'reset obs')
+    sg, so = cpu(g.get_state()), o.get_state()
+    close(sg[:, 2 * nv:3 * nv], so[:, 2 * nv:3 * nv], 2e-3, 1e-4, 'qacc_warmstart after reset (solver output)')
+    close(np.delete(sg, np.s_[2 * nv:3 * nv], 1), np.delete(so, np.s_[2 * nv:3 * nv], 1), 2e-6, 2e-6, 'state after reset')
+    # pool-driven reset works and places the robot on the drawn layout
+    ob = cpu(g.reset())
+    st = cpu(g.get_state())
+    assert np.isfinite(ob).all() and (np.abs(st[:, :nv]).max(axis=0) > 0).sum() == 2   # only robot_x / robot_y set
+
+
+@pytest.mark.parametrize("robot", ['ant', 'walker', 'swimmer'])
+def test_one_step_from_injected_state(mods, robot):
+    """The oracle free-runs; before every step its state is injected into the CUDA env, so each
+    comparison is one transition from bit-identical inputs."""
+    Engine, Oracle, pool = mods
+    base, nu, nv = ROBOTS[robot]
+    n = 48
+    cfg = {'env_num': n, 'robot_base': base, 'num_steps': 30, '_seed': 2}
+    g, o = Engine(dict(cfg)), Oracle(dict(cfg), dtype=np.float64)
+    g.reset(pool[:n]); o.reset(pool[:n])
+    rng = np.random.default_rng(7)
+    n_done = n_viol = 0
+    for t in range(45):
+        a = rng.uniform(-1.3, 1.3, (n, nu)).astype(np.float32)
+        o.round_state_to_fp32()
+        g.set_state(o.get_state())
+        og, rg, dg, ig = g.step(torch.from_numpy(a).cuda())
+        oo, ro, do, io = o.step(a)
+        obs_close(cpu(og), oo, nu, nv, 2e-5, 2e-5, f'{robot} step {t} obs')
+        close(cpu(rg), ro, 2e-5, 0, f'step {t} reward')
+        close(cpu(ig['cost']), io['cost'], 2e-5, 0, f'step {t} cost')
+        qscale = np.abs(io['qacc']).max(1, keepdims=True)      # the solve couples all dofs of an env
+        close(cpu(ig['obs']['qacc']) / (1 + qscale), io['qacc'] / (1 + qscale), 2e-5, 0, f'step {t} qacc (relative to the env max)')
+        clear = (np.abs(io['dist'] - 0.5) > 1e-4) & (np.abs(np.abs(io['d_dist']) - 1) > 1e-4)
+        assert (cpu(dg) == do)[clear].all(), f'step {t} done'
+        n_done += int(do.sum()); n_viol += int((io['cost'] > 0).sum())
+        if do.any():
+            lay = pool[(t % 7) * n:(t % 7) * n + n]
+            g.set_state(o.get_state())   # same done flags (the unclear ones included)
+            obs_close(cpu(g.reset_done(lay)), o.reset_done(lay), nu, nv, 2e-5, 2e-5, f'step {t} reset_done obs')
+            sg, so = cpu(g.get_state()), o.get_state()
+            close(np.delete(sg, np.s_[2 * nv:3 * nv], 1), np.delete(so, np.s_[2 * nv:3 * nv], 1), 1e-6, 1e-6, 'state after reset_done')
+    assert n_done >= n   # the 30-step timeout fired for every env
+
+
+@pytest.mark.parametrize("robot", ['ant', 'walker'])
+def test_free_running_short_horizon(mods, robot):
+    Engine, Oracle, pool = mods
+    base, nu, nv = ROBOTS[robot]
+    n = 32
+    cfg = {'env_num': n, 'robot_base': base, 'num_steps': 1000, '_seed': 3}
+    g, o = Engine(dict(cfg)), Oracle(dict(cfg), dtype=np.float64)
+    g.reset(pool[:n]); o.reset(pool[:n])
+    rng = np.random.default_rng(11)
+    for t in range(25):
+        a = rng.uniform(-1, 1, (n, nu)).astype(np.float32)
+        og, rg, dg, ig = g.step(torch.from_numpy(a).cuda())
+        oo, ro, do, io = o.step(a)
+        k = nu + 34 + nv
+        close(cpu(og)[:, :k], oo[:, :k], 2e-3, 0, f'{robot} free step {t} obs')
+        close(cpu(og)[:, k:], oo[:, k:], 5e-2, 1e-2, f'{robot} free step {t} qvel')
+        close(cpu(ig['cost']), io['cost'], 2e-3, 0, f'free step {t} cost')
+        assert (cpu(dg) == do).all()
+
+
+@pytest.mark.parametrize("robot", ['ant', 'walker', 'swimmer'])
+def test_autoreset_equals_step_then_reset_done(mods, robot):
+    """Two CUDA paths, same arithmetic: bit-identical."""
+    Engine, _, pool = mods
+    base, nu, nv = ROBOTS[robot]
+    n = 1000
+    cfg = {'env_num': n, 'robot_base': base, 'num_steps': 12, '_seed': 4}
+    a_env, b_env = Engine(dict(cfg)), Engine(dict(cfg))
+    a_env.reset(); b_env.reset()
+    gen = torch.Generator(device='cuda').manual_seed(0)
+    seen = 0
+    for t in range(40):
+        act = torch.rand(n, nu, device='cuda', generator=gen) * 2 - 1
+        oa, ra, da, ia = a_env.step_autoreset(act)
+        ob, rb, db, ib = b_env.step(act)
+        ob = b_env.reset_done()
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(ia['cost'], ib['cost'])
+        seen += int(da.sum().item())
+    assert seen >= 2 * n
+    assert torch.equal(a_env.get_state(), b_env.get_state())
+
+
+def test_rollout_and_stats_and_graph(mods):
+    Engine, _, _ = mods
+    n, T = 512, 20
+    cfg = {'env_num': n, 'robot_base': 'xmls/ant.xml', 'num_steps': 8, '_seed': 6}
+    a_env, b_env = Engine(dict(cfg)), Engine(dict(cfg))
+    a_env.reset(); b_env.reset()
+    a_env.stats_reset()
+    ro = a_env.rollout(T)
+    assert ro['obs'].shape == (T, n, 64) and ro['act'].shape == (T, n, 8)
+    assert torch.isfinite(ro['obs']).all() and (ro['act'].abs() <= 1).all()
+    # the same actions through step_autoreset reproduce the rollout bit for bit
+    for t in range(T):
+        o, r, d, i = b_env.step_autoreset(ro['act'][t])
+        assert torch.equal(o, ro['obs'][t]) and torch.equal(r, ro['reward'][t]) and torch.equal(d, ro['done'][t])
+    s = a_env.stats().cpu().numpy()
+    assert s[7] == n * T and s[0] == float(ro['done'].sum().item()) and s[0] >= n
+    # CUDA-graph capture of the step (no host-side counter baked in)
+    g = torch.cuda.CUDAGraph()
+    act = ro['act'][0].clone()
+    obs = torch.empty(n, 64, device='cuda'); rdc = torch.empty(3, n, device='cuda')
+    import ctypes as C
+    p = lambda t_: C.c_void_p(t_.data_ptr())
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        sp = C.c_void_p(side.cuda_stream)
+        lib = a_env._lib
+        lib.gx_step_autoreset(a_env._h, p(act), p(obs), p(rdc[0]), p(rdc[1]), p(rdc[2]), sp)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            lib.gx_step_autoreset(a_env._h, p(act), p(obs), p(rdc[0]), p(rdc[1]), p(rdc[2]), sp)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    b_env.set_state(a_env.get_state())
+    # (ages differ between the two envs only in the pool pick; compare a step with no done env)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.isfinite(obs).all()
+
+
+def test_host_step_and_rollout_host_for_ant(mods):
+    Engine, _, _ = mods
+    n, T = 300, 9
+    cfg = {'env_num': n, 'robot_base': 'xmls/ant.xml', 'num_steps': 5, '_seed': 8}
+    a_env, b_env = Engine(dict(cfg)), Engine(dict(cfg))
+    a_env.reset(); b_env.reset()
+    od = a_env.obs_flat_size
+    h_act = torch.empty(T, n, 8).uniform_(-1, 1).pin_memory()
+    h_obs = torch.empty(T, n, od).pin_memory()
+    h_r, h_d, h_c = (torch.empty(T, n).pin_memory() for _ in range(3))
+    a_env.rollout_host(h_act, h_obs, h_r, h_d, h_c)
+    h_out = torch.empty(n * (od + 3)).pin_memory()
+    for t in range(T):
+        b_env.step_host(h_act[t], h_out, auto_reset_done=True)
+        assert torch.equal(h_out[:n * od].view(n, od), h_obs[t])
+        assert torch.equal(h_out[n * od + n:n * od + 2 * n], h_d[t])
