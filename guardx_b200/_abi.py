@@ -145,7 +145,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("GUARDX_LIB") or LIB_PATH   # GUARDX_LIB: developer override (kernel build variants)
     if not os.path.exists(p):
         raise GuardXError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -835,9 +835,16 @@ static int gx_art_launch(gx_env* e, cudaStream_t st, const float* layout, const 
   do {                                                                                                       \
     const int grid = div_up(n * (L), block);                                                                 \
     const size_t sh = (size_t)(block / (L)) * e->p.obs_dim * sizeof(float);                                  \
-    gx_art_kernel<L, NL, K, NB, MODE, AR><<<grid, block, sh, st>>>(e->p, e->s, e->art, e->pool, layout,     \
-                                                                       action, obs_in, obs, act_out, reward, \
-                                                                       done, cost, qacc, e->stats_on ? 1 : 0); \
+    if constexpr (MODE == GX_ART_STEP) {                                                                     \
+      if (grid > 3 * e->sm_count) {                                                                          \
+      gx_art_kernel<L, NL, K, NB, MODE, AR, 4><<<grid, block, sh, st>>>(e->p, e->s, e->art, e->pool, layout, \
+                                                                        action, obs_in, obs, act_out, reward, \
+                                                                        done, cost, qacc, e->stats_on ? 1 : 0); \
+      break; }                                                                                               \
+    }                                                                                                        \
+      gx_art_kernel<L, NL, K, NB, MODE, AR, 2><<<grid, block, sh, st>>>(e->p, e->s, e->art, e->pool, layout, \
+                                                                        action, obs_in, obs, act_out, reward, \
+                                                                        done, cost, qacc, e->stats_on ? 1 : 0); \
   } while (0)
   switch (e->art_shape) {
     case 1: GX_ART_GO(4, 4, 2, 3); break;

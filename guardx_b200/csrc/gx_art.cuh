@@ -517,20 +517,6 @@ GX_HD void gx_art_step(const GxArtModel& m, int lane, unsigned mask, GxArtLane<L
       }
     }
   }
-  // ---------------- qacc_smooth = M^-1 qfrc_smooth ----------------
-  float sr[3] = {fr[0], fr[1], fr[2]}, sl[LPL][K];
-  {
-    float A[LPL][K][K];
-#pragma unroll
-    for (int j = 0; j < LPL; ++j)
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        sl[j][i] = fl[j][i];
-#pragma unroll
-        for (int s = 0; s < K; ++s) A[j][i][s] = Mll[j][i][s];
-      }
-    gx_art_arrow_solve<LANES, NLEG, K>(&A, C, nullptr, Mrr, nk, sl, sr, mask);
-  }
   // ---------------- constraint rows (mjx make_constraint) ----------------
   GxArtRows<K> rows[LPL];
   int any_row = 0;
@@ -600,107 +586,73 @@ GX_HD void gx_art_step(const GxArtModel& m, int lane, unsigned mask, GxArtLane<L
     }
   }
   any_row = gx_art_or<LANES>(any_row, mask);
-  // ---------------- solver.solve: Newton on the primal cost ----------------
-  float ar[3] = {sr[0], sr[1], sr[2]}, al[LPL][K];     // qacc
-  float fcr[3] = {0.f, 0.f, 0.f}, fcl[LPL][K];          // qfrc_constraint
+  // ---------------- one phase loop for every linear solve ----------------
+  // qacc_smooth = M^-1 qfrc_smooth, then (if any constraint row is active) solver.solve:
+  // Newton on the primal cost with warm start, then euler's implicit-damping solve
+  // (M + dt*damping) qacc = qfrc_smooth + qfrc_constraint.  All three are "assemble an
+  // arrowhead matrix, factor, solve"; keeping them in ONE non-unrolled loop keeps ONE copy
+  // of the assembly / Cholesky / Schur code in the instruction stream (the fully inlined
+  // version was 55 k SASS instructions and stalled 28 % of the time on instruction fetch).
+  float sr[3] = {0.f, 0.f, 0.f}, sl[LPL][K];      // qacc_smooth
+  float ar[3] = {0.f, 0.f, 0.f}, al[LPL][K];      // qacc
+  float fcr[3] = {0.f, 0.f, 0.f}, fcl[LPL][K];    // qfrc_constraint
+  float Mar[3] = {0.f, 0.f, 0.f}, Mal[LPL][K], jl[LPL][K], jc[LPL][4];   // M*qacc, J*qacc - aref
+  float er[3] = {0.f, 0.f, 0.f}, el[LPL][K];      // euler qacc
 #pragma unroll
-  for (int j = 0; j < LPL; ++j)
+  for (int j = 0; j < LPL; ++j) {
 #pragma unroll
-    for (int i = 0; i < K; ++i) { al[j][i] = sl[j][i]; fcl[j][i] = 0.0f; }
-  int iters = 0;
-  if (any_row) {
-    // M*x for the arrowhead matrix (root part reduced over lanes)
-    auto mul_m = [&](const float* xr, const float (*xl)[K], float* yr, float (*yl)[K]) {
-      float t[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < K; ++i) { sl[j][i] = 0.f; al[j][i] = 0.f; fcl[j][i] = 0.f; Mal[j][i] = 0.f; jl[j][i] = 0.f; el[j][i] = 0.f; }
 #pragma unroll
-      for (int j = 0; j < LPL; ++j)
+    for (int k = 0; k < 4; ++k) jc[j][k] = 0.f;
+  }
+  // M*x for the arrowhead matrix (root part reduced over lanes)
+  auto mul_m = [&](const float* xr, const float (*xl)[K], float* yr, float (*yl)[K]) {
+    float t[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-          float s = 0.0f;
-          if (i < nk[j]) {
+    for (int j = 0; j < LPL; ++j)
 #pragma unroll
-            for (int k = 0; k < K; ++k) if (k < nk[j]) s = gx_fma(k <= i ? Mll[j][i][k] : Mll[j][k][i], xl[j][k], s);
+      for (int i = 0; i < K; ++i) {
+        float s = 0.0f;
+        if (i < nk[j]) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) { s = gx_fma(C[j][i][r], xr[r], s); t[r] = gx_fma(C[j][i][r], xl[j][i], t[r]); }
-          }
-          yl[j][i] = s;
+          for (int k = 0; k < K; ++k) if (k < nk[j]) s = gx_fma(k <= i ? Mll[j][i][k] : Mll[j][k][i], xl[j][k], s);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) { s = gx_fma(C[j][i][r], xr[r], s); t[r] = gx_fma(C[j][i][r], xl[j][i], t[r]); }
         }
-#pragma unroll
-      for (int r = 0; r < 3; ++r) t[r] = gx_art_sum<LANES>(t[r], mask);
-      yr[0] = t[0] + (Mrr[0] * xr[0] + Mrr[1] * xr[1] + Mrr[3] * xr[2]);
-      yr[1] = t[1] + (Mrr[1] * xr[0] + Mrr[2] * xr[1] + Mrr[4] * xr[2]);
-      yr[2] = t[2] + (Mrr[3] * xr[0] + Mrr[4] * xr[1] + Mrr[5] * xr[2]);
-    };
-    // J*x for this lane's rows: limits K, contact 4
-    auto mul_j = [&](int j, const float* xr, const float* xl, float* ylim, float* ycon) {
-      const GxArtRows<K>& R = rows[j];
-#pragma unroll
-      for (int i = 0; i < K; ++i) ylim[i] = R.ls[i] * xl[i];
-      float n = 0.f, t1 = 0.f, t2 = 0.f;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) { n = gx_fma(R.cj[0][r], xr[r], n); t1 = gx_fma(R.cj[1][r], xr[r], t1); t2 = gx_fma(R.cj[2][r], xr[r], t2); }
-#pragma unroll
-      for (int i = 0; i < K; ++i) { n = gx_fma(R.cj[0][3 + i], xl[i], n); t1 = gx_fma(R.cj[1][3 + i], xl[i], t1); t2 = gx_fma(R.cj[2][3 + i], xl[i], t2); }
-      ycon[0] = n + R.cmu * t1; ycon[1] = n - R.cmu * t1; ycon[2] = n + R.cmu * t2; ycon[3] = n - R.cmu * t2;
-    };
-    // cost of a candidate qacc (+ its Ma, Jaref), replicated on all lanes
-    float Mar[3], Mal[LPL][K], jl[LPL][K], jc[LPL][4];
-    auto eval = [&](const float* xr, const float (*xl)[K]) -> float {
-      mul_m(xr, xl, Mar, Mal);
-      float local = 0.0f;
-#pragma unroll
-      for (int j = 0; j < LPL; ++j) {
-        mul_j(j, xr, xl[j], jl[j], jc[j]);
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-          jl[j][i] -= rows[j].laref[i];
-          if (jl[j][i] < 0.0f) local = gx_fma(0.5f * rows[j].lD[i] * jl[j][i], jl[j][i], local);
-          local = gx_fma(0.5f * (Mal[j][i] - fl[j][i]), xl[j][i] - sl[j][i], local);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          jc[j][k] -= rows[j].caref[k];
-          if (rows[j].con && jc[j][k] < 0.0f) local = gx_fma(0.5f * rows[j].cD * jc[j][k], jc[j][k], local);
-        }
+        yl[j][i] = s;
       }
-      float cost = gx_art_sum<LANES>(local, mask);
 #pragma unroll
-      for (int r = 0; r < 3; ++r) cost = gx_fma(0.5f * (Mar[r] - fr[r]), xr[r] - sr[r], cost);
-      return cost;
-    };
-    // warm start (mjx solver.solve): start from qacc_warmstart iff its cost beats qacc_smooth's
-    const float cost_w = eval(st.wr, st.wl);
-    const float cost_s = eval(sr, sl);
-    if (cost_w < cost_s) {
+    for (int r = 0; r < 3; ++r) t[r] = gx_art_sum<LANES>(t[r], mask);
+    yr[0] = t[0] + (Mrr[0] * xr[0] + Mrr[1] * xr[1] + Mrr[3] * xr[2]);
+    yr[1] = t[1] + (Mrr[1] * xr[0] + Mrr[2] * xr[1] + Mrr[4] * xr[2]);
+    yr[2] = t[2] + (Mrr[3] * xr[0] + Mrr[4] * xr[1] + Mrr[5] * xr[2]);
+  };
+  // J*x for this lane's rows: limits K, contact 4
+  auto mul_j = [&](int j, const float* xr, const float* xl, float* ylim, float* ycon) {
+    const GxArtRows<K>& R = rows[j];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) ar[r] = st.wr[r];
+    for (int i = 0; i < K; ++i) ylim[i] = R.ls[i] * xl[i];
+    float n = 0.f, t1 = 0.f, t2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < LPL; ++j)
+    for (int r = 0; r < 3; ++r) { n = gx_fma(R.cj[0][r], xr[r], n); t1 = gx_fma(R.cj[1][r], xr[r], t1); t2 = gx_fma(R.cj[2][r], xr[r], t2); }
 #pragma unroll
-        for (int i = 0; i < K; ++i) al[j][i] = st.wl[j][i];
-      eval(ar, al);
-    }
-    for (int it = 0; it < m.max_iter; ++it) {
-      // gradient = Ma - qfrc_smooth - J^T force ; Hessian blocks = M + J^T D J (active rows)
-      float gr_loc[3] = {0.f, 0.f, 0.f}, gl[LPL][K];
-      float A[LPL][K][K], Cc[LPL][K][3], Arr[LPL][6];
-      float gn_loc = 0.0f;
+    for (int i = 0; i < K; ++i) { n = gx_fma(R.cj[0][3 + i], xl[i], n); t1 = gx_fma(R.cj[1][3 + i], xl[i], t1); t2 = gx_fma(R.cj[2][3 + i], xl[i], t2); }
+    ycon[0] = n + R.cmu * t1; ycon[1] = n - R.cmu * t1; ycon[2] = n + R.cmu * t2; ycon[3] = n - R.cmu * t2;
+  };
+  enum { PH_SMOOTH = 0, PH_NEWTON = 1, PH_EULER = 2 };
+  int mode = PH_SMOOTH, iters = 0;
+  bool finish = false;
+#pragma unroll 1
+  for (int trip = 0; trip < m.max_iter + 4; ++trip) {
+    float A[LPL][K][K], Cc[LPL][K][3], Arr[LPL][6], bl[LPL][K], br[3];
+    // ---- Newton: constraint forces and gradient at the current qacc
+    if (mode == PH_NEWTON) {
+      float gr_loc[3] = {0.f, 0.f, 0.f}, gn_loc = 0.0f;
 #pragma unroll
       for (int j = 0; j < LPL; ++j) {
         const GxArtRows<K>& R = rows[j];
 #pragma unroll
-        for (int e = 0; e < 6; ++e) Arr[j][e] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-#pragma unroll
-          for (int s = 0; s < K; ++s) A[j][i][s] = Mll[j][i][s];
-#pragma unroll
-          for (int r = 0; r < 3; ++r) Cc[j][i][r] = C[j][i][r];
-          float force = 0.0f;
-          if (jl[j][i] < 0.0f) { force = -R.lD[i] * jl[j][i]; A[j][i][i] += R.lD[i]; }  // ls^2 = 1 on active rows
-          fcl[j][i] = R.ls[i] * force;
-        }
-        float fc_r[3] = {0.f, 0.f, 0.f};
+        for (int i = 0; i < K; ++i) fcl[j][i] = (jl[j][i] < 0.0f) ? R.ls[i] * (-R.lD[i] * jl[j][i]) : 0.0f;
         if (R.con) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -708,157 +660,235 @@ GX_HD void gx_art_step(const GxArtModel& m, int lane, unsigned mask, GxArtLane<L
               const float force = -R.cD * jc[j][k];
               const float sg_ = (k & 1) ? -R.cmu : R.cmu;
               const int ta = 1 + (k >> 1);
-              float row[3 + K];
 #pragma unroll
-              for (int i = 0; i < 3 + K; ++i) row[i] = gx_fma(sg_, R.cj[ta][i], R.cj[0][i]);
+              for (int r = 0; r < 3; ++r) gr_loc[r] = gx_fma(gx_fma(sg_, R.cj[ta][r], R.cj[0][r]), force, gr_loc[r]);
 #pragma unroll
-              for (int r = 0; r < 3; ++r) fc_r[r] = gx_fma(row[r], force, fc_r[r]);
-              int e = 0;
-#pragma unroll
-              for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int s = 0; s <= r; ++s, ++e) Arr[j][e] = gx_fma(R.cD * row[r], row[s], Arr[j][e]);
-#pragma unroll
-              for (int i = 0; i < K; ++i) {
-                fcl[j][i] = gx_fma(row[3 + i], force, fcl[j][i]);
-                const float di = R.cD * row[3 + i];
-#pragma unroll
-                for (int s = 0; s < K; ++s) if (s <= i) A[j][i][s] = gx_fma(di, row[3 + s], A[j][i][s]);
-#pragma unroll
-                for (int r = 0; r < 3; ++r) Cc[j][i][r] = gx_fma(di, row[r], Cc[j][i][r]);
-              }
+              for (int i = 0; i < K; ++i) fcl[j][i] = gx_fma(gx_fma(sg_, R.cj[ta][3 + i], R.cj[0][3 + i]), force, fcl[j][i]);
             }
           }
         }
 #pragma unroll
-        for (int r = 0; r < 3; ++r) gr_loc[r] += fc_r[r];
-#pragma unroll
         for (int i = 0; i < K; ++i) {
-          gl[j][i] = i < nk[j] ? (Mal[j][i] - fl[j][i]) - fcl[j][i] : 0.0f;
-          gn_loc = gx_fma(gl[j][i], gl[j][i], gn_loc);
+          bl[j][i] = i < nk[j] ? fcl[j][i] - (Mal[j][i] - fl[j][i]) : 0.0f;   // -gradient
+          gn_loc = gx_fma(bl[j][i], bl[j][i], gn_loc);
         }
       }
-      float gr[3];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         fcr[r] = gx_art_sum<LANES>(gr_loc[r], mask);
-        gr[r] = (Mar[r] - fr[r]) - fcr[r];
+        br[r] = fcr[r] - (Mar[r] - fr[r]);
       }
-      const float gnorm = gx_sqrt(gx_art_sum<LANES>(gn_loc, mask) + gr[0] * gr[0] + gr[1] * gr[1] + gr[2] * gr[2]);
-      if (gnorm < m.tol_scale) break;
-      // search = -H^-1 grad
-      float dr[3] = {-gr[0], -gr[1], -gr[2]}, dl[LPL][K];
+      const float gnorm = gx_sqrt(gx_art_sum<LANES>(gn_loc, mask) + br[0] * br[0] + br[1] * br[1] + br[2] * br[2]);
+      // converged, out of iterations, or NaN (singular model state: the env's NaN guard fires)
+      if (finish || !(gnorm >= m.tol_scale) || iters >= m.max_iter) {
+        if (forward_only) break;
+        mode = PH_EULER;
+      }
+    }
+    // ---- assemble the arrowhead system of this phase
 #pragma unroll
-      for (int j = 0; j < LPL; ++j)
+    for (int j = 0; j < LPL; ++j) {
+      const GxArtSeg& sg = m.leg[j * LANES + lane];
+      const GxArtRows<K>& R = rows[j];
 #pragma unroll
-        for (int i = 0; i < K; ++i) dl[j][i] = -gl[j][i];
-      gx_art_arrow_solve<LANES, NLEG, K>(&A, Cc, Arr, Mrr, nk, dl, dr, mask);
-      // line-search quadratics
-      float mvr[3], mvl[LPL][K], jvl[LPL][K], jvc[LPL][4];
-      mul_m(dr, dl, mvr, mvl);
-      float g0 = 0.0f, h0 = 0.0f;
+      for (int e = 0; e < 6; ++e) Arr[j][e] = 0.0f;
 #pragma unroll
-      for (int j = 0; j < LPL; ++j) {
-        mul_j(j, dr, dl[j], jvl[j], jvc[j]);
+      for (int i = 0; i < K; ++i) {
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-          g0 = gx_fma(dl[j][i], Mal[j][i] - fl[j][i], g0);
-          h0 = gx_fma(dl[j][i], mvl[j][i], h0);
+        for (int s2 = 0; s2 < K; ++s2) A[j][i][s2] = Mll[j][i][s2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) Cc[j][i][r] = C[j][i][r];
+        if (mode == PH_SMOOTH) bl[j][i] = fl[j][i];
+        if (mode == PH_EULER) {
+          bl[j][i] = fl[j][i] + fcl[j][i];
+          if (i < nk[j]) A[j][i][i] = gx_fma(m.dt, sg.dof[i].damping, A[j][i][i]);
         }
+        if (mode == PH_NEWTON && jl[j][i] < 0.0f) A[j][i][i] += R.lD[i];   // ls^2 = 1 on active rows
       }
-      g0 = gx_art_sum<LANES>(g0, mask);
-      h0 = gx_art_sum<LANES>(h0, mask);
+      if (mode == PH_NEWTON && R.con) {
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          if (jc[j][k] < 0.0f) {
+            const float sg_ = (k & 1) ? -R.cmu : R.cmu;
+            const int ta = 1 + (k >> 1);
+            float row[3 + K];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) { g0 = gx_fma(dr[r], Mar[r] - fr[r], g0); h0 = gx_fma(dr[r], mvr[r], h0); }
-      // exact minimiser of the piecewise-quadratic 1-D cost: Newton on its derivative, bracketed
-      float alpha = 0.0f, lo = 0.0f, hi = 3.0e38f, slope0 = 0.0f;
-      for (int ls = 0; ls < 40; ++ls) {
-        float d1 = 0.0f, d2 = 0.0f;
+            for (int i = 0; i < 3 + K; ++i) row[i] = gx_fma(sg_, ta == 1 ? R.cj[1][i] : R.cj[2][i], R.cj[0][i]);
+            int e = 0;
 #pragma unroll
-        for (int j = 0; j < LPL; ++j) {
+            for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int i = 0; i < K; ++i) {
-            const float x = gx_fma(alpha, jvl[j][i], jl[j][i]);
-            if (x < 0.0f) { const float dj = rows[j].lD[i] * jvl[j][i]; d1 = gx_fma(dj, x, d1); d2 = gx_fma(dj, jvl[j][i], d2); }
-          }
-          if (rows[j].con) {
+              for (int s2 = 0; s2 <= r; ++s2, ++e) Arr[j][e] = gx_fma(R.cD * row[r], row[s2], Arr[j][e]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float x = gx_fma(alpha, jvc[j][k], jc[j][k]);
-              if (x < 0.0f) { const float dj = rows[j].cD * jvc[j][k]; d1 = gx_fma(dj, x, d1); d2 = gx_fma(dj, jvc[j][k], d2); }
+            for (int i = 0; i < K; ++i) {
+              const float di = R.cD * row[3 + i];
+#pragma unroll
+              for (int s2 = 0; s2 < K; ++s2) if (s2 <= i) A[j][i][s2] = gx_fma(di, row[3 + s2], A[j][i][s2]);
+#pragma unroll
+              for (int r = 0; r < 3; ++r) Cc[j][i][r] = gx_fma(di, row[r], Cc[j][i][r]);
             }
           }
         }
-        d1 = gx_art_sum<LANES>(d1, mask) + gx_fma(alpha, h0, g0);
-        d2 = gx_art_sum<LANES>(d2, mask) + h0;
-        if (ls == 0) slope0 = d1;
-        if (d1 == 0.0f) break;
-        if (d1 < 0.0f) lo = alpha; else hi = alpha;
-        float nxt = alpha - gx_div(d1, d2);
-        const bool bad = !(nxt > lo && nxt < hi);
-        if (bad) nxt = hi < 3.0e38f ? 0.5f * (lo + hi) : 2.0f * gx_max(lo, 1.0f);
-        // converged when the step lands in the same active set
-        int changed = bad ? 1 : 0;
+      }
+      if (mode == PH_EULER && lane == 0 && j == 0) {   // root damping enters the Schur sum once
+        Arr[j][0] = m.dt * m.root.dof[0].damping;
+        Arr[j][2] = m.dt * m.root.dof[1].damping;
+        Arr[j][5] = m.dt * m.root.dof[2].damping;
+      }
+    }
+    if (mode == PH_SMOOTH) { br[0] = fr[0]; br[1] = fr[1]; br[2] = fr[2]; }
+    if (mode == PH_EULER) { br[0] = fr[0] + fcr[0]; br[1] = fr[1] + fcr[1]; br[2] = fr[2] + fcr[2]; }
+    gx_art_arrow_solve<LANES, NLEG, K>(&A, Cc, Arr, Mrr, nk, bl, br, mask);
+    // ---- what the solution is, per phase
+    if (mode == PH_EULER) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) er[r] = br[r];
+#pragma unroll
+      for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int i = 0; i < K; ++i) el[j][i] = bl[j][i];
+      break;
+    }
+    if (mode == PH_SMOOTH) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { sr[r] = br[r]; ar[r] = br[r]; }
+#pragma unroll
+      for (int j = 0; j < LPL; ++j)
+#pragma unroll
+        for (int i = 0; i < K; ++i) { sl[j][i] = bl[j][i]; al[j][i] = bl[j][i]; }
+      if (!any_row) {
+        if (forward_only) break;
+        mode = PH_EULER;
+        continue;
+      }
+      // warm start (mjx solver.solve): start from qacc_warmstart iff its cost beats qacc_smooth's.
+      // Candidates in the order warm, smooth, warm-again so that the quantities derived from the
+      // winner (M*qacc, J*qacc - aref) are the ones left behind by the last evaluation.
+      float cost_w = 0.0f;
+#pragma unroll 1
+      for (int cnd = 0; cnd < 3; ++cnd) {
+        const bool usew = cnd != 1;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) ar[r] = usew ? st.wr[r] : sr[r];
+#pragma unroll
+        for (int j = 0; j < LPL; ++j)
+#pragma unroll
+          for (int i = 0; i < K; ++i) al[j][i] = usew ? st.wl[j][i] : sl[j][i];
+        mul_m(ar, al, Mar, Mal);
+        float local = 0.0f;
 #pragma unroll
         for (int j = 0; j < LPL; ++j) {
+          mul_j(j, ar, al[j], jl[j], jc[j]);
 #pragma unroll
-          for (int i = 0; i < K; ++i)
-            changed |= (gx_fma(alpha, jvl[j][i], jl[j][i]) < 0.0f) != (gx_fma(nxt, jvl[j][i], jl[j][i]) < 0.0f) && rows[j].lD[i] > 0.0f;
-          if (rows[j].con) {
+          for (int i = 0; i < K; ++i) {
+            jl[j][i] -= rows[j].laref[i];
+            if (jl[j][i] < 0.0f) local = gx_fma(0.5f * rows[j].lD[i] * jl[j][i], jl[j][i], local);
+            local = gx_fma(0.5f * (Mal[j][i] - fl[j][i]), al[j][i] - sl[j][i], local);
+          }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              changed |= (gx_fma(alpha, jvc[j][k], jc[j][k]) < 0.0f) != (gx_fma(nxt, jvc[j][k], jc[j][k]) < 0.0f);
+          for (int k = 0; k < 4; ++k) {
+            jc[j][k] -= rows[j].caref[k];
+            if (rows[j].con && jc[j][k] < 0.0f) local = gx_fma(0.5f * rows[j].cD * jc[j][k], jc[j][k], local);
           }
         }
-        changed = gx_art_or<LANES>(changed, mask);
-        alpha = nxt;
-        if (!changed) break;
-      }
-      // move
+        float cost = gx_art_sum<LANES>(local, mask);
 #pragma unroll
-      for (int r = 0; r < 3; ++r) { ar[r] = gx_fma(alpha, dr[r], ar[r]); Mar[r] = gx_fma(alpha, mvr[r], Mar[r]); }
+        for (int r = 0; r < 3; ++r) cost = gx_fma(0.5f * (Mar[r] - fr[r]), ar[r] - sr[r], cost);
+        if (cnd == 0) cost_w = cost;
+        else if (cnd == 1 && !(cost_w < cost)) break;
+      }
+      mode = PH_NEWTON;
+      continue;
+    }
+    // ---- Newton: (br, bl) is the search direction; exact line search, then move
+    float mvr[3], mvl[LPL][K], jvl[LPL][K], jvc[LPL][4];
+    mul_m(br, bl, mvr, mvl);
+    float g0 = 0.0f, h0 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+      mul_j(j, br, bl[j], jvl[j], jvc[j]);
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        g0 = gx_fma(bl[j][i], Mal[j][i] - fl[j][i], g0);
+        h0 = gx_fma(bl[j][i], mvl[j][i], h0);
+      }
+    }
+    g0 = gx_art_sum<LANES>(g0, mask);
+    h0 = gx_art_sum<LANES>(h0, mask);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { g0 = gx_fma(br[r], Mar[r] - fr[r], g0); h0 = gx_fma(br[r], mvr[r], h0); }
+    // exact minimiser of the piecewise-quadratic 1-D cost: Newton on its derivative, bracketed
+    float alpha = 0.0f, lo = 0.0f, hi = 3.0e38f, slope0 = 0.0f;
+#pragma unroll 1
+    for (int ls = 0; ls < 40; ++ls) {
+      float d1 = 0.0f, d2 = 0.0f;
 #pragma unroll
       for (int j = 0; j < LPL; ++j) {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-          al[j][i] = gx_fma(alpha, dl[j][i], al[j][i]);
-          Mal[j][i] = gx_fma(alpha, mvl[j][i], Mal[j][i]);
-          jl[j][i] = gx_fma(alpha, jvl[j][i], jl[j][i]);
+          const float x = gx_fma(alpha, jvl[j][i], jl[j][i]);
+          if (x < 0.0f) { const float dj = rows[j].lD[i] * jvl[j][i]; d1 = gx_fma(dj, x, d1); d2 = gx_fma(dj, jvl[j][i], d2); }
         }
+        if (rows[j].con) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) jc[j][k] = gx_fma(alpha, jvc[j][k], jc[j][k]);
-      }
-      ++iters;
-      // mjx stops on cost(prev) - cost(now) < tolerance (scaled).  In fp32 that difference of two
-      // O(1e3) numbers is rounding noise, so the decrease is taken from the line-search model
-      // instead: the area under the (piecewise linear) directional derivative, -alpha*f'(0)/2.
-      const float improvement = -0.5f * alpha * slope0;
-      if (improvement < m.tol_scale) break;
-    }
-    // qfrc_constraint = J^T force at the final qacc
-    float loc[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < LPL; ++j) {
-      const GxArtRows<K>& R = rows[j];
-#pragma unroll
-      for (int i = 0; i < K; ++i) fcl[j][i] = (jl[j][i] < 0.0f) ? R.ls[i] * (-R.lD[i] * jl[j][i]) : 0.0f;
-      if (R.con) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (jc[j][k] < 0.0f) {
-            const float force = -R.cD * jc[j][k];
-            const float sg_ = (k & 1) ? -R.cmu : R.cmu;
-            const int ta = 1 + (k >> 1);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) loc[r] = gx_fma(gx_fma(sg_, R.cj[ta][r], R.cj[0][r]), force, loc[r]);
-#pragma unroll
-            for (int i = 0; i < K; ++i) fcl[j][i] = gx_fma(gx_fma(sg_, R.cj[ta][3 + i], R.cj[0][3 + i]), force, fcl[j][i]);
+          for (int k = 0; k < 4; ++k) {
+            const float x = gx_fma(alpha, jvc[j][k], jc[j][k]);
+            if (x < 0.0f) { const float dj = rows[j].cD * jvc[j][k]; d1 = gx_fma(dj, x, d1); d2 = gx_fma(dj, jvc[j][k], d2); }
           }
         }
       }
-    }
+      d1 = gx_art_sum<LANES>(d1, mask) + gx_fma(alpha, h0, g0);
+      d2 = gx_art_sum<LANES>(d2, mask) + h0;
+      if (ls == 0) slope0 = d1;
+      if (!(d1 < 0.0f || d1 > 0.0f)) break;   // exact minimiser, or NaN
+      if (d1 < 0.0f) lo = alpha; else hi = alpha;
+      float nxt = alpha - gx_div(d1, d2);
+      const bool bad = !(nxt > lo && nxt < hi);
+      if (bad) nxt = hi < 3.0e38f ? 0.5f * (lo + hi) : 2.0f * gx_max(lo, 1.0f);
+      // converged when the step lands in the same active set
+      int changed = bad ? 1 : 0;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) fcr[r] = gx_art_sum<LANES>(loc[r], mask);
+      for (int j = 0; j < LPL; ++j) {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+          changed |= ((gx_fma(alpha, jvl[j][i], jl[j][i]) < 0.0f) != (gx_fma(nxt, jvl[j][i], jl[j][i]) < 0.0f)) && rows[j].lD[i] > 0.0f;
+        if (rows[j].con) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            changed |= (gx_fma(alpha, jvc[j][k], jc[j][k]) < 0.0f) != (gx_fma(nxt, jvc[j][k], jc[j][k]) < 0.0f);
+        }
+      }
+      changed = gx_art_or<LANES>(changed, mask);
+      alpha = nxt;
+      if (!changed) break;
+    }
+    float ss = 0.0f, qq = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { ar[r] = gx_fma(alpha, br[r], ar[r]); Mar[r] = gx_fma(alpha, mvr[r], Mar[r]); }
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        al[j][i] = gx_fma(alpha, bl[j][i], al[j][i]);
+        Mal[j][i] = gx_fma(alpha, mvl[j][i], Mal[j][i]);
+        jl[j][i] = gx_fma(alpha, jvl[j][i], jl[j][i]);
+        ss = gx_fma(bl[j][i], bl[j][i], ss);
+        qq = gx_fma(al[j][i], al[j][i], qq);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) jc[j][k] = gx_fma(alpha, jvc[j][k], jc[j][k]);
+    }
+    ++iters;
+    // mjx stops on cost(prev) - cost(now) < tolerance (scaled).  In fp32 that difference of two
+    // O(1e3) numbers is rounding noise, so the decrease is taken from the line-search model
+    // instead: the area under the (piecewise linear) directional derivative, -alpha*f'(0)/2.
+    const float improvement = -0.5f * alpha * slope0;
+    // ... and a step below fp32 resolution of qacc cannot improve anything (near-singular mass
+    // matrices: the planar roots of ant / walker degenerate at yaw = +-90 deg, where the x and y
+    // slides align)
+    ss = gx_art_sum<LANES>(ss, mask) + br[0] * br[0] + br[1] * br[1] + br[2] * br[2];
+    qq = gx_art_sum<LANES>(qq, mask) + ar[0] * ar[0] + ar[1] * ar[1] + ar[2] * ar[2];
+    if (!(improvement >= m.tol_scale) || !(alpha * alpha * ss > 1e-12f * qq)) finish = true;
   }
   if (iters_out) *iters_out = iters;
   if (!keep_warm) {
@@ -877,30 +907,6 @@ GX_HD void gx_art_step(const GxArtModel& m, int lane, unsigned mask, GxArtLane<L
 #pragma unroll
       for (int i = 0; i < K; ++i) { qlo[j][i] = st.ql[j][i]; vlo[j][i] = st.vl[j][i]; }
     return;
-  }
-  // ---------------- euler: (M + dt*damping) qacc = qfrc_smooth + qfrc_constraint ----------------
-  float er[3], el[LPL][K];
-  {
-    float A[LPL][K][K], Mh[6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) Mh[e] = Mrr[e];
-    Mh[0] = gx_fma(m.dt, m.root.dof[0].damping, Mh[0]);
-    Mh[2] = gx_fma(m.dt, m.root.dof[1].damping, Mh[2]);
-    Mh[5] = gx_fma(m.dt, m.root.dof[2].damping, Mh[5]);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) er[r] = fr[r] + fcr[r];
-#pragma unroll
-    for (int j = 0; j < LPL; ++j) {
-      const GxArtSeg& sg = m.leg[j * LANES + lane];
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-#pragma unroll
-        for (int s = 0; s < K; ++s) A[j][i][s] = Mll[j][i][s];
-        if (i < nk[j]) A[j][i][i] = gx_fma(m.dt, sg.dof[i].damping, A[j][i][i]);
-        el[j][i] = fl[j][i] + fcl[j][i];
-      }
-    }
-    gx_art_arrow_solve<LANES, NLEG, K>(&A, C, nullptr, Mh, nk, el, er, mask);
   }
 #pragma unroll
   for (int r = 0; r < 3; ++r) {

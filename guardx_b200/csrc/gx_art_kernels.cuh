@@ -111,8 +111,12 @@ __device__ __forceinline__ float gx_art_synth_action(const gx_params& p, uint64_
   return gx_uniform(u.v[a & 3], -1.0f, 1.0f);
 }
 
-template <int LANES, int NLEG, int K, int NB, int MODE, bool AUTORESET>
-__global__ void __launch_bounds__(128) gx_art_kernel(const __grid_constant__ gx_params p, const GxState s,
+// MINB = resident 128-thread blocks per SM the register allocation aims for: 2 (no spills,
+// ~250 registers) is fastest while the batch leaves SMs idle anyway; 4 (128 registers, some
+// spills to L1) wins by ~30 % once the grid covers the machine several times (measured:
+// ant, 65 536 envs, 512 -> 393 us per step).
+template <int LANES, int NLEG, int K, int NB, int MODE, bool AUTORESET, int MINB>
+__global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant__ gx_params p, const GxState s,
                                                      const GxArtDev a, const float* __restrict__ pool,
                                                      const float* __restrict__ layout,
                                                      const float* __restrict__ action, const float* obs_in,
@@ -257,49 +261,56 @@ __global__ void __launch_bounds__(128) gx_art_kernel(const __grid_constant__ gx_
       }
     }
     const float last_dist = prev_dist, last_done = was_done;
-    for (int k = 0; k < p.substeps; ++k)
-      gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, st, cr, cl, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
-    if (qacc_out && live) {   // info['obs']['qacc'] (engine.py:763-764): the solver's qacc of the last forward
-      if (lane == 0)
+    // pass 0: the step.  pass 1 (AUTORESET and done): Engine.reset_done's throw-away step on the
+    // re-placed env.  One loop body = one copy of the dynamics in the instruction stream.
+    const float* lay = nullptr;
+#pragma unroll 1
+    for (int pass = 0; pass < (AUTORESET ? 2 : 1); ++pass) {
+      if (pass == 1) {
+        if (!(o_done > 0.0f)) break;
+        lay = gx_pick_layout(p, pool, nullptr, i, age, GX_STREAM_PICK);
+        place(lay);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) qacc_out[(size_t)i * nv + m.root_qadr + r] = st.wr[r];
+        for (int r = 0; r < 3; ++r) cr[r] = 0.0f;
 #pragma unroll
-      for (int j = 0; j < LPL; ++j)
+        for (int j = 0; j < LPL; ++j)
 #pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (k < m.leg[j * LANES + lane].nk) qacc_out[(size_t)i * nv + m.leg_qadr[j * LANES + lane] + k] = st.wl[j][k];
-    }
-    GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, nullptr, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
-    // reward_done (engine.py:787-802), guards (:696-699), timeout + counter (:492-493)
-    const float dist = o.dist_goal;
-    const float last = last_done > 0.0f ? dist : last_dist;
-    const float d_dist = last - dist;
-    o_reward = d_dist * p.reward_distance;
-    o_done = dist < p.goal_size ? 1.0f : 0.0f;
-    if (gx_abs(d_dist) > 1.0f) { o_done = 1.0f; o_reward = 0.0f; }
-    if (o.bad) { o_reward = 0.0f; o_done = 1.0f; }
-    if (steps > p.num_steps) o_done = 1.0f;
-    steps = o_done > 0.0f ? 0.0f : steps + 1.0f;
-    was_done = o_done;
-    prev_dist = dist;
-    age += 1;
-    o_cost = o.cost;
-    if (stats_on && lane == 0 && live) gx_stats_step(s, i, o_reward, o_cost, o_done);
-    if (AUTORESET && o_done > 0.0f) {
-      const float* lay = gx_pick_layout(p, pool, nullptr, i, age, GX_STREAM_PICK);
-      place(lay);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) cr[r] = 0.0f;
-#pragma unroll
-      for (int j = 0; j < LPL; ++j)
-#pragma unroll
-        for (int k = 0; k < K; ++k) cl[j][k] = 0.0f;
-      {
-        GxArtLane<LANES, NLEG, K, NB> tmp = st;
-        for (int k = 0; k < p.substeps; ++k)
-          gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, tmp, nullptr, nullptr, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
+          for (int k = 0; k < K; ++k) cl[j][k] = 0.0f;
       }
-      gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+      GxArtLane<LANES, NLEG, K, NB> wk = st;   // pass 1 works on a scratch copy: the state stays un-stepped
+      for (int k = 0; k < p.substeps; ++k)
+        gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, wk, cr, cl, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
+      if (pass == 0) {
+        st = wk;
+        if (qacc_out && live) {   // info['obs']['qacc'] (engine.py:763-764): the solver's qacc of the last forward
+          if (lane == 0)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) qacc_out[(size_t)i * nv + m.root_qadr + r] = st.wr[r];
+#pragma unroll
+          for (int j = 0; j < LPL; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+              if (k < m.leg[j * LANES + lane].nk) qacc_out[(size_t)i * nv + m.leg_qadr[j * LANES + lane] + k] = st.wl[j][k];
+        }
+      }
+      GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+      if (pass == 0) {
+        // reward_done (engine.py:787-802), guards (:696-699), timeout + counter (:492-493)
+        const float dist = o.dist_goal;
+        const float last = last_done > 0.0f ? dist : last_dist;
+        const float d_dist = last - dist;
+        o_reward = d_dist * p.reward_distance;
+        o_done = dist < p.goal_size ? 1.0f : 0.0f;
+        if (gx_abs(d_dist) > 1.0f) { o_done = 1.0f; o_reward = 0.0f; }
+        if (o.bad) { o_reward = 0.0f; o_done = 1.0f; }
+        if (steps > p.num_steps) o_done = 1.0f;
+        steps = o_done > 0.0f ? 0.0f : steps + 1.0f;
+        was_done = o_done;
+        prev_dist = dist;
+        age += 1;
+        o_cost = o.cost;
+        if (stats_on && lane == 0 && live) gx_stats_step(s, i, o_reward, o_cost, o_done);
+      }
     }
   }
 

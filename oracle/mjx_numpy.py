@@ -424,6 +424,31 @@ def linesearch_exact(g0, h0, jaref, jv, D, iters=40):
     return alpha
 
 
+def _spd_solve(H, g):
+    """H^-1 g per env; envs whose matrix is singular / not positive definite in the working
+    precision (the planar roots of ant / walker degenerate at yaw = +-90 deg) get NaN, which the
+    env's NaN guard turns into done = 1 (engine.py:696-699)."""
+    out = np.full(g.shape, np.nan, H.dtype)
+    H64, g64 = H.astype(np.float64), g.astype(np.float64)
+    try:
+        L = np.linalg.cholesky(H64)
+        ok = np.arange(H.shape[0])
+    except np.linalg.LinAlgError:
+        ok = []
+        for e in range(H.shape[0]):
+            try:
+                np.linalg.cholesky(H64[e]); ok.append(e)
+            except np.linalg.LinAlgError:
+                pass
+        ok = np.asarray(ok, int)
+        if ok.size == 0:
+            return out
+        L = np.linalg.cholesky(H64[ok])
+    y = np.linalg.solve(L, g64[ok][..., None])
+    out[ok] = np.linalg.solve(np.swapaxes(L, 1, 2), y)[..., 0].astype(H.dtype)
+    return out
+
+
 def solve(mm: MjxModel, M, J, D, aref, qfrc_smooth, qacc_smooth, warm, return_iters=False):
     m, dt = mm.m, mm.dtype
     N = M.shape[0]
@@ -438,13 +463,11 @@ def solve(mm: MjxModel, M, J, D, aref, qfrc_smooth, qacc_smooth, warm, return_it
         efc_force = -D * jaref * act
         grad = Ma - qfrc_smooth - np.einsum('nev,ne->nv', J, efc_force)
         gnorm = np.sqrt(np.sum(grad * grad, 1))
-        done |= gnorm * scale < mm.tolerance
+        done |= ~(gnorm * scale >= mm.tolerance)
         if done.all():
             break
         H = M + np.einsum('nev,ne,new->nvw', J, D * act, J)
-        L = np.linalg.cholesky(H.astype(np.float64)).astype(dt) if dt == np.float32 else np.linalg.cholesky(H)
-        y = np.linalg.solve(L.astype(np.float64), grad.astype(np.float64)[..., None])
-        search = -np.linalg.solve(np.swapaxes(L, 1, 2).astype(np.float64), y)[..., 0].astype(dt)
+        search = -_spd_solve(H, grad)
         mv = np.einsum('nij,nj->ni', M, search)
         jv = np.einsum('nev,nv->ne', J, search)
         g0 = np.einsum('ni,ni->n', search, Ma - qfrc_smooth)
@@ -459,7 +482,7 @@ def solve(mm: MjxModel, M, J, D, aref, qfrc_smooth, qacc_smooth, warm, return_it
         gauss = 0.5 * np.einsum('ni,ni->n', Ma - qfrc_smooth, qacc - qacc_smooth)
         cost = gauss + 0.5 * np.sum(D * jaref * jaref * act, 1)
         niter += ~done
-        done |= ((prev - cost) * scale < mm.tolerance)
+        done |= ~((prev - cost) * scale >= mm.tolerance)
     efc_force = -D * jaref * act
     qfrc_constraint = np.einsum('nev,ne->nv', J, efc_force)
     if return_iters:
@@ -469,7 +492,7 @@ def solve(mm: MjxModel, M, J, D, aref, qfrc_smooth, qacc_smooth, warm, return_it
 
 # ----------------------------------------------------------------- forward / step
 def _chol_solve(M, f):
-    return np.linalg.solve(M.astype(np.float64), f.astype(np.float64)[..., None])[..., 0].astype(M.dtype)
+    return _spd_solve(M, f)
 
 
 def forward(mm: MjxModel, qpos, qvel, ctrl, warm):
