@@ -20,6 +20,8 @@ One JSON line on stdout (rank 0).  Keys beyond the driver's contract:
                 e2e.per_step_sync is the blocking one-call-per-step variant
   rollout       the fused multi-step kernel (gx_rollout): T steps per launch,
                 state in registers, vs its own 192-byte I/O-only roofline
+  legged        Goal_Ant_8Hazards, 65536 envs sharded over the ranks (BASELINE configs[3]),
+                the articulated step kernel (leg-per-lane mjx.step with a Newton contact solver)
   sweep         (N=1 only) step-kernel GB/s at larger batches, to show where the
                 kernel sits against the roofline once launch latency is amortised
 
@@ -275,6 +277,7 @@ def main():
     ap.add_argument("--impl", default="guardx", choices=["guardx", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-legged", action="store_true", help="skip the ant / 65536-env measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -371,14 +374,16 @@ def main():
     hp_r, hp_d, hp_c = (torch.empty(Tp, n).pin_memory() for _ in range(3))
     reps_p = max(2, min(40, (K + Tp - 1) // Tp))
 
+    Rp = min(R, 8)   # PCIe, not L2, bounds this path; 8 batches keep every call on a different env state
+
     def e2e_pipe(k):
         acc = 0.0
         for j in range(k):
-            batches[j % R].env.rollout_host(hp_act, hp_obs, hp_r, hp_d, hp_c)
+            batches[j % Rp].env.rollout_host(hp_act, hp_obs, hp_r, hp_d, hp_c)
             acc += float(hp_r[-1, -1])   # the rollout's result is read on the host
         return acc
 
-    e2e_pipe(2)
+    e2e_pipe(2 * Rp)   # warm-up: every batch has its chunk ring, streams and events before the timed region
     if barrier:
         barrier()
     torch.cuda.synchronize()
@@ -421,6 +426,40 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt_ro = float(t.item())
     ro_value = world * n * T * reps / dt_ro
+    # ---- BASELINE configs[3]: legged robot (ant), 65536 envs sharded over the ranks --------
+    legged = None
+    if not args.no_legged:
+        n_leg = 65536 // world
+        Tl = 30
+        aenv = Engine({'env_num': n_leg, 'robot_base': 'xmls/ant.xml', 'num_steps': 1000, '_seed': 0},
+                      env_id_offset=rank * n_leg)
+        aenv.reset()
+        aenv.stats_reset()
+        lo = aenv.rollout(Tl)      # warm-up + buffers (obs [T, n, 64] etc.)
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        rc = lib.gx_rollout(aenv._h, Tl, pr(lo['obs']), pr(lo['act']), pr(lo['reward']), pr(lo['cost']), pr(lo['done']), sp)
+        assert rc == 0, lib.gx_last_error()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        dt_leg = ev0.elapsed_time(ev1) * 1e-3
+        if dist:
+            t = torch.tensor([dt_leg], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_leg = float(t.item())
+        leg_bytes = 4 * (2 * 3 * 11 + 8 + 2 + 16 + 64 + 3)   # q,v,warm r+w | d2 r+w | goal | hazards | obs | r,c,d
+        legged = {"workload": "Goal_Ant_8Hazards, 65536 envs in total, random actions drawn in-kernel, fused step + "
+                              "auto-reset, one launch per step (BASELINE.json configs[3])",
+                  "envs_per_gpu": n_leg, "steps": Tl, "value": world * n_leg * Tl / dt_leg, "unit": "env-steps/s",
+                  "us_per_step": 1e6 * dt_leg / Tl, "scaling": "strong", "alg_bytes_per_env_step": leg_bytes,
+                  "achieved_gbs": n_leg * Tl * leg_bytes / dt_leg / 1e9,
+                  "bound": "issue/latency (Newton contact solver per env, ~1.9 k warp-instructions per env-step), "
+                           "not HBM", "finite": bool(torch.isfinite(lo['obs']).all().item())}
+        del aenv, lo
+        torch.cuda.empty_cache()
     clocks = sampler.stop()
 
     # the dominant kernel's average duration over the timed region (one launch per step)
@@ -496,6 +535,8 @@ def main():
                         "frac": ro_value / world * ALG_BYTES_ROLLOUT / 1e9 / hbm_peak},
             "episode_stats": gxd.episode_summary(stats.tolist()),
         }
+        if legged is not None:
+            line["legged"] = legged
         if sweep is not None:
             line["sweep"] = sweep
         if cpu_base is not None:
