@@ -52,3 +52,21 @@ def episode_summary(stats) -> dict:
         'CostRate': s[TOTAL_COST] / max(s[TOTAL_STEPS], 1.0),
         'TotalEnvInteracts': s[TOTAL_STEPS],
     }
+
+
+def global_mean(x: torch.Tensor, group=None) -> torch.Tensor:
+    """mpi_avg (mpi_tools.py:56-58) of a scalar tensor, on the device."""
+    import torch.distributed as dist
+    x = x.detach().clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(x, op=dist.ReduceOp.SUM, group=group)
+        x /= dist.get_world_size(group)
+    return x
+
+
+def sync_params(module: torch.nn.Module, group=None) -> None:
+    """sync_params (mpi_pytorch.py:29-35): broadcast rank 0's parameters."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for p in module.parameters():
+            dist.broadcast(p.data, src=0, group=group)
