@@ -166,3 +166,96 @@ def test_art_model_lowering_and_rejections():
     assert info['shape'] == (1, 2, 2) and (am.root_x, am.root_y) == (0, 1) and len(info['ignored_pairs']) == 3
     with pytest.raises(AssertionError):
         robots.robot_spec('xmls/doggo.xml')
+
+
+# ---------------------------------------------------------------------------
+# The mjx.step restatement against closed-form rigid-body results.  MuJoCo itself is absent
+# (parity unpinned), so these anchor the oracle -- and through the oracle the kernels -- to
+# physics that can be checked on paper.
+# ---------------------------------------------------------------------------
+def _pendulum(length=0.3, radius=0.02, density=800.0, armature=0.0, damping=0.0, axis=(0., 1., 0.)):
+    """One capsule hanging from a hinge at the world origin along -z (plus the planar root the
+    lowering expects is NOT needed for the oracle: it takes any hinge/slide tree)."""
+    s = mjcf.Spec()
+    s.opt = dict(mjcf.OPT_DEFAULT, timestep=0.001)
+    s.angle = 'radian'
+    s.bodies.append(dict(name='world', parent=-1, pos=(0., 0., 0.), quat=(1., 0., 0., 0.), joints=[], geoms=[]))
+    s.bodies.append(dict(name='rod', parent=0, pos=(0., 0., 1.0), quat=(1., 0., 0., 0.),
+                         joints=[dict(type='hinge', axis=axis, name='h', armature=armature, damping=damping)],
+                         geoms=[dict(type='capsule', fromto=(0., 0., 0., 0., 0., -length), size=(radius,), density=density,
+                                     contype=0, conaffinity=0)]))
+    return mjcf.compile_spec(s)
+
+
+def test_pendulum_acceleration_and_energy():
+    m = _pendulum()
+    mm = mx.MjxModel(m, np.float64)
+    mass, com = m.body_mass[1], -m.body_ipos[1][2]
+    I_pivot = m.body_inertia_full[1][1, 1] + mass * com * com          # parallel axis, about the hinge (y axis)
+    for th in (0.0, 0.3, -1.2, 2.5):
+        d = mx.forward(mm, np.array([[th]]), np.zeros((1, 1)), np.zeros((1, 0)), np.zeros((1, 1)))
+        assert d['qM'][0, 0, 0] == pytest.approx(I_pivot, rel=1e-12)
+        # rotation by +theta about y moves the bob (0,0,-l) to (-l sin, 0, -l cos): torque = -m g l sin(theta)
+        assert d['qacc'][0, 0] == pytest.approx(-mass * 9.81 * com * np.sin(th) / I_pivot, rel=1e-10, abs=1e-12)
+    # semi-implicit Euler at dt = 1 ms keeps the energy of a large swing within 0.5 % over 2 s
+    q, v = np.array([[1.0]]), np.zeros((1, 1))
+    energy = lambda q, v: 0.5 * I_pivot * v[0, 0] ** 2 - mass * 9.81 * com * np.cos(q[0, 0])
+    e0 = energy(q, v)
+    qmax = 0.0
+    for _ in range(2000):
+        q, v, _ = mx.step(mm, q, v, np.zeros((1, 0)), np.zeros((1, 1)))
+        qmax = max(qmax, abs(q[0, 0]))
+    assert abs(energy(q, v) - e0) < 5e-3 * abs(e0) and 0.99 < qmax < 1.01
+
+
+def test_centrifugal_and_coriolis_terms_of_a_two_link_arm():
+    """Planar double pendulum in a horizontal plane (hinge axes = z, so gravity does no work):
+    the bias forces must equal the textbook  h * (-(2 w1 w2 + w2^2), w1^2)  with h = m2 l1 lc2 sin(q2)."""
+    s = mjcf.Spec()
+    s.opt = dict(mjcf.OPT_DEFAULT, timestep=0.001)
+    s.angle = 'radian'
+    s.bodies.append(dict(name='world', parent=-1, pos=(0., 0., 0.), quat=(1., 0., 0., 0.), joints=[], geoms=[]))
+    cap = dict(type='capsule', size=(0.02,), density=500.0, contype=0, conaffinity=0)
+    s.bodies.append(dict(name='l1', parent=0, pos=(0., 0., 0.5), quat=(1., 0., 0., 0.),
+                         joints=[dict(type='hinge', axis=(0., 0., 1.), name='j1')], geoms=[dict(cap, fromto=(0., 0., 0., 0.4, 0., 0.))]))
+    s.bodies.append(dict(name='l2', parent=1, pos=(0.4, 0., 0.), quat=(1., 0., 0., 0.),
+                         joints=[dict(type='hinge', axis=(0., 0., 1.), name='j2')], geoms=[dict(cap, fromto=(0., 0., 0., 0.3, 0., 0.))]))
+    m = mjcf.compile_spec(s)
+    mm = mx.MjxModel(m, np.float64)
+    m1, m2 = m.body_mass[1], m.body_mass[2]
+    lc1, lc2, l1 = m.body_ipos[1][0], m.body_ipos[2][0], 0.4
+    I1, I2 = m.body_inertia_full[1][2, 2], m.body_inertia_full[2][2, 2]
+    q = np.array([[0.7, -1.1]]); w = np.array([[1.3, -2.2]])
+    d = mx.forward(mm, q, w, np.zeros((1, 0)), np.zeros((1, 2)))
+    c2, s2 = np.cos(q[0, 1]), np.sin(q[0, 1])
+    M11 = I1 + I2 + m1 * lc1 ** 2 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * c2)
+    M12 = I2 + m2 * (lc2 ** 2 + l1 * lc2 * c2)
+    M22 = I2 + m2 * lc2 ** 2
+    np.testing.assert_allclose(d['qM'][0], [[M11, M12], [M12, M22]], rtol=1e-12)
+    h = m2 * l1 * lc2 * s2
+    np.testing.assert_allclose(d['qfrc_bias'][0], [-h * (2 * w[0, 0] * w[0, 1] + w[0, 1] ** 2), h * w[0, 0] ** 2], rtol=1e-10, atol=1e-14)
+
+
+def test_joint_limit_and_contact_are_soft_springs_with_the_documented_constants():
+    """A limited hinge pushed 0.1 rad past its range and a sphere 5 mm into the floor: the solver's
+    force must be the solref/solimp spring  D * (aref - J qacc)  with k = 1/(dmax^2 tc^2 zeta^2),
+    b = 2/(dmax tc), imp = dmax beyond `width`, R = invweight (1-imp)/imp -- checked in closed form
+    for the 1-DoF limit case."""
+    m = _pendulum(armature=0.5, axis=(0., 1., 0.))
+    m.jnt_limited[0] = 1
+    m.jnt_range[0] = [-0.2, 0.2]
+    mm = mx.MjxModel(m, np.float64)
+    th, w = 0.3, 0.4
+    d = mx.forward(mm, np.array([[th]]), np.array([[w]]), np.zeros((1, 0)), np.zeros((1, 1)))
+    dt, tc, dmax = m.opt['timestep'], 0.02, 0.95
+    k, b = 1 / (dmax ** 2 * tc ** 2), 2 / (dmax * tc)
+    pos = 0.2 - th                                   # -0.1: past the upper limit, J = -1
+    aref = -b * (-w) - k * dmax * pos
+    R = m.dof_invweight0[0] * (1 - dmax) / dmax
+    M = d['qM'][0, 0, 0]
+    fs = d['qfrc_smooth'][0, 0]
+    # minimise 0.5 M (a - a_s)^2 + 0.5/R (-a - aref)^2  =>  a = (fs - aref/R) / (M + 1/R)
+    a = (fs - aref / R) / (M + 1 / R)
+    assert (-a - aref) < 0                           # the row is active
+    assert d['qacc'][0, 0] == pytest.approx(a, rel=1e-9)
+    assert d['efc_force'][0, 0] == pytest.approx(-(1 / R) * (-a - aref), rel=1e-9) and d['efc_force'][0, 0] > 0
