@@ -27,7 +27,7 @@ __device__ __forceinline__ void gx_art_hazard(const GxState& s, const float* lay
   hy = (h & 1) ? v.w : v.y;
 }
 
-struct GxArtObs { float dist_goal, cost; int bad; };
+struct GxArtObs { float dist_goal, cost; int bad, violations; };
 
 // Observation row of one env, written by its LANES lanes into `row` (shared memory):
 // geometry from the pose snapshot (engine.py:754-758, 817-900), qpos / qvel = (q, v) given
@@ -37,7 +37,7 @@ __device__ __forceinline__ GxArtObs gx_art_obs_row(const gx_params& p, const GxS
                                                    int lane, unsigned mask, const float* lay, float gx_, float gy_,
                                                    const GxArtSnap& sn, const float* cr, const float (*cl)[K],
                                                    const float* qr, const float* vr, const float (*ql)[K],
-                                                   const float (*vl)[K], float* row) {
+                                                   const float (*vl)[K], float* row, int32_t* aux_row) {
   constexpr int LPL = NLEG / LANES;
   GxArtObs o;
   int bad = 0;
@@ -78,11 +78,13 @@ __device__ __forceinline__ GxArtObs gx_art_obs_row(const gx_params& p, const GxS
   __syncwarp(mask);
   if (lane == 0) {
     if (p.off_compass >= 0) { row[p.off_compass] = gex; row[p.off_compass + 1] = gey; bad |= gx_notfinite(gex) | gx_notfinite(gey); }
-    if (p.off_glidar >= 0) bad |= gx_lidar_scatter(p, gx_lidar_ray(p, gex, gey), row + p.off_glidar);
+    const GxRay gr = gx_lidar_ray(p, gex, gey);
+    if (aux_row) aux_row[2] = gr.bin;
+    if (p.off_glidar >= 0) bad |= gx_lidar_scatter(p, gr, row + p.off_glidar);
   }
   // hazards: lane l takes hazards l, l + LANES, ...; the scatters into the shared row are
   // serialised lane by lane (all updates are max, so the order cannot change the result)
-  float cost = 0.0f;
+  float cost = 0.0f, viol = 0.0f;
 #pragma unroll 1
   for (int ph = 0; ph < LANES; ++ph) {
     if (lane == ph) {
@@ -90,15 +92,22 @@ __device__ __forceinline__ GxArtObs gx_art_obs_row(const gx_params& p, const GxS
         float hx, hy, ex, ey;
         gx_art_hazard(s, lay, i, h, hx, hy);
         gx_ego(hx, hy, sn.px, sn.py, sn.r00, sn.r10, ex, ey);
-        if (p.off_hlidar >= 0) bad |= gx_lidar_scatter(p, gx_lidar_ray(p, ex, ey), row + p.off_hlidar);
+        if (p.off_hlidar >= 0 || aux_row) {
+          const GxRay r = gx_lidar_ray(p, ex, ey);
+          if (aux_row) aux_row[3 + h] = r.bin;
+          if (p.off_hlidar >= 0) bad |= gx_lidar_scatter(p, r, row + p.off_hlidar);
+        }
         const float dx = hx - sn.px, dy = hy - sn.py;
         const float dist = gx_sqrt(dx * dx + dy * dy);
-        cost = cost + (p.hazards_size - gx_min(dist, p.hazards_size));
+        const float term = p.hazards_size - gx_min(dist, p.hazards_size);
+        if (term > 0.0f) viol += 1.0f;
+        cost = cost + term;
       }
     }
     __syncwarp(mask);
   }
   o.cost = gx_art_sum<LANES>(cost, mask);
+  o.violations = (int)gx_art_sum<LANES>(viol, mask);
   o.bad = gx_art_or<LANES>(bad, mask);
   return o;
 }
@@ -122,7 +131,8 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
                                                      const float* __restrict__ action, const float* obs_in,
                                                      float* obs, float* __restrict__ act_out,
                                                      float* __restrict__ reward, float* __restrict__ done,
-                                                     float* __restrict__ cost, float* __restrict__ qacc_out, int stats_on) {
+                                                     float* __restrict__ cost, float* __restrict__ qacc_out, int32_t* __restrict__ aux,
+                                                     int stats_on) {
   constexpr int LPL = NLEG / LANES;
   constexpr int EPW = 32 / LANES;
   const int lw = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -224,7 +234,7 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
 #pragma unroll
       for (int k = 0; k < K; ++k) st.wl[j][k] = 0.0f;
     gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, st, nullptr, nullptr, false, true, false, sn, qro, vro, qlo, vlo, nullptr);
-    GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+    GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row, nullptr);
     prev_dist = o.dist_goal;
     steps = 0.0f;
     if (lane == 0 && live && s.ep) s.ep[i] = make_float4(0.f, 0.f, 0.f, s.ep[i].w);
@@ -239,7 +249,7 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
       for (int k = 0; k < p.substeps; ++k)
         gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, tmp, nullptr, nullptr, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
     }
-    gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+    gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row, nullptr);
   } else {
     // Engine.step (engine.py:469-495) + mjx_step (:659-700)
     const uint64_t g = p.env_id_offset + (uint64_t)i;
@@ -293,7 +303,8 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
               if (k < m.leg[j * LANES + lane].nk) qacc_out[(size_t)i * nv + m.leg_qadr[j * LANES + lane] + k] = st.wl[j][k];
         }
       }
-      GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row);
+      int32_t* aux_row = (aux && live && pass == 0) ? aux + (size_t)i * p.aux_dim : nullptr;
+      GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row, aux_row);
       if (pass == 0) {
         // reward_done (engine.py:787-802), guards (:696-699), timeout + counter (:492-493)
         const float dist = o.dist_goal;
@@ -301,9 +312,11 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
         const float d_dist = last - dist;
         o_reward = d_dist * p.reward_distance;
         o_done = dist < p.goal_size ? 1.0f : 0.0f;
-        if (gx_abs(d_dist) > 1.0f) { o_done = 1.0f; o_reward = 0.0f; }
-        if (o.bad) { o_reward = 0.0f; o_done = 1.0f; }
-        if (steps > p.num_steps) o_done = 1.0f;
+        int flags = o_done > 0.0f ? GX_AUX_GOAL : 0;
+        if (gx_abs(d_dist) > 1.0f) { o_done = 1.0f; o_reward = 0.0f; flags |= GX_AUX_JUMP; }
+        if (o.bad) { o_reward = 0.0f; o_done = 1.0f; flags |= GX_AUX_GUARD; }
+        if (steps > p.num_steps) { o_done = 1.0f; flags |= GX_AUX_TIMEOUT; }
+        if (aux_row && lane == 0) { aux_row[0] = flags; aux_row[1] = o.violations; }
         steps = o_done > 0.0f ? 0.0f : steps + 1.0f;
         was_done = o_done;
         prev_dist = dist;

@@ -84,7 +84,7 @@ def test_one_step_from_injected_state(mods, robot):
     g, o = Engine(dict(cfg)), Oracle(dict(cfg), dtype=np.float64)
     g.reset(pool[:n]); o.reset(pool[:n])
     rng = np.random.default_rng(7)
-    n_done = n_viol = 0
+    n_done = n_viol = bin_mismatch = bin_total = 0
     for t in range(45):
         a = rng.uniform(-1.3, 1.3, (n, nu)).astype(np.float32)
         o.round_state_to_fp32()
@@ -94,14 +94,25 @@ def test_one_step_from_injected_state(mods, robot):
         # slides become parallel at yaw = +-90 deg and the root mass block turns singular -- a property
         # of the reference's models.  Near it every fp32 solve is noise; those rows are left out.
         wc = np.ones(n, bool) if robot == 'swimmer' else np.abs(np.cos(st[:, 1])) > 0.5
-        og, rg, dg, ig = g.step(torch.from_numpy(a).cuda())
+        og, rg, dg, ig = g.step(torch.from_numpy(a).cuda(), want_aux=True)
         oo, ro, do, io = o.step(a)
         assert wc.sum() >= n // 2
+        # integer outputs: lidar bin indices (goal + hazards), violation count, done-reason flags
+        aux = cpu(ig['aux'])
+        bins_g = aux[:, 2:3 + 8]
+        bins_o = np.concatenate([io['goal_bin'], io['hazard_bins']], 1)
+        diff = (bins_g != bins_o) & wc[:, None]
+        bin_mismatch += int(diff.sum()); bin_total += int(wc.sum()) * 9
+        assert (((bins_g - bins_o)[diff] % 16) % 14 == 1).all()      # an edge case flips to the NEIGHBOURING bin only
+        viol_o = (0.3 - np.minimum(np.linalg.norm(o.get_state()[:, 3 * nv + 5:].reshape(n, 8, 2) - io['xpos'][:, None, :2], axis=2), 0.3) > 1e-6).sum(1)
+        viol_hi = (0.3 - np.minimum(np.linalg.norm(o.get_state()[:, 3 * nv + 5:].reshape(n, 8, 2) - io['xpos'][:, None, :2], axis=2), 0.3) > -1e-6).sum(1)
+        assert ((aux[:, 1] >= viol_o) & (aux[:, 1] <= viol_hi))[wc].all()
         obs_close(cpu(og)[wc], oo[wc], nu, nv, 2e-5, 2e-5, f'{robot} step {t} obs')
         close(cpu(rg)[wc], ro[wc], 2e-5, 0, f'step {t} reward')
         close(cpu(ig['cost'])[wc], io['cost'][wc], 2e-5, 0, f'step {t} cost')
         qscale = np.abs(io['qacc']).max(1, keepdims=True)      # the solve couples all dofs of an env
-        close((cpu(ig['obs']['qacc']) / (1 + qscale))[wc], (io['qacc'] / (1 + qscale))[wc], 2e-4, 0, f'step {t} qacc (relative to the env max)')
+        close((cpu(ig['obs']['qacc']) / (1 + qscale))[wc], (io['qacc'] / (1 + qscale))[wc], 2e-3 if robot == 'walker' else 2e-4, 0,
+              f'step {t} qacc (relative to the env max; walker: hip armature 0.01 next to 1.0 makes the solve ill-conditioned)')
         clear = wc & (np.abs(io['dist'] - 0.5) > 1e-4) & (np.abs(np.abs(io['d_dist']) - 1) > 1e-4)
         assert (cpu(dg) == do)[clear].all(), f'step {t} done'
         n_done += int(do.sum()); n_viol += int((io['cost'] > 0).sum())
@@ -112,6 +123,9 @@ def test_one_step_from_injected_state(mods, robot):
             sg, so = cpu(g.get_state()), o.get_state()
             close(np.delete(sg, np.s_[2 * nv:3 * nv], 1), np.delete(so, np.s_[2 * nv:3 * nv], 1), 1e-6, 1e-6, 'state after reset_done')
     assert n_done >= n   # the 30-step timeout fired for every env
+    # bins are decided by an fp32 angle / bin_size quotient: the two independent dynamics differ by ~1e-7 in the
+    # pose, so a ray within that of a bin edge may land next door -- at most a handful in ~2e4 rays
+    assert bin_total > 10000 and bin_mismatch <= 3, (bin_mismatch, bin_total)
 
 
 @pytest.mark.parametrize("robot", ['ant', 'walker'])
