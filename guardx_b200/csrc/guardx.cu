@@ -15,6 +15,7 @@
 #include "gx_device.cuh"
 #include "gx_lanes.cuh"
 #include "gx_art.cuh"
+#include "gx_art_launch.h"
 
 #define GX_API extern "C" __attribute__((visibility("default")))
 
@@ -207,16 +208,6 @@ __global__ void __launch_bounds__(128) gx_pool_kernel(const __grid_constant__ gx
 // ---------------------------------------------------------------------------
 // placement of one env from a layout row (layout2qpos, engine.py:623-639)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ const float* gx_pick_layout(const gx_params& p, const float* pool,
-                                                       const float* layout, int i, uint64_t t_global,
-                                                       uint32_t stream) {
-  if (layout) return layout + (size_t)i * p.lay_dim;
-  const uint64_t g = p.env_id_offset + (uint64_t)i;
-  gx_u32x4 r = gx_philox4x32_10((uint32_t)g, (uint32_t)t_global, (uint32_t)(t_global >> 32), stream, p.seed_lo, p.seed_hi);
-  const uint32_t idx = gx_randint(r.v[0], (uint32_t)p.pool_size);
-  return pool + (size_t)idx * p.lay_dim;
-}
-
 template <int NH_CT>
 __device__ __forceinline__ void gx_place(const gx_params& p, const GxState& s, int i, const float* lay,
                                          float& gx_, float& gy_, float4* hz_regs, GxDyn& d) {
@@ -255,7 +246,6 @@ __device__ __forceinline__ void gx_load_static(const GxState& s, int i, float& g
   }
 }
 
-extern __shared__ __align__(16) float gx_smem[];
 
 // ---- Engine.reset (engine.py:454-467) -------------------------------------
 template <int NH_CT>
@@ -306,20 +296,6 @@ __device__ __forceinline__ void gx_reset_done_env(const gx_params& p, const GxSt
 // Per-env accumulators only -- no atomics and no grid-wide reduction in the step
 // (4096 same-address atomics per launch cost more than the step itself).  The
 // sums over envs are taken, deterministically, when the statistics are read.
-__device__ __forceinline__ void gx_stats_step(const GxState& s, int i, float reward, float cost, float done) {
-  float4 e = s.ep[i];
-  e.x += reward; e.y += cost; e.z += 1.0f; e.w += cost;
-  if (done > 0.0f) {
-    float4 f0 = s.fin[i], f1 = s.fin[(size_t)s.cap + i];
-    f0.x += 1.0f; f0.y += e.x; f0.z += e.y; f0.w += e.z;
-    f1.x += e.x * e.x; f1.y += e.y * e.y;
-    s.fin[i] = f0;
-    s.fin[(size_t)s.cap + i] = f1;
-    e.x = 0.f; e.y = 0.f; e.z = 0.f;
-  }
-  s.ep[i] = e;
-}
-
 // out[8] = n_episodes, sum_ret, sum_cost, sum_len, sum_ret^2, sum_cost^2,
 // total_cost, total_env_steps.  One block, fixed tree => deterministic.
 __global__ void __launch_bounds__(1024) gx_stats_reduce_kernel(const GxState s, int n, unsigned long long age0,
@@ -623,7 +599,40 @@ __global__ void gx_set_state_kernel(const __grid_constant__ gx_params p, const G
   s.hf[i] = (x[4] > 0.0f ? 1u : 0u) | ((uint32_t)hist << 1);
 }
 
-#include "gx_art_kernels.cuh"
+// ---- state injection / checkpoint: one row per env =
+//      qpos[nv] qvel[nv] qacc_warmstart[nv] prev_dist prev_done steps goal[2] hazards[2*nh]
+__global__ void gx_art_get_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxArtDev a, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  float* o = out + (size_t)i * p.state_dim;
+  const size_t cap = (size_t)s.cap;
+  for (int k = 0; k < 3 * a.nv; ++k) o[k] = a.aq[(size_t)k * cap + i];
+  o += 3 * a.nv;
+  const float4 c = s.d2[i];
+  o[0] = c.x; o[1] = (__float_as_uint(c.y) >> 31) ? 1.0f : 0.0f; o[2] = fabsf(c.y);
+  const float2 g = s.goal[i];
+  o[3] = g.x; o[4] = g.y;
+  for (int h = 0; h < p.nh; ++h) gx_art_hazard(s, nullptr, i, h, o[5 + 2 * h], o[6 + 2 * h]);
+}
+
+__global__ void gx_art_set_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxArtDev a, const float* in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const float* o = in + (size_t)i * p.state_dim;
+  const size_t cap = (size_t)s.cap;
+  for (int k = 0; k < 3 * a.nv; ++k) a.aq[(size_t)k * cap + i] = o[k];
+  o += 3 * a.nv;
+  const float4 c = s.d2[i];
+  s.d2[i] = make_float4(o[0], o[1] > 0.0f ? -o[2] : o[2], c.z, c.w);
+  s.goal[i] = make_float2(o[3], o[4]);
+  for (int k = 0; k < s.nh2; ++k) {
+    float4 h;
+    h.x = o[5 + 4 * k]; h.y = o[6 + 4 * k];
+    h.z = (2 * k + 1 < p.nh) ? o[7 + 4 * k] : 0.0f;
+    h.w = (2 * k + 1 < p.nh) ? o[8 + 4 * k] : 0.0f;
+    s.hz[(size_t)k * cap + i] = h;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // C ABI
@@ -826,34 +835,23 @@ static int gx_generate_pool(gx_env* e, cudaStream_t st) {
   return GX_OK;
 }
 
-// ---- articulated robots: one launcher for reset / step / reset_done ----------
+// ---- articulated robots: the kernels live in one translation unit per robot shape
+//      (gx_art_ant.cu, gx_art_walker.cu, gx_art_swimmer.cu) so that the build parallelises
 template <int MODE, bool AR>
 static int gx_art_launch(gx_env* e, cudaStream_t st, const float* layout, const float* action, const float* obs_in,
                          float* obs, float* act_out, float* reward, float* done, float* cost, float* qacc, int32_t* aux = nullptr) {
-  const int n = e->p.n, block = 128;
-#define GX_ART_GO(L, NL, K, NB)                                                                              \
-  do {                                                                                                       \
-    const int grid = div_up(n * (L), block);                                                                 \
-    const size_t sh = (size_t)(block / (L)) * e->p.obs_dim * sizeof(float);                                  \
-    if constexpr (MODE == GX_ART_STEP) {                                                                     \
-      if (grid > 3 * e->sm_count) {                                                                          \
-      gx_art_kernel<L, NL, K, NB, MODE, AR, 4><<<grid, block, sh, st>>>(e->p, e->s, e->art, e->pool, layout, \
-                                                                        action, obs_in, obs, act_out, reward, \
-                                                                        done, cost, qacc, aux, e->stats_on ? 1 : 0); \
-      break; }                                                                                               \
-    }                                                                                                        \
-      gx_art_kernel<L, NL, K, NB, MODE, AR, 2><<<grid, block, sh, st>>>(e->p, e->s, e->art, e->pool, layout, \
-                                                                        action, obs_in, obs, act_out, reward, \
-                                                                        done, cost, qacc, aux, e->stats_on ? 1 : 0); \
-  } while (0)
+  GxArtLaunch a;
+  a.p = &e->p; a.s = &e->s; a.art = &e->art; a.pool = e->pool; a.layout = layout; a.action = action; a.obs_in = obs_in;
+  a.obs = obs; a.act_out = act_out; a.reward = reward; a.done = done; a.cost = cost; a.qacc = qacc; a.aux = aux;
+  a.stats_on = e->stats_on ? 1 : 0; a.mode = MODE; a.autoreset = AR ? 1 : 0; a.sm_count = e->sm_count; a.stream = st;
+  cudaError_t err;
   switch (e->art_shape) {
-    case 1: GX_ART_GO(4, 4, 2, 3); break;
-    case 2: GX_ART_GO(2, 2, 5, 3); break;
-    case 3: GX_ART_GO(1, 1, 2, 2); break;
+    case 1: err = gx_art_launch_ant(a); break;
+    case 2: err = gx_art_launch_walker(a); break;
+    case 3: err = gx_art_launch_swimmer(a); break;
     default: return gx_fail(GX_EINVAL, "gx_art_launch: no kernel for this robot shape");
   }
-#undef GX_ART_GO
-  GX_LAUNCH_CHECK("gx_art_kernel");
+  if (err != cudaSuccess) return gx_fail(GX_ECUDA, "gx_art_kernel launch failed: %s", cudaGetErrorString(err));
   return GX_OK;
 }
 

@@ -10,21 +10,15 @@
 #define GX_ART_KERNELS_CUH_
 
 #include "gx_art.cuh"
+#include "gx_art_launch.h"
+#include "gx_device.cuh"
 
-enum { GX_ART_RESET = 0, GX_ART_STEP = 1, GX_ART_RESET_DONE = 2 };
 
 template <int LANES>
 __device__ __forceinline__ unsigned gx_art_mask() {
   if (LANES == 32) return 0xffffffffu;
   const unsigned lw = threadIdx.x & 31u;
   return ((1u << LANES) - 1u) << (lw & ~(unsigned)(LANES - 1));
-}
-
-__device__ __forceinline__ void gx_art_hazard(const GxState& s, const float* lay, int i, int h, float& hx, float& hy) {
-  if (lay) { hx = lay[4 + 2 * h]; hy = lay[5 + 2 * h]; return; }
-  const float4 v = s.hz[(size_t)(h >> 1) * s.cap + i];
-  hx = (h & 1) ? v.z : v.x;
-  hy = (h & 1) ? v.w : v.y;
 }
 
 struct GxArtObs { float dist_goal, cost; int bad, violations; };
@@ -376,39 +370,23 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
   }
 }
 
-// ---- state injection / checkpoint: one row per env =
-//      qpos[nv] qvel[nv] qacc_warmstart[nv] prev_dist prev_done steps goal[2] hazards[2*nh]
-__global__ void gx_art_get_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxArtDev a, float* out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
-  float* o = out + (size_t)i * p.state_dim;
-  const size_t cap = (size_t)s.cap;
-  for (int k = 0; k < 3 * a.nv; ++k) o[k] = a.aq[(size_t)k * cap + i];
-  o += 3 * a.nv;
-  const float4 c = s.d2[i];
-  o[0] = c.x; o[1] = (__float_as_uint(c.y) >> 31) ? 1.0f : 0.0f; o[2] = fabsf(c.y);
-  const float2 g = s.goal[i];
-  o[3] = g.x; o[4] = g.y;
-  for (int h = 0; h < p.nh; ++h) gx_art_hazard(s, nullptr, i, h, o[5 + 2 * h], o[6 + 2 * h]);
-}
-
-__global__ void gx_art_set_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxArtDev a, const float* in) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
-  const float* o = in + (size_t)i * p.state_dim;
-  const size_t cap = (size_t)s.cap;
-  for (int k = 0; k < 3 * a.nv; ++k) a.aq[(size_t)k * cap + i] = o[k];
-  o += 3 * a.nv;
-  const float4 c = s.d2[i];
-  s.d2[i] = make_float4(o[0], o[1] > 0.0f ? -o[2] : o[2], c.z, c.w);
-  s.goal[i] = make_float2(o[3], o[4]);
-  for (int k = 0; k < s.nh2; ++k) {
-    float4 h;
-    h.x = o[5 + 4 * k]; h.y = o[6 + 4 * k];
-    h.z = (2 * k + 1 < p.nh) ? o[7 + 4 * k] : 0.0f;
-    h.w = (2 * k + 1 < p.nh) ? o[8 + 4 * k] : 0.0f;
-    s.hz[(size_t)k * cap + i] = h;
-  }
+// Host launcher for one robot shape: picks the mode / auto-reset instance and, for the step,
+// the register budget (MINB) by grid size.
+template <int L, int NL, int K, int NB>
+static cudaError_t gx_art_launch_shape(const GxArtLaunch& a) {
+  const int n = a.p->n, block = 128;
+  const int grid = (n * L + block - 1) / block;
+  const size_t sh = (size_t)(block / L) * a.p->obs_dim * sizeof(float);
+#define GX_ART_GO(MODE, AR, MB)                                                                            \
+  gx_art_kernel<L, NL, K, NB, MODE, AR, MB><<<grid, block, sh, a.stream>>>(                              \
+      *a.p, *a.s, *a.art, a.pool, a.layout, a.action, a.obs_in, a.obs, a.act_out, a.reward, a.done, a.cost, \
+      a.qacc, a.aux, a.stats_on)
+  if (a.mode == GX_ART_RESET) GX_ART_GO(GX_ART_RESET, false, 2);
+  else if (a.mode == GX_ART_RESET_DONE) GX_ART_GO(GX_ART_RESET_DONE, false, 2);
+  else if (grid > 3 * a.sm_count) { if (a.autoreset) GX_ART_GO(GX_ART_STEP, true, 4); else GX_ART_GO(GX_ART_STEP, false, 4); }
+  else { if (a.autoreset) GX_ART_GO(GX_ART_STEP, true, 2); else GX_ART_GO(GX_ART_STEP, false, 2); }
+#undef GX_ART_GO
+  return cudaGetLastError();
 }
 
 #endif  // GX_ART_KERNELS_CUH_

@@ -414,4 +414,46 @@ __device__ __forceinline__ void gx_store_tile(const float* tile, float* gdst, in
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------
+// shared by the Point kernels (guardx.cu) and the articulated kernels (gx_art_*.cu)
+// ---------------------------------------------------------------------------
+extern __shared__ __align__(16) float gx_smem[];
+
+// layout row of env i: caller-supplied, or a pool slot drawn with the env's own counter
+__device__ __forceinline__ const float* gx_pick_layout(const gx_params& p, const float* pool,
+                                                       const float* layout, int i, uint64_t t_global,
+                                                       uint32_t stream) {
+  if (layout) return layout + (size_t)i * p.lay_dim;
+  const uint64_t g = p.env_id_offset + (uint64_t)i;
+  gx_u32x4 r = gx_philox4x32_10((uint32_t)g, (uint32_t)t_global, (uint32_t)(t_global >> 32), stream, p.seed_lo, p.seed_hi);
+  const uint32_t idx = gx_randint(r.v[0], (uint32_t)p.pool_size);
+  return pool + (size_t)idx * p.lay_dim;
+}
+
+// hazard h of env i: from a layout row (while re-placing) or from the state arrays
+__device__ __forceinline__ void gx_art_hazard(const GxState& s, const float* lay, int i, int h, float& hx, float& hy) {
+  if (lay) { hx = lay[4 + 2 * h]; hy = lay[5 + 2 * h]; return; }
+  const float4 v = s.hz[(size_t)(h >> 1) * s.cap + i];
+  hx = (h & 1) ? v.z : v.x;
+  hy = (h & 1) ? v.w : v.y;
+}
+
+// ---- episode statistics (ppo_train.py:370-376, 405-411 on the host) --------
+// Per-env accumulators only -- no atomics and no grid-wide reduction in the step
+// (4096 same-address atomics per launch cost more than the step itself).  The
+// sums over envs are taken, deterministically, when the statistics are read.
+__device__ __forceinline__ void gx_stats_step(const GxState& s, int i, float reward, float cost, float done) {
+  float4 e = s.ep[i];
+  e.x += reward; e.y += cost; e.z += 1.0f; e.w += cost;
+  if (done > 0.0f) {
+    float4 f0 = s.fin[i], f1 = s.fin[(size_t)s.cap + i];
+    f0.x += 1.0f; f0.y += e.x; f0.z += e.y; f0.w += e.z;
+    f1.x += e.x * e.x; f1.y += e.y * e.y;
+    s.fin[i] = f0;
+    s.fin[(size_t)s.cap + i] = f1;
+    e.x = 0.f; e.y = 0.f; e.z = 0.f;
+  }
+  s.ep[i] = e;
+}
+
 #endif  // GX_DEVICE_CUH_
