@@ -256,7 +256,9 @@ int gx_stats_reset(gx_env* env, void* stream);
 
 /* ---- host-buffer convenience (the end-to-end path of bench.py): H2D of the
  *      action, step, optional reset_done, D2H of obs/reward/done/cost, and a
- *      stream synchronise.  Host pointers should be pinned. ----------------- */
+ *      stream synchronise.  When all five buffers are pinned AND mapped (cudaHostAlloc,
+ *      cudaHostRegister, torch pin_memory) the copies are skipped: one launch reads
+ *      the actions from and writes the outputs to host memory directly. -------- */
 int gx_step_host(gx_env* env, const float* h_action, float* h_obs, float* h_reward,
                  float* h_done, float* h_cost, int32_t auto_reset_done, void* stream);
 

@@ -393,14 +393,19 @@ def test_golden_reference_source_vectors_through_cuda(mods, golden_dir):
     assert (cpu(r) == 0).all()  # prev_done injected as 1 => reward 0 (engine.py:795)
 
 
-def test_step_host_matches_step(mods):
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_matches_step(mods, pinned):
+    """pinned + mapped buffers take the zero-copy route (the kernel reads / writes host memory),
+    pageable ones the staged-copy route; both equal step() + reset_done()."""
     Engine, _ = mods
     cfg = {'env_num': 1000, 'num_steps': 20, '_seed': 6}
     a, b = Engine(dict(cfg)), Engine(dict(cfg))
     a.reset(); b.reset()
     n, od = 1000, a.obs_flat_size
-    h_act = torch.empty(n, 2).pin_memory()
-    h_out = torch.empty(n * (od + 3)).pin_memory()
+    h_act = torch.empty(n, 2)
+    h_out = torch.empty(n * (od + 3))
+    if pinned:
+        h_act, h_out = h_act.pin_memory(), h_out.pin_memory()
     rng = np.random.default_rng(1)
     for t in range(50):
         act = torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32))
