@@ -127,6 +127,7 @@ PROTOTYPES = {
     "gx_stats_reset": (_I, [_P, _P]),
     "gx_step_host": (_I, [_P, _P, _P, _P, _P, _P, C.c_int32, _P]),
     "gx_rollout_host": (_I, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "gx_compact_done": (_I, [_P, C.c_int32, _P, _P, _P]),
     "gx_gae": (_I, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, _P, _P, _P]),
     "gx_debug_math": (_I, [_I, _P, _P, _P, _P, _I, _P]),
 }

@@ -1278,3 +1278,44 @@ GX_API int gx_gae(const float* reward, const float* value, const float* done, co
   GX_LAUNCH_CHECK("gx_gae_kernel");
   return GX_OK;
 }
+
+// ---- done-compaction: indices of the envs whose done flag is set, ascending,
+// plus their count -- what callers of the reference obtain on the host with
+// np.where(done == 1) after a device->host copy (ppo_train.py:403-411, scpo/scpo.py:722).
+// One block: ballot + popc per warp, a 32-entry scan per 1024-env chunk; deterministic order.
+__global__ void __launch_bounds__(1024) gx_compact_done_kernel(const float* __restrict__ done, int n,
+                                                               int32_t* __restrict__ idx, int32_t* __restrict__ count) {
+  __shared__ int warp_excl[32];
+  __shared__ int chunk_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int base = 0;  // envs found in earlier chunks (same value in every thread)
+  for (int start = 0; start < n; start += 1024) {
+    const int i = start + threadIdx.x;
+    const bool on = i < n && done[i] > 0.0f;
+    const unsigned m = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) warp_excl[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int v = warp_excl[lane];
+      int incl = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      warp_excl[lane] = incl - v;
+      if (lane == 31) chunk_total = incl;
+    }
+    __syncthreads();
+    if (on) idx[base + warp_excl[warp] + __popc(m & ((1u << lane) - 1u))] = i;
+    base += chunk_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+
+GX_API int gx_compact_done(const float* done, int32_t n, int32_t* idx, int32_t* count, void* stream) {
+  if (!done || !idx || !count || n < 0) return gx_fail(GX_EINVAL, "gx_compact_done: bad argument");
+  gx_compact_done_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(done, n, idx, count);
+  GX_LAUNCH_CHECK("gx_compact_done_kernel");
+  return GX_OK;
+}

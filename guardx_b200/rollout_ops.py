@@ -34,3 +34,24 @@ def gae(reward: torch.Tensor, value: torch.Tensor, done: torch.Tensor, last_valu
         _abi.check(lib, lib.gx_gae(p(reward), p(value), p(done), p(last_value), T, n, float(gamma), float(lam),
                                    p(adv), p(ret), stream), "gx_gae")
     return adv, ret
+
+
+def done_indices(done: torch.Tensor):
+    """Ascending indices of the envs whose ``done`` flag is set, without a host round trip.
+
+    Replaces ``np.where(done == 1)`` on a device->host copy (ppo_train.py:403-411,
+    scpo/scpo.py:722: ``env.reset_done()[np.where(done == 1)]``).  Returns ``(idx, count)``:
+    ``idx`` int32 ``[N]`` whose first ``count`` entries are valid, ``count`` int32 ``[1]`` -- both
+    on the device; ``idx[:int(count)]`` is the only point that needs the host.
+    """
+    assert done.is_cuda and done.dtype == torch.float32 and done.dim() == 1
+    done = done.contiguous()
+    n = done.numel()
+    idx = torch.empty(n, dtype=torch.int32, device=done.device)
+    count = torch.empty(1, dtype=torch.int32, device=done.device)
+    lib = _abi.load_library()
+    with torch.cuda.device(done.device):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _abi.check(lib, lib.gx_compact_done(C.c_void_p(done.data_ptr()), n, C.c_void_p(idx.data_ptr()),
+                                            C.c_void_p(count.data_ptr()), stream), "gx_compact_done")
+    return idx, count

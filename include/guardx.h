@@ -287,6 +287,11 @@ int gx_rollout_host(gx_env* env, int32_t T, const float* h_action, float* h_obs,
 int gx_gae(const float* reward, const float* value, const float* done, const float* last_value,
            int32_t T, int32_t n, double gamma, double lam, float* adv, float* ret, void* stream);
 
+/* ---- rollout-side op: done-compaction.  idx[0 .. *count) = ascending indices of
+ *      the envs with done > 0 (idx has room for n entries), *count = how many -- replaces the
+ *      host-side np.where(done == 1) of ppo_train.py:403-411 / scpo/scpo.py:722.  No env handle. */
+int gx_compact_done(const float* done, int32_t n, int32_t* idx, int32_t* count, void* stream);
+
 /* ---- diagnostics: evaluate the shared fp32 math (csrc/gx_math.h) on the
  *      device, so tests can prove host/device bit-equality of the header.
  *      fn: 0 sincos(a)->out,out2   1 atan2(a,b)->out   2 exp(a)->out

@@ -75,3 +75,18 @@ def test_cuda_gae_bit_exact(oracle_lib, T, N, p_done, with_last):
                        None if last is None else torch.from_numpy(last).cuda(), 0.99, 0.95)
     assert np.array_equal(g_adv.cpu().numpy().view(np.uint32), adv.view(np.uint32))
     assert np.array_equal(g_ret.cpu().numpy().view(np.uint32), ret.view(np.uint32))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p", [(1, 1.0), (1000, 0.3), (4096, 0.0), (70001, 0.02), (65536, 1.0)])
+def test_done_compaction(n, p):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from guardx_b200.rollout_ops import done_indices
+    rng = np.random.default_rng(n)
+    done = (rng.random(n) < p).astype(np.float32)
+    idx, count = done_indices(torch.from_numpy(done).cuda())
+    want = np.where(done == 1)[0]
+    assert int(count.item()) == len(want)
+    assert np.array_equal(idx[:len(want)].cpu().numpy(), want)
