@@ -41,6 +41,9 @@ __device__ __forceinline__ GxArtObs gx_art_obs_row(const gx_params& p, const GxS
   if (p.off_hlidar >= 0) for (int k = lane; k < nb; k += LANES) row[p.off_hlidar + k] = 0.0f;
   // root entries: lane 0; leg entries: owning lane
   if (lane == 0) {
+    // vel / acc default to 0 = obs(data, None, None, None, None) (engine.py:656, 726); a step overwrites them
+    if (p.off_acc >= 0) { row[p.off_acc] = 0.0f; row[p.off_acc + 1] = 0.0f; }
+    if (p.off_vel >= 0) { row[p.off_vel] = 0.0f; row[p.off_vel + 1] = 0.0f; }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int a = m.root.dof[r].act;
@@ -232,6 +235,11 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
     prev_dist = o.dist_goal;
     steps = 0.0f;
     if (lane == 0 && live && s.ep) s.ep[i] = make_float4(0.f, 0.f, 0.f, s.ep[i].w);
+    if (lane == 0 && live && ((p.off_vel >= 0) | (p.off_acc >= 0))) {   // Engine._data.xpos <- reset pose; _last_data stays
+      float4 h = s.hx[i];
+      h.x = sn.px; h.y = sn.py;
+      s.hx[i] = h;
+    }
   } else if (MODE == GX_ART_RESET_DONE) {
     // Engine.reset_done for a done env (engine.py:702-731): re-place, ctrl 0, one throw-away
     // mjx.step for the observation; the state keeps the UN-stepped pose, the stale warm start,
@@ -299,6 +307,12 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
       }
       int32_t* aux_row = (aux && live && pass == 0) ? aux + (size_t)i * p.aux_dim : nullptr;
       GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row, aux_row);
+      if (pass == 0 && ((p.off_vel >= 0) | (p.off_acc >= 0))) {
+        // ego_vel_acc (engine.py:902-929) + update_data's history shift, as for the Point
+        int vb = 0;
+        if (lane == 0 && live) vb = gx_vel_acc(p, s, i, sn.px, sn.py, sn.r00, sn.r10, last_done, row);
+        o.bad |= gx_art_or<LANES>(vb, mask);
+      }
       if (pass == 0) {
         // reward_done (engine.py:787-802), guards (:696-699), timeout + counter (:492-493)
         const float dist = o.dist_goal;

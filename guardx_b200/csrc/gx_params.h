@@ -54,7 +54,6 @@ static inline const char* gx_lower_config(const gx_config* c, gx_params* p) {
   if (c->robot != GX_ROBOT_POINT && c->robot != GX_ROBOT_ART) return "unknown robot";
   const int art = c->robot == GX_ROBOT_ART;
   if (art && (c->art_nu < 1 || c->art_nv < 3 || c->art_nu > 64 || c->art_nv > 64)) return "art_nu / art_nv out of range";
-  if (art && (c->obs_mask & (GX_OBS_ACC | GX_OBS_VEL))) return "observe_vel / observe_acc are not built for articulated robots";
   p->nu = art ? c->art_nu : 3; p->nv = art ? c->art_nv : 3;
   if (c->hazards_num < 1 || c->hazards_num > GX_MAX_HAZARDS)
     return "hazards_num out of range (the reference crashes for 0: engine.py:370-384)";

@@ -142,8 +142,7 @@ int gx_create(const gx_config* h_cfg, int device, gx_env** out);
 /* Same for cfg->robot == GX_ROBOT_ART: h_model is the compiled robot (guardx_art.h), what
  * mujoco.MjModel.from_xml_string + mjx.put_model produce in the reference (engine.py:228-231).
  * Every entry point below then works on that robot: action [env_num, nu], qacc
- * [env_num, nv], state rows as documented at gx_get_state, aux rows as for the Point.
- * observe_vel / observe_acc are not built for articulated robots (GX_EINVAL). */
+ * [env_num, nv], state rows as documented at gx_get_state, aux rows as for the Point. */
 int gx_create_art(const gx_config* h_cfg, const GxArtModel* h_model, int device, gx_env** out);
 int gx_destroy(gx_env* env);
 

@@ -44,7 +44,8 @@ class ArtOracleEngine:
         self.obs_dim = self.nu + 2 + 2 * self.nb + 2 * self.nq_robot
         assert self.config['observe_goal_lidar'] and self.config['observe_goal_comp'] and self.config['observe_hazards']
         assert self.config['observe_qpos'] and self.config['observe_qvel'] and self.config['observe_ctrl']
-        assert not self.config['observe_vel'] and not self.config['observe_acc']
+        self.with_vel, self.with_acc = bool(self.config['observe_vel']), bool(self.config['observe_acc'])
+        self.obs_dim += 2 * (self.with_vel + self.with_acc)
         # joint_name2qpos_id (engine.py:310-316)
         self.qadr = {m.jnt_name[j]: int(m.jnt_qposadr[j]) for j in range(m.njnt) if m.jnt_name[j]}
         n = self.n
@@ -54,6 +55,10 @@ class ArtOracleEngine:
         self.prev_dist = np.zeros(n, np.float32)
         self._obs = None
         self.last_data = None
+        # history read by ego_vel_acc (engine.py:902-929): xpos of Engine._data / _last_data, _last_done, and how
+        # many of _last_done / _last_last_done are not None yet (update_data, engine.py:426-431)
+        self.hx_data = np.zeros((n, 2), np.float32); self.hx_last = np.zeros((n, 2), np.float32)
+        self.h_last_done = np.zeros(n, np.float32); self.h_depth = 0
 
     # layout rows: goal xy, robot xy, hazard0 xy, ... (same as guardx.h)
     def layout2qpos(self, layout):
@@ -73,14 +78,21 @@ class ArtOracleEngine:
                        for h in range(self.nh)], 1).astype(np.float32)
         return xpos, xmat, goal, hz
 
-    def _obs_rows(self, d, qpos_geom, qpos, qvel, ctrl):
-        """Engine.obs (engine.py:738-778): ctrl | goal_compass | goal_lidar | hazards_lidar | qpos | qvel."""
+    def _obs_rows(self, d, qpos_geom, qpos, qvel, ctrl, vel=None, acc=None):
+        """Engine.obs (engine.py:738-778), sorted key order:
+        [acc] | ctrl | goal_compass | goal_lidar | hazards_lidar | qpos | qvel | [vel]."""
         n = qpos.shape[0]
         xpos, xmat, goal, hz = self._geometry(d, qpos_geom)
         obs = np.zeros((n, self.obs_dim), np.float32)
         cost = np.zeros(n, np.float32)
         gb = np.zeros((n, 1), np.int32); hb = np.zeros((n, self.nh), np.int32)
         o = 0
+        if self.with_acc:
+            if acc is not None:
+                obs[:, 0:2] = acc
+            o = 2
+        if self.with_vel and vel is not None:
+            obs[:, -2:] = vel
         obs[:, o:o + self.nu] = ctrl; o += self.nu
         comp = np.zeros(2, np.float32); lid = np.zeros(self.nb, np.float32); c1 = np.zeros(1, np.float32)
         cfg = C.byref(self.gx_config)
@@ -117,6 +129,7 @@ class ArtOracleEngine:
         self.steps[:] = 0
         self._obs = obs
         self.last_data = d
+        self.hx_data = d['xpos'][:, self.robot_body, :2].astype(np.float32)   # Engine._data <- reset data; _last_data stays
         return obs
 
     def step(self, action):
@@ -127,7 +140,23 @@ class ArtOracleEngine:
             qpos_pre = self.qpos
             self.qpos, self.qvel, d = mx.step(self.mm, self.qpos, self.qvel, self.ctrl, self.warm)
             self.warm = d['qacc'].copy()
-        obs, cost, dist, extra = self._obs_rows(d, qpos_pre, self.qpos, self.qvel, self.ctrl)
+        vel = acc = None
+        xp = d['xpos'][:, self.robot_body, :2].astype(np.float32)
+        if self.with_vel or self.with_acc:
+            # update_data: _last_last_data <- _last_data <- _data, same for done (engine.py:426-430)
+            vel = np.zeros((self.n, 2), np.float32); acc = np.zeros((self.n, 2), np.float32)
+            xm = d['xmat'][:, self.robot_body].astype(np.float32).reshape(-1, 9)
+            cfg = C.byref(self.gx_config)
+            for i in range(self.n):
+                cur, la, ll = (np.ascontiguousarray(a) for a in (xp[i], self.hx_data[i], self.hx_last[i]))
+                v2, a2 = np.zeros(2, np.float32), np.zeros(2, np.float32)
+                self.L.gxo_piece_vel_acc(cfg, _p(np.ascontiguousarray(xm[i])), _p(cur), _p(la), _p(ll), C.c_int(self.h_depth),
+                                         C.c_float(float(self.done[i])), C.c_float(float(self.h_last_done[i])), _p(v2), _p(a2))
+                vel[i], acc[i] = v2, a2
+        self.hx_last, self.hx_data = self.hx_data, xp.copy()
+        self.h_last_done = self.done.copy()
+        self.h_depth = min(self.h_depth + 1, 2)
+        obs, cost, dist, extra = self._obs_rows(d, qpos_pre, self.qpos, self.qvel, self.ctrl, vel, acc)
         last = np.where(self.done > 0, dist, self.prev_dist).astype(np.float32)
         d_dist = (last - dist).astype(np.float32)
         reward = (d_dist * np.float32(self.config['reward_distance'])).astype(np.float32)

@@ -271,3 +271,34 @@ def test_config_variants_one_step(mods, extra):
             g.set_state(o.get_state())
             l2 = np.ascontiguousarray(pool[n:2 * n, :4 + 2 * nh])
             close(cpu(g.reset_done(l2))[:, :k], o.reset_done(l2)[:, :k], 5e-5, 5e-5, 'reset_done obs')
+
+
+def test_observe_vel_acc_for_articulated_robots(mods):
+    """ego_vel_acc (engine.py:902-929) on the ant: finite differences of the root xpos in the robot
+    frame with the done-masking and the None-ness of the first two steps; obs = acc | default | vel."""
+    Engine, Oracle, pool = mods
+    n, nu, nv = 24, 8, 11
+    cfg = {'env_num': n, 'robot_base': 'xmls/ant.xml', 'num_steps': 7, '_seed': 2, 'observe_vel': True, 'observe_acc': True}
+    g, o = Engine(dict(cfg)), Oracle(dict(cfg), dtype=np.float64)
+    assert g.observation_space.shape == (4 + nu + 34 + 2 * nv,)
+    lay = pool[:n]
+    close(cpu(g.reset(lay)), o.reset(lay), 2e-6, 2e-6, 'reset obs (vel = acc = 0)')
+    rng = np.random.default_rng(5)
+    seen_done = 0
+    for t in range(20):
+        a = rng.uniform(-1, 1, (n, nu)).astype(np.float32)
+        o.round_state_to_fp32()
+        g.set_state(o.get_state())          # joint state injected; the xpos history evolves on each side
+        og, rg, dg, ig = g.step(torch.from_numpy(a).cuda())
+        oo, ro, do, io = o.step(a)
+        og = cpu(og)
+        close(og[:, 2:2 + nu + 34 + nv], oo[:, 2:2 + nu + 34 + nv], 5e-5, 5e-5, f'step {t} default part')
+        close(og[:, -2:], oo[:, -2:], 2e-4, 1e-4, f'step {t} vel')            # d(xpos)/dt, dt = 0.09
+        close(og[:, :2], oo[:, :2], 5e-3, 1e-3, f'step {t} acc')              # second difference / dt^2
+        assert (cpu(dg) == do).all()
+        seen_done += int(do.sum())
+        if do.any():
+            g.set_state(o.get_state())
+            l2 = pool[n * (1 + t % 3):n * (2 + t % 3)]
+            close(cpu(g.reset_done(l2))[:, 2:2 + nu + 34 + nv], o.reset_done(l2)[:, 2:2 + nu + 34 + nv], 5e-5, 5e-5, 'reset_done obs')
+    assert seen_done >= n and np.abs(oo[:, -2:]).max() > 1e-3
