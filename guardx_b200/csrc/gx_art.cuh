@@ -782,19 +782,30 @@ GX_HD void gx_art_step(const GxArtModel& m, int lane, unsigned mask, GxArtLane<L
         continue;
       }
       // warm start (mjx solver.solve): start from qacc_warmstart iff its cost beats qacc_smooth's.
-      // Candidates in the order warm, smooth, warm-again so that the quantities derived from the
-      // winner (M*qacc, J*qacc - aref) are the ones left behind by the last evaluation.
-      float cost_w = 0.0f;
+      // Candidates in the order smooth, warm, smooth-again so that the quantities derived from the
+      // winner (M*qacc, J*qacc - aref) are the ones left behind by the last evaluation.  At
+      // qacc_smooth the Gauss term vanishes identically and M*qacc = qfrc_smooth, so that candidate
+      // needs no matrix-vector product.
+      float cost_s = 0.0f;
 #pragma unroll 1
       for (int cnd = 0; cnd < 3; ++cnd) {
-        const bool usew = cnd != 1;
+        const bool usew = cnd == 1;
 #pragma unroll
         for (int r = 0; r < 3; ++r) ar[r] = usew ? st.wr[r] : sr[r];
 #pragma unroll
         for (int j = 0; j < LPL; ++j)
 #pragma unroll
           for (int i = 0; i < K; ++i) al[j][i] = usew ? st.wl[j][i] : sl[j][i];
-        mul_m(ar, al, Mar, Mal);
+        if (usew) {
+          mul_m(ar, al, Mar, Mal);
+        } else {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) Mar[r] = fr[r];
+#pragma unroll
+          for (int j = 0; j < LPL; ++j)
+#pragma unroll
+            for (int i = 0; i < K; ++i) Mal[j][i] = fl[j][i];
+        }
         float local = 0.0f;
 #pragma unroll
         for (int j = 0; j < LPL; ++j) {
@@ -814,8 +825,8 @@ GX_HD void gx_art_step(const GxArtModel& m, int lane, unsigned mask, GxArtLane<L
         float cost = gx_art_sum<LANES>(local, mask);
 #pragma unroll
         for (int r = 0; r < 3; ++r) cost = gx_fma(0.5f * (Mar[r] - fr[r]), ar[r] - sr[r], cost);
-        if (cnd == 0) cost_w = cost;
-        else if (cnd == 1 && !(cost_w < cost)) break;
+        if (cnd == 0) cost_s = cost;
+        else if (cnd == 1 && cost < cost_s) break;       // warm start wins: its derived quantities are current
       }
       mode = PH_NEWTON;
       continue;

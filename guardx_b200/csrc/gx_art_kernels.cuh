@@ -385,8 +385,11 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
 }
 
 // Host launcher for one robot shape: picks the mode / auto-reset instance and, for the step,
-// the register budget (MINB) by grid size.
-template <int L, int NL, int K, int NB>
+// the register budget by grid size: 2 resident blocks per SM (no spills) up to 3 waves, MINB_BIG
+// beyond -- measured per shape at 65 536 envs: ant 2/4/6/8/10/12 -> 512/348/333/313/368/417 us (8 wins:
+// 64 registers, spills served by L1, 32 warps per SM hide the dependent-instruction latency); walker
+// 4/6/8 -> 599/729/807 us; swimmer indifferent.
+template <int L, int NL, int K, int NB, int MINB_BIG>
 static cudaError_t gx_art_launch_shape(const GxArtLaunch& a) {
   const int n = a.p->n, block = 128;
   const int grid = (n * L + block - 1) / block;
@@ -397,7 +400,7 @@ static cudaError_t gx_art_launch_shape(const GxArtLaunch& a) {
       a.qacc, a.aux, a.stats_on)
   if (a.mode == GX_ART_RESET) GX_ART_GO(GX_ART_RESET, false, 2);
   else if (a.mode == GX_ART_RESET_DONE) GX_ART_GO(GX_ART_RESET_DONE, false, 2);
-  else if (grid > 3 * a.sm_count) { if (a.autoreset) GX_ART_GO(GX_ART_STEP, true, 4); else GX_ART_GO(GX_ART_STEP, false, 4); }
+  else if (grid > 3 * a.sm_count) { if (a.autoreset) GX_ART_GO(GX_ART_STEP, true, MINB_BIG); else GX_ART_GO(GX_ART_STEP, false, MINB_BIG); }
   else { if (a.autoreset) GX_ART_GO(GX_ART_STEP, true, 2); else GX_ART_GO(GX_ART_STEP, false, 2); }
 #undef GX_ART_GO
   return cudaGetLastError();
