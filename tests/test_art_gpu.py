@@ -302,3 +302,25 @@ def test_observe_vel_acc_for_articulated_robots(mods):
             l2 = pool[n * (1 + t % 3):n * (2 + t % 3)]
             close(cpu(g.reset_done(l2))[:, 2:2 + nu + 34 + nv], o.reset_done(l2)[:, 2:2 + nu + 34 + nv], 5e-5, 5e-5, 'reset_done obs')
     assert seen_done >= n and np.abs(oo[:, -2:]).max() > 1e-3
+
+
+@pytest.mark.parametrize("robot", ['ant', 'walker', 'swimmer'])
+def test_large_grid_kernel_variant_equals_small_grid_variant(mods, robot):
+    """Grids above 3 waves use the high-occupancy build of the step kernel (fewer registers, spills);
+    same arithmetic, so the first rows of a 20 000-env batch must equal a 1000-env batch bit for bit."""
+    Engine, _, pool = mods
+    base, nu, nv = ROBOTS[robot]
+    small, big = 1000, 20000
+    lay_small = pool[:small]
+    lay_big = np.concatenate([pool[:small]] + [pool[:small]] * (big // small - 1), 0)
+    a_env = Engine({'env_num': small, 'robot_base': base, 'num_steps': 1000, '_seed': 1})
+    b_env = Engine({'env_num': big, 'robot_base': base, 'num_steps': 1000, '_seed': 1})
+    oa, ob = a_env.reset(lay_small), b_env.reset(lay_big)
+    assert torch.equal(oa, ob[:small])
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    for t in range(12):
+        act = torch.rand(small, nu, device='cuda', generator=gen) * 2 - 1
+        oa, ra, da, ia = a_env.step(act)
+        ob, rb, db, ib = b_env.step(act.repeat(big // small, 1))
+        assert torch.equal(oa, ob[:small]) and torch.equal(ob[:small], ob[-small:]), t
+        assert torch.equal(ra, rb[:small]) and torch.equal(ia['cost'], ib['cost'][:small]) and torch.equal(da, db[:small])
