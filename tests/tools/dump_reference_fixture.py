@@ -5,9 +5,9 @@ been run there; it exists so that the assumption tags A1-A4 of DESIGN.md can be
 discharged on any machine that has the reference's dependencies).
 
     # on a machine with the reference installed (JAX_PLATFORMS=cpu is fine)
-    python tools/dump_reference_fixture.py dump  --ref /path/to/guardX --out fixture_true.npz
+    python tests/tools/dump_reference_fixture.py dump  --ref /path/to/guardX --out fixture_true.npz
     # anywhere (CPU is enough): replay the same layouts/actions through the oracle
-    python tools/dump_reference_fixture.py check --fixture fixture_true.npz
+    python tests/tools/dump_reference_fixture.py check --fixture fixture_true.npz
 
 `dump` drives the reference exactly as BASELINE.json configs[0] says (Goal_Point_8Hazards,
 64 envs, 1000 random-action steps), but with INJECTED layouts and actions so that RNG
@@ -35,7 +35,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 N, T = 64, 1000
