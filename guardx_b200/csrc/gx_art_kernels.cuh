@@ -394,10 +394,16 @@ static cudaError_t gx_art_launch_shape(const GxArtLaunch& a) {
   const int n = a.p->n, block = 128;
   const int grid = (n * L + block - 1) / block;
   const size_t sh = (size_t)(block / L) * a.p->obs_dim * sizeof(float);
-#define GX_ART_GO(MODE, AR, MB)                                                                            \
-  gx_art_kernel<L, NL, K, NB, MODE, AR, MB><<<grid, block, sh, a.stream>>>(                              \
-      *a.p, *a.s, *a.art, a.pool, a.layout, a.action, a.obs_in, a.obs, a.act_out, a.reward, a.done, a.cost, \
-      a.qacc, a.aux, a.stats_on)
+#define GX_ART_GO(MODE, AR, MB)                                                                              \
+  do {                                                                                                       \
+    auto kern = gx_art_kernel<L, NL, K, NB, MODE, AR, MB>;                                                   \
+    if (sh > 48 * 1024) { /* large lidars on a 1-lane robot: opt in to more dynamic shared memory */        \
+      cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);     \
+      if (e_ != cudaSuccess) return e_;                                                                      \
+    }                                                                                                        \
+    kern<<<grid, block, sh, a.stream>>>(*a.p, *a.s, *a.art, a.pool, a.layout, a.action, a.obs_in, a.obs,     \
+                                        a.act_out, a.reward, a.done, a.cost, a.qacc, a.aux, a.stats_on);     \
+  } while (0)
   if (a.mode == GX_ART_RESET) GX_ART_GO(GX_ART_RESET, false, 2);
   else if (a.mode == GX_ART_RESET_DONE) GX_ART_GO(GX_ART_RESET_DONE, false, 2);
   else if (grid > 3 * a.sm_count) { if (a.autoreset) GX_ART_GO(GX_ART_STEP, true, MINB_BIG); else GX_ART_GO(GX_ART_STEP, false, MINB_BIG); }

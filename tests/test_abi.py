@@ -58,13 +58,13 @@ def test_no_cpu_fallback():
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under guardx_b200/ may import,
     include, link or dlopen it."""
-    pkg = os.path.join(ROOT, "guardx_b200")
     bad = re.compile(r"^\s*(from|import)\s+oracle\b|#\s*include\s*[\"<][^\">]*oracle|gxoracle|gxo_", re.M)
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
-                text = open(os.path.join(dirpath, f)).read()
-                assert not bad.search(text), f"{f} references the oracle"
+    for sub in ("guardx_b200", "tools", "include"):     # tools/ are developer scripts of the product side too
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not bad.search(text), f"{sub}/{f} references the oracle"
 
 
 def test_bad_config_is_rejected_like_the_reference():

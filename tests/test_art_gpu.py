@@ -324,3 +324,18 @@ def test_large_grid_kernel_variant_equals_small_grid_variant(mods, robot):
         ob, rb, db, ib = b_env.step(act.repeat(big // small, 1))
         assert torch.equal(oa, ob[:small]) and torch.equal(ob[:small], ob[-small:]), t
         assert torch.equal(ra, rb[:small]) and torch.equal(ia['cost'], ib['cost'][:small]) and torch.equal(da, db[:small])
+
+
+def test_swimmer_with_the_largest_lidars(mods):
+    """64 bins x 2 lidars on the one-lane-per-env robot: the warp tile needs > 48 KB of dynamic shared
+    memory per block (opt-in attribute)."""
+    Engine, Oracle, pool = mods
+    n = 200
+    cfg = {'env_num': n, 'robot_base': 'xmls/swimmer.xml', 'num_steps': 50, 'lidar_num_bins': 64, '_seed': 3}
+    g, o = Engine(dict(cfg)), Oracle(dict(cfg), dtype=np.float64)
+    assert g.observation_space.shape == (2 + 2 + 128 + 10,)
+    close(cpu(g.reset(pool[:n])), o.reset(pool[:n]), 2e-6, 2e-6, 'reset obs')
+    a = np.random.default_rng(0).uniform(-1, 1, (n, 2)).astype(np.float32)
+    og, rg, dg, ig = g.step(torch.from_numpy(a).cuda())
+    oo, ro, do, io = o.step(a)
+    close(cpu(og)[:, :137], oo[:, :137], 2e-5, 2e-5, 'obs')
