@@ -259,3 +259,45 @@ def test_joint_limit_and_contact_are_soft_springs_with_the_documented_constants(
     assert (-a - aref) < 0                           # the row is active
     assert d['qacc'][0, 0] == pytest.approx(a, rel=1e-9)
     assert d['efc_force'][0, 0] == pytest.approx(-(1 / R) * (-a - aref), rel=1e-9) and d['efc_force'][0, 0] > 0
+
+
+def test_mjcf_parser_rules_and_rejections():
+    """Defaults resolution, the actuator-shortcut rule behind assumption A1, autolimits, fromto
+    frames, and clear errors for what the compiler does not cover."""
+    xml = """<mujoco><option timestep="0.005"/>
+      <default><joint damping="2" armature="0.5"/><geom density="10" contype="0" conaffinity="0"/>
+        <motor ctrllimited="true" ctrlrange="-1 1" forcelimited="true" forcerange="-3 3"/><velocity kv="4"/></default>
+      <worldbody><geom name="floor" type="plane" size="1 1 .1" conaffinity="1"/>
+        <body name="robot" pos="0 0 .2">
+          <joint type="slide" axis="2 0 0" name="robot_x"/><joint type="slide" axis="0 1 0" name="robot_y" damping="7"/>
+          <joint type="hinge" axis="0 0 1" name="robot_z" range="-90 90"/>
+          <geom type="capsule" fromto="0 0 0 0 0.4 0" size="0.05"/>
+          <body name="tip" pos="0 0.4 0"><joint name="j" axis="1 0 0" limited="false" range="-10 10"/>
+            <geom type="sphere" size="0.03" contype="1"/></body></body></worldbody>
+      <actuator><general joint="j" gear="5"/><motor joint="robot_z" gear="2"/></actuator></mujoco>"""
+    m = mjcf.compile_spec(mjcf.parse_mjcf(xml))
+    assert m.opt['timestep'] == 0.005 and m.nq == 4 and m.nu == 2
+    np.testing.assert_allclose(m.jnt_axis[0], [1, 0, 0])                       # normalised
+    assert m.dof_damping.tolist() == [2, 7, 2, 2] and m.dof_armature.tolist() == [0.5] * 4
+    assert m.jnt_limited.tolist() == [0, 0, 1, 0]                              # autolimits; explicit false wins
+    np.testing.assert_allclose(m.jnt_range[2], [-math.pi / 2, math.pi / 2])    # degrees by default
+    # <general> inherits the default actuator as left by the LAST shortcut (<velocity kv=4>): gain 4, bias (0,0,-4);
+    # <motor> resets it to gain 1, no bias; both keep the limits of the defaults class
+    np.testing.assert_allclose(m.actuator_gainprm0, [4, 1]); np.testing.assert_allclose(m.actuator_biasprm, [[0, 0, -4], [0, 0, 0]])
+    assert m.actuator_forcelimited.tolist() == [1, 1] and m.actuator_gear.tolist() == [5, 2]
+    # fromto capsule: centre at the midpoint, z axis along +y, half-length 0.2
+    g = 1
+    np.testing.assert_allclose(m.geom_pos[g], [0, 0.2, 0]); assert m.geom_size[g][1] == pytest.approx(0.2)
+    np.testing.assert_allclose(mjcf.quat2mat(m.geom_quat[g])[:, 2], [0, 1, 0], atol=1e-12)
+    assert m.contact_pairs == [(0, 2)]                                        # only the tip sphere meets the floor
+    for bad, exc in (('<mujoco><default><default class="a"/></default><worldbody/></mujoco>', NotImplementedError),
+                     ('<mujoco><compiler coordinate="global"/><worldbody/></mujoco>', NotImplementedError)):
+        with pytest.raises(exc):
+            mjcf.parse_mjcf(bad)
+    free = mjcf.parse_mjcf('<mujoco><worldbody><body name="robot"><freejoint name="robot"/><geom size=".1"/></body></worldbody></mujoco>')
+    with pytest.raises(NotImplementedError):
+        mjcf.compile_spec(free)
+    # topology the kernels do not cover is refused by the lowering, not silently mis-simulated
+    tree = mjcf.parse_mjcf(xml.replace('range="-90 90"', '').replace('<body name="tip" pos="0 0.4 0">', '<body name="side" pos="0.1 0 0"><joint name="s" axis="0 0 1"/><geom size=".02"/><body name="a"><joint name="a1"/><geom size=".02"/></body><body name="b"><joint name="b1"/><geom size=".02"/></body></body><body name="tip" pos="0 0.4 0">'))
+    with pytest.raises(AssertionError, match="serial chains"):
+        art_model.lower_art(mjcf.compile_spec(tree))
