@@ -275,6 +275,14 @@ class Engine:
         self._obs = out
         return out
 
+    def done_indices(self):
+        """(idx, count) of the envs whose last `done` was 1, on the device (rollout_ops.done_indices):
+        what SCPO's ``env.reset_done()[np.where(done == 1)]`` (scpo/scpo.py:722) needs, without the
+        device->host copy of `done`."""
+        assert self._done is not None, 'done_indices() before the first step()'
+        from . import rollout_ops
+        return rollout_ops.done_indices(self._done)
+
     def rollout(self, T: int, want=("obs", "act", "reward", "cost", "done")):
         ''' T steps of a ~ U(-1,1) (as trpo/myTest.py:31 drives the reference) with
         reset_done after every step, in one kernel launch. '''

@@ -90,3 +90,20 @@ def test_done_compaction(n, p):
     want = np.where(done == 1)[0]
     assert int(count.item()) == len(want)
     assert np.array_equal(idx[:len(want)].cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+def test_engine_done_indices():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from guardx_b200 import make
+    env = make("Goal_Point_8Hazards", env_num=500, seed=1, max_ep_len=5)
+    env.reset()
+    for t in range(8):
+        o, r, d, i = env.step(torch.zeros(500, 2, device='cuda'))
+        idx, count = env.done_indices()
+        want = torch.nonzero(d > 0).squeeze(-1).to(torch.int32)
+        assert int(count) == want.numel() and torch.equal(idx[:want.numel()], want)
+        env.reset_done()
+    assert int(count) >= 0
