@@ -17,8 +17,9 @@ Two front ends produce the same intermediate ``Spec``:
 ``add_world_geoms`` appends the goal/hazard bodies the way ``World.build`` does.
 ``compile_spec`` turns a ``Spec`` into a ``Model`` of numpy arrays named like ``mjModel``.
 
-Scope: kinematic trees of hinge / slide joints (planar-root robots: Point, Swimmer, Ant,
-Walker).  Free joints are parsed but ``compile_spec`` rejects them (Doggo: next).
+Scope: kinematic trees of hinge / slide joints, optionally under one free joint (Doggo's root).
+The CUDA kernels of this round cover the planar-root robots (Point, Swimmer, Ant, Walker); the
+free-joint path is compiled and restated in the oracle (oracle/mjx_numpy.py) as groundwork.
 """
 from __future__ import annotations
 
@@ -325,7 +326,8 @@ class Model:
     actuator_gainprm0: np.ndarray
     actuator_biasprm: np.ndarray  # [nu, 3]
     stat_meaninertia: float
-    contact_pairs: list          # (geom1, geom2) that pass the contype/conaffinity + body filters
+    body_weldid: np.ndarray = None   # set by compile_spec
+    contact_pairs: list = None          # (geom1, geom2) that pass the contype/conaffinity + body filters
 
     def body_id(self, name):
         return self.body_name.index(name)
@@ -364,8 +366,23 @@ def compile_spec(spec: Spec) -> Model:
         for jg in body['joints']:
             j = _resolve(spec.defaults['joint'], JOINT_DEFAULT, jg)
             t = _JNT_TYPES[j['type']]
-            if t in (JNT_FREE, JNT_BALL):
-                raise NotImplementedError('free/ball joints (Doggo) are not compiled by this build')
+            if t == JNT_BALL:
+                raise NotImplementedError('ball joints are not compiled by this build')
+            if t == JNT_FREE:
+                # <freejoint>: no attributes, the defaults class is NOT applied (no damping, armature,
+                # stiffness, never limited); 7 qpos (position + unit quaternion, qpos0 = the body frame),
+                # 6 dofs (linear in world axes, angular in body axes)
+                if len(body['joints']) != 1 or body['parent'] != 0:
+                    raise NotImplementedError('a free joint must be the only joint of a top-level body')
+                J['name'].append(jg.get('name')); J['type'].append(t); J['body'].append(b)
+                J['pos'].append(np.zeros(3)); J['axis'].append(np.array([0., 0., 1.]))
+                J['qposadr'].append(nq); J['dofadr'].append(nv)
+                J['limited'].append(0); J['range'].append(np.zeros(2)); J['stiffness'].append(0.0); J['margin'].append(0.0)
+                J['solref'].append(np.asarray(JOINT_DEFAULT['solreflimit'], float)); J['solimp'].append(np.asarray(JOINT_DEFAULT['solimplimit'], float))
+                J['damping'].append(0.0); J['armature'].append(0.0); J['springref'].append(0.0); J['ref'].append(0.0)
+                J.setdefault('nq', []).append(7); J.setdefault('nv', []).append(6)
+                nq += 7; nv += 6
+                continue
             axis = np.asarray(j['axis'], float)
             axis = axis / np.linalg.norm(axis)
             rng = np.asarray(j['range'], float) * (deg if t == JNT_HINGE else 1.0)
@@ -381,6 +398,7 @@ def compile_spec(spec: Spec) -> Model:
             J['solref'].append(np.asarray(j['solreflimit'], float)); J['solimp'].append(np.asarray(j['solimplimit'], float))
             J['damping'].append(j['damping']); J['armature'].append(j['armature'])
             J['springref'].append(j['springref'] * scale); J['ref'].append(j['ref'] * scale)
+            J.setdefault('nq', []).append(1); J.setdefault('nv', []).append(1)
             nq += 1; nv += 1
         body_dofnum.append(nv - dof0)
         for gg in body['geoms']:
@@ -430,7 +448,19 @@ def compile_spec(spec: Spec) -> Model:
             V[:, 2] = -V[:, 2]
         body_inertia[b] = w
         body_iquat[b] = _mat2quat(V)
-    jnt_qpos0 = np.asarray(J['ref'], float) if njnt else np.zeros(0)
+    # per-qpos / per-dof expansions (a free joint owns 7 qpos and 6 dofs)
+    jnt_nq, jnt_nv = J.get('nq', []), J.get('nv', [])
+    jnt_qpos0 = np.zeros(nq); qpos_spring = np.zeros(nq)
+    dof_jnt, dof_damping, dof_armature = [], [], []
+    for jid in range(njnt):
+        a = J['qposadr'][jid]
+        if J['type'][jid] == JNT_FREE:
+            b_ = J['body'][jid]
+            jnt_qpos0[a:a + 3] = body_pos[b_]; jnt_qpos0[a + 3:a + 7] = body_quat[b_]
+            qpos_spring[a:a + 7] = jnt_qpos0[a:a + 7]
+        else:
+            jnt_qpos0[a] = J['ref'][jid]; qpos_spring[a] = J['springref'][jid]
+        dof_jnt += [jid] * jnt_nv[jid]; dof_damping += [J['damping'][jid]] * jnt_nv[jid]; dof_armature += [J['armature'][jid]] * jnt_nv[jid]
     mdl = Model(
         opt=dict(spec.opt), nq=nq, nv=nv, nu=0, nbody=nbody, njnt=njnt, ngeom=ngeom,
         body_name=[b['name'] for b in spec.bodies], body_parentid=np.asarray(body_parent, np.int32),
@@ -445,10 +475,10 @@ def compile_spec(spec: Spec) -> Model:
         jnt_limited=np.asarray(J['limited'], np.int32), jnt_range=np.asarray(J['range']).reshape(njnt, 2),
         jnt_stiffness=np.asarray(J['stiffness'], float), jnt_margin=np.asarray(J['margin'], float),
         jnt_solref=np.asarray(J['solref']).reshape(njnt, 2), jnt_solimp=np.asarray(J['solimp']).reshape(njnt, 5),
-        qpos0=jnt_qpos0.copy(), qpos_spring=np.asarray(J['springref'], float),
-        dof_bodyid=np.asarray(J['body'], np.int32), dof_jntid=np.arange(njnt, dtype=np.int32),
-        dof_parentid=np.zeros(nv, np.int32), dof_damping=np.asarray(J['damping'], float),
-        dof_armature=np.asarray(J['armature'], float), dof_invweight0=np.zeros(nv),
+        qpos0=jnt_qpos0.copy(), qpos_spring=qpos_spring,
+        dof_bodyid=np.asarray([J['body'][jid] for jid in dof_jnt], np.int32), dof_jntid=np.asarray(dof_jnt, np.int32),
+        dof_parentid=np.zeros(nv, np.int32), dof_damping=np.asarray(dof_damping, float),
+        dof_armature=np.asarray(dof_armature, float), dof_invweight0=np.zeros(nv),
         geom_name=G['name'], geom_type=np.asarray(G['type'], np.int32), geom_bodyid=np.asarray(G['body'], np.int32),
         geom_pos=np.asarray(G['pos']).reshape(ngeom, 3), geom_quat=np.asarray(G['quat']).reshape(ngeom, 4),
         geom_size=np.asarray(G['size']).reshape(ngeom, 3), geom_friction=np.asarray(G['friction']).reshape(ngeom, 3),
@@ -460,6 +490,7 @@ def compile_spec(spec: Spec) -> Model:
         actuator_ctrlrange=np.zeros((0, 2)), actuator_forcelimited=np.zeros(0, np.int32),
         actuator_forcerange=np.zeros((0, 2)), actuator_gainprm0=np.zeros(0), actuator_biasprm=np.zeros((0, 3)),
         stat_meaninertia=1.0, contact_pairs=[])
+    mdl.contact_pairs = []
     # dof tree: parent dof = previous dof of the same body, else last dof of the nearest ancestor with dofs
     for i in range(nv):
         b = mdl.dof_bodyid[i]
@@ -490,16 +521,22 @@ def compile_spec(spec: Spec) -> Model:
     mdl.actuator_forcerange = np.asarray([a['forcerange'] for a in acts], float).reshape(nu, 2)
     mdl.actuator_gainprm0 = np.asarray([a['gainprm0'] for a in acts], float)
     mdl.actuator_biasprm = np.asarray([a['biasprm'] for a in acts], float).reshape(nu, 3)
-    # ---- collision pairs (broad-phase filters) ----------------------------------
+    # ---- collision pairs (broad-phase filters, engine_collision_driver.c) ---------------------
+    # bodies without joints are welded to their parent: filters work on weld ids
+    weld = np.zeros(nbody, np.int32)
+    for b in range(1, nbody):
+        weld[b] = b if mdl.body_jntnum[b] > 0 else weld[mdl.body_parentid[b]]
+    mdl.body_weldid = weld
     for g1 in range(ngeom):
         for g2 in range(g1 + 1, ngeom):
-            b1, b2 = mdl.geom_bodyid[g1], mdl.geom_bodyid[g2]
-            if b1 == b2:
+            w1, w2 = weld[mdl.geom_bodyid[g1]], weld[mdl.geom_bodyid[g2]]
+            if w1 == w2:
                 continue
             if not ((mdl.geom_contype[g1] & mdl.geom_conaffinity[g2]) or (mdl.geom_contype[g2] & mdl.geom_conaffinity[g1])):
                 continue
-            # parent-child filter (does not apply when the parent is the world)
-            if (mdl.body_parentid[b1] == b2 and b2 != 0) or (mdl.body_parentid[b2] == b1 and b1 != 0):
+            # parent-child filter on welded bodies (does not apply when the parent is the world)
+            p1, p2 = weld[mdl.body_parentid[w1]] if w1 else -1, weld[mdl.body_parentid[w2]] if w2 else -1
+            if (w1 != 0 and w1 == p2) or (w2 != 0 and w2 == p1):
                 continue
             mdl.contact_pairs.append((g1, g2))
     _set_const(mdl)
@@ -536,6 +573,12 @@ def kinematics0(m: Model, qpos=None):
         quat = quat_mul(xquat[p], m.body_quat[b])
         for k in range(m.body_jntnum[b]):
             j = m.body_jntadr[b] + k
+            if m.jnt_type[j] == JNT_FREE:      # the pose IS the qpos
+                a = m.jnt_qposadr[j]
+                pos = np.array(qpos[a:a + 3], float); quat = np.array(qpos[a + 3:a + 7], float)
+                quat = quat / np.linalg.norm(quat)
+                xanchor[j] = pos; xaxis[j] = quat2mat(quat) @ m.jnt_axis[j]
+                continue
             R = quat2mat(quat)
             xanchor[j] = pos + R @ m.jnt_pos[j]
             xaxis[j] = R @ m.jnt_axis[j]
@@ -568,7 +611,13 @@ def body_jac(m: Model, kin, b: int, point):
         for k in range(m.body_jntnum[b]):
             j = m.body_jntadr[b] + k
             i = m.jnt_dofadr[j]
-            if m.jnt_type[j] == JNT_SLIDE:
+            if m.jnt_type[j] == JNT_FREE:      # 3 translations along world axes, 3 rotations about body axes
+                jp[:, i:i + 3] = np.eye(3)
+                R = kin['xmat'][b]
+                for a in range(3):
+                    jr[:, i + 3 + a] = R[:, a]
+                    jp[:, i + 3 + a] = np.cross(R[:, a], point - kin['xpos'][b])
+            elif m.jnt_type[j] == JNT_SLIDE:
                 jp[:, i] = kin['xaxis'][j]
             else:
                 jr[:, i] = kin['xaxis'][j]
@@ -586,6 +635,11 @@ def _set_const(m: Model):
     Minv = np.linalg.inv(M)
     m.stat_meaninertia = float(np.trace(M) / m.nv)
     m.dof_invweight0 = np.diag(Minv).copy()
+    for j in range(m.njnt):                # free joint: one value for the 3 translations, one for the 3 rotations
+        if m.jnt_type[j] == JNT_FREE:
+            i = m.jnt_dofadr[j]
+            m.dof_invweight0[i:i + 3] = m.dof_invweight0[i:i + 3].mean()
+            m.dof_invweight0[i + 3:i + 6] = m.dof_invweight0[i + 3:i + 6].mean()
     for b in range(1, m.nbody):
         jp, jr = body_jac(m, kin, b, kin['xipos'][b])
         A = jp @ Minv @ jp.T

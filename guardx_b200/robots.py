@@ -15,6 +15,8 @@ from .mjcf import Spec, OPT_DEFAULT
 
 ROBOT_FILES = {'xmls/point.xml': 'point', 'xmls/ant.xml': 'ant', 'xmls/walker.xml': 'walker',
                'xmls/swimmer.xml': 'swimmer'}
+# described and compiled, but without CUDA kernels yet (free-joint root, capsule contacts): groundwork
+GROUNDWORK_FILES = {'xmls/doggo.xml': 'doggo'}
 
 
 def _spec(timestep, angle='degree'):
@@ -146,7 +148,44 @@ def swimmer() -> Spec:
     return s
 
 
+def doggo() -> Spec:
+    """xmls/doggo.xml: free-joint torso (two 0.075 capsules; the rear one behind a waist hinge), four
+    legs of hip-z, hip-y and ankle hinges with joint springs (stiffness 0.01, springref), every geom a
+    colliding capsule; 12 motors, gear 0.02; timestep 0.01.  No CUDA kernels for it yet."""
+    s = _spec(0.01)
+    s.defaults['joint'] = dict(limited=True, stiffness=0.01)
+    s.defaults['geom'] = dict(condim=3, size=(0.032,), type='capsule', density=5.0)
+    s.defaults['actuator'] = dict(ctrllimited=True, ctrlrange=(-1., 1.), gear=0.02, gainprm0=1.0, biasprm=(0., 0., 0.))
+    s.bodies[0]['geoms'].append(dict(name='floor', type='plane', size=(5., 5., 0.1), condim=3))
+    r = _body(s, 'robot', 0, (0, 0, 0.3))
+    s.bodies[r]['joints'] = [dict(type='free', name='robot')]
+    s.bodies[r]['geoms'] = [dict(name='robot', pos=(0., 0., 0.), size=(0.075,), fromto=(0., 0., 0., .2, 0., 0.), type='capsule', density=0.5)]
+
+    def leg(k, parent, sx, sy, hip_y_range, hip_y_spring):
+        b0 = _body(s, f'leg_{k}', parent, (0, 0, 0))
+        s.bodies[b0]['geoms'] = [dict(name=f'aux_{k}', fromto=(.1 * sx, 0., 0., .2 * sx, .1 * sy, 0.))]
+        b1 = _body(s, f'aux_{k}', b0, (.2 * sx, .1 * sy, 0))
+        s.bodies[b1]['joints'] = [dict(type='hinge', axis=(0., 0., float(sy)), name=f'hip_{k}_z', pos=(0., 0., 0.), range=(-10., 30.), springref=0.),
+                                  dict(type='hinge', axis=(0., 1., 0.), name=f'hip_{k}_y', pos=(0., 0., 0.), range=hip_y_range, springref=hip_y_spring)]
+        s.bodies[b1]['geoms'] = [dict(name=f'hip_{k}', fromto=(0., 0., 0., 0.098, 0.0566 * sy, -.05))]
+        b2 = _body(s, None, b1, (0.098, 0.0566 * sy, -.05))
+        s.bodies[b2]['joints'] = [dict(type='hinge', axis=(-.5 * sy, .866, 0.), name=f'ankle_{k}', pos=(0., 0., 0.), range=(-75., 0.), springref=-20.)]
+        s.bodies[b2]['geoms'] = [dict(name=f'ankle_{k}', fromto=(0., 0., 0., -0.1176, -0.0679 * sy, -.1))]
+
+    leg(1, r, 1, 1, (-75., 15.), -10.)
+    leg(4, r, 1, -1, (-75., 15.), -10.)
+    rear = _body(s, 'rear', r, (0, 0, 0))
+    s.bodies[rear]['geoms'] = [dict(name='robot2', pos=(0., 0., 0.), size=(0.075,), fromto=(-.2, 0., 0., 0., 0., 0.), type='capsule', density=0.5)]
+    s.bodies[rear]['joints'] = [dict(type='hinge', axis=(1., 0., 0.), name='waist_x', pos=(0., 0., 0.), range=(-30., 30.), springref=0.)]
+    leg(2, rear, -1, 1, (0., 135.), 0.)
+    leg(3, rear, -1, -1, (0., 135.), 0.)
+    for nm in ('hip_{}_z', 'hip_{}_y', 'ankle_{}'):
+        s.actuators += [dict(joint=nm.format(k), name=nm.format(k)) for k in (1, 2, 3, 4)]
+    return s
+
+
 BUILTIN = {'point': point, 'ant': ant, 'walker': walker, 'swimmer': swimmer}
+GROUNDWORK = {'doggo': doggo}
 
 
 def robot_spec(robot_base: str) -> Spec:

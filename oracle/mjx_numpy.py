@@ -58,7 +58,7 @@ def quat2mat(q):
 class MjxModel:
     """mjx.put_model: the compiled constants cast to the working dtype."""
 
-    def __init__(self, m: mjcf.Model, dtype=np.float32):
+    def __init__(self, m: mjcf.Model, dtype=np.float32, capsules=None):
         self.m = m
         self.dtype = dtype
         f = lambda a: np.asarray(a, dtype)
@@ -80,18 +80,25 @@ class MjxModel:
         for b in range(1, m.nbody):
             p = m.body_parentid[b]
             self.body_rootid[b] = b if p == 0 else self.body_rootid[p]
-        # contact candidates: (plane geom, sphere geom)
-        self.sphere_plane = []
+        # contact candidates by collision function: (plane, sphere), (plane, capsule), (capsule, capsule)
+        self.sphere_plane, self.capsule_plane, self.capsule_capsule = [], [], []
+        self.ignored_pairs = []
+        # capsule contacts are restated for free-joint robots (Doggo); for the planar robots the
+        # capsule-plane pairs of the swimmer sit exactly at dist == margin and are treated as never
+        # active (assumption A2), as is the Point's box-plane pair
+        with_capsules = bool((m.jnt_type == mjcf.JNT_FREE).any()) if capsules is None else capsules
         for g1, g2 in m.contact_pairs:
-            t1, t2 = m.geom_type[g1], m.geom_type[g2]
+            t1, t2 = int(m.geom_type[g1]), int(m.geom_type[g2])
+            if t2 == mjcf.GEOM_PLANE:
+                g1, g2, t1, t2 = g2, g1, t2, t1
             if t1 == mjcf.GEOM_PLANE and t2 == mjcf.GEOM_SPHERE:
                 self.sphere_plane.append((g1, g2))
-            elif t2 == mjcf.GEOM_PLANE and t1 == mjcf.GEOM_SPHERE:
-                self.sphere_plane.append((g2, g1))
-            # other pairs (point: box-plane, swimmer: capsule-plane) are handled as never
-            # active (assumption A2) and listed in `ignored_pairs`
-        self.ignored_pairs = [p for p in m.contact_pairs
-                              if not ({m.geom_type[p[0]], m.geom_type[p[1]]} == {mjcf.GEOM_PLANE, mjcf.GEOM_SPHERE})]
+            elif with_capsules and t1 == mjcf.GEOM_PLANE and t2 == mjcf.GEOM_CAPSULE:
+                self.capsule_plane.append((g1, g2))
+            elif with_capsules and t1 == mjcf.GEOM_CAPSULE and t2 == mjcf.GEOM_CAPSULE:
+                self.capsule_capsule.append((g1, g2))
+            else:
+                self.ignored_pairs.append((g1, g2))
         self.limited = [j for j in range(m.njnt) if m.jnt_limited[j]]
 
 
@@ -110,6 +117,13 @@ def kinematics(mm: MjxModel, qpos):
         quat = quat_mul(xquat[:, p], np.broadcast_to(mm.body_quat[b], (N, 4)))
         for k in range(m.body_jntnum[b]):
             j = m.body_jntadr[b] + k
+            if m.jnt_type[j] == mjcf.JNT_FREE:     # the pose is the qpos (position + normalised quaternion)
+                a = m.jnt_qposadr[j]
+                pos = qpos[:, a:a + 3].copy()
+                quat = qpos[:, a + 3:a + 7] / np.linalg.norm(qpos[:, a + 3:a + 7], axis=1, keepdims=True)
+                xanchor[:, j] = pos
+                xaxis[:, j] = np.einsum('nij,j->ni', quat2mat(quat), mm.jnt_axis[j])
+                continue
             R = quat2mat(quat)
             xanchor[:, j] = pos + np.einsum('nij,j->ni', R, mm.jnt_pos[j])
             xaxis[:, j] = np.einsum('nij,j->ni', R, mm.jnt_axis[j])
@@ -152,7 +166,14 @@ def com_pos(mm: MjxModel, d):
     for j in range(m.njnt):
         i = m.jnt_dofadr[j]
         b = m.jnt_bodyid[j]
-        if m.jnt_type[j] == mjcf.JNT_SLIDE:
+        if m.jnt_type[j] == mjcf.JNT_FREE:
+            # three translations along the world axes, three rotations about the body axes
+            for a in range(3):
+                cdof[:, i + a, 3 + a] = 1
+                ax = d['xmat'][:, b, :, a]
+                cdof[:, i + 3 + a, :3] = ax
+                cdof[:, i + 3 + a, 3:] = _cross(ax, root_com[:, b] - d['xpos'][:, b])
+        elif m.jnt_type[j] == mjcf.JNT_SLIDE:
             cdof[:, i, 3:] = d['xaxis'][:, j]
         else:
             cdof[:, i, :3] = d['xaxis'][:, j]
@@ -208,7 +229,19 @@ def com_vel(mm: MjxModel, d, qvel):
     cdof_dot = np.zeros((N, m.nv, 6), dt)
     for b in range(1, m.nbody):
         v = cvel[:, m.body_parentid[b]].copy()
-        for k in range(m.body_dofnum[b]):
+        k0 = 0
+        if m.body_jntnum[b] and m.jnt_type[m.body_jntadr[b]] == mjcf.JNT_FREE:
+            # mj_comVel: the translations have cdof_dot = 0; the three rotations all use the velocity
+            # after the translations (not sequentially updated)
+            i0 = m.body_dofadr[b]
+            for a in range(3):
+                v = v + d['cdof'][:, i0 + a] * qvel[:, i0 + a, None]
+            for a in range(3):
+                cdof_dot[:, i0 + 3 + a] = _cross_motion(v, d['cdof'][:, i0 + 3 + a])
+            for a in range(3):
+                v = v + d['cdof'][:, i0 + 3 + a] * qvel[:, i0 + 3 + a, None]
+            k0 = 6
+        for k in range(k0, m.body_dofnum[b]):
             i = m.body_dofadr[b] + k
             cdof_dot[:, i] = _cross_motion(v, d['cdof'][:, i])
             v = v + d['cdof'][:, i] * qvel[:, i, None]
@@ -221,8 +254,8 @@ def passive(mm: MjxModel, qpos, qvel):
     m = mm.m
     f = -mm.dof_damping[None, :] * qvel
     for j in range(m.njnt):
-        if m.jnt_stiffness[j] != 0:
-            f[:, m.jnt_dofadr[j]] -= mm.jnt_stiffness[j] * (qpos[:, m.jnt_qposadr[j]] - mm.qpos_spring[j])
+        if m.jnt_stiffness[j] != 0 and m.jnt_type[j] in (mjcf.JNT_SLIDE, mjcf.JNT_HINGE):
+            f[:, m.jnt_dofadr[j]] -= mm.jnt_stiffness[j] * (qpos[:, m.jnt_qposadr[j]] - mm.qpos_spring[m.jnt_qposadr[j]])
     return f
 
 
@@ -336,35 +369,37 @@ def make_constraint(mm: MjxModel, d, qpos, qvel):
         Js.append(J); Ds.append(np.where(active, 1 / R, 0).astype(dt)); arefs.append(np.where(active, aref, 0).astype(dt))
         meta.append(('limit', j))
     contact_dist = []
-    for (gp, gs) in mm.sphere_plane:
-        bs, bp = m.geom_bodyid[gs], m.geom_bodyid[gp]
-        spos = d['xpos'][:, bs] + np.einsum('nij,j->ni', d['xmat'][:, bs], mm.geom_pos[gs])
-        ppos = d['xpos'][:, bp] + np.einsum('nij,j->ni', d['xmat'][:, bp], mm.geom_pos[gp])
-        pmat = np.einsum('nij,jk->nik', d['xmat'][:, bp], mjcf.quat2mat(m.geom_quat[gp]).astype(dt))
-        n = pmat[:, :, 2]
-        r = mm.geom_size[gs, 0]
-        dist = np.einsum('ni,ni->n', spos - ppos, n) - r
-        cpos = spos - n * (r + dist * dt(0.5))[:, None]
-        margin = max(mm.geom_margin[gp], mm.geom_margin[gs])
-        gap = max(mm.geom_gap[gp], mm.geom_gap[gs])
-        includemargin = margin - gap
-        fri = np.maximum(mm.geom_friction[gp], mm.geom_friction[gs])
-        condim = max(m.geom_condim[gp], m.geom_condim[gs])
-        assert condim == 3, 'only condim 3 (pyramidal, 4 rows per contact) is restated'
-        solref = 0.5 * (m.geom_solref[gp] + m.geom_solref[gs])   # solmix 1:1
-        solimp = 0.5 * (m.geom_solimp[gp] + m.geom_solimp[gs])
-        # frame: normal + two tangents (math.make_frame)
-        a = n
+
+    def geom_pose(g):
+        bd = m.geom_bodyid[g]
+        pos = d['xpos'][:, bd] + np.einsum('nij,j->ni', d['xmat'][:, bd], mm.geom_pos[g])
+        mat = np.einsum('nij,jk->nik', d['xmat'][:, bd], mjcf.quat2mat(m.geom_quat[g]).astype(dt))
+        return pos, mat
+
+    def make_frame(a):
+        """math.make_frame: tangent from the y (or z) axis, orthogonalised against the normal."""
         yref = np.where((np.abs(a[:, 1]) < 0.5)[:, None], np.array([0, 1, 0], dt), np.array([0, 0, 1], dt))
         t1 = yref - a * np.einsum('ni,ni->n', a, yref)[:, None]
         t1 = t1 / np.linalg.norm(t1, axis=1, keepdims=True)
-        t2 = _cross(a, t1)
-        jac = _jac_point(mm, d, bs, cpos) - _jac_point(mm, d, bp, cpos)     # body2 - body1, geom1 = plane
-        jn = np.einsum('ni,niv->nv', a, jac)
+        return t1, _cross(a, t1)
+
+    def add_contact(g1, g2, dist, cpos, nrm, t1, t2):
+        """pyramidal rows (condim 3: 4 per contact) of one contact between geoms g1 and g2."""
+        b1, b2 = m.geom_bodyid[g1], m.geom_bodyid[g2]
+        margin = max(mm.geom_margin[g1], mm.geom_margin[g2])
+        gap = max(mm.geom_gap[g1], mm.geom_gap[g2])
+        includemargin = margin - gap
+        fri = np.maximum(mm.geom_friction[g1], mm.geom_friction[g2])
+        condim = max(m.geom_condim[g1], m.geom_condim[g2])
+        assert condim == 3, 'only condim 3 (pyramidal, 4 rows per contact) is restated'
+        solref = 0.5 * (m.geom_solref[g1] + m.geom_solref[g2])   # solmix 1:1
+        solimp = 0.5 * (m.geom_solimp[g1] + m.geom_solimp[g2])
+        jac = _jac_point(mm, d, b2, cpos) - _jac_point(mm, d, b1, cpos)     # body2 - body1
+        jn = np.einsum('ni,niv->nv', nrm, jac)
         jt = [np.einsum('ni,niv->nv', t1, jac), np.einsum('ni,niv->nv', t2, jac)]
         pos = dist - includemargin
         active = pos < 0
-        invweight = mm.body_invweight0[bp, 0] + mm.body_invweight0[bs, 0]
+        invweight = mm.body_invweight0[b1, 0] + mm.body_invweight0[b2, 0]
         invweight = invweight + fri[0] * fri[0] * invweight
         invweight = invweight * 2 * fri[0] * fri[0] / mm.impratio
         k, b, imp = _kbi(mm, solref, solimp, pos)
@@ -375,11 +410,86 @@ def make_constraint(mm: MjxModel, d, qpos, qvel):
                 aref = -b * np.einsum('nv,nv->n', J, qvel) - k * imp * pos
                 Js.append(J.astype(dt)); Ds.append(np.where(active, 1 / R, 0).astype(dt))
                 arefs.append(np.where(active, aref, 0).astype(dt))
-                meta.append(('contact', gs))
+                meta.append(('contact', g2))
         contact_dist.append(dist)
+
+    def plane_sphere(n, ppos, spos, r):
+        dist = np.einsum('ni,ni->n', spos - ppos, n) - r
+        return dist, spos - n * (r + dist * dt(0.5))[:, None]
+
+    for (gp, gs) in mm.sphere_plane:                     # collision_primitive.plane_sphere
+        ppos, pmat = geom_pose(gp)
+        spos, _ = geom_pose(gs)
+        n = pmat[:, :, 2]
+        dist, cpos = plane_sphere(n, ppos, spos, mm.geom_size[gs, 0])
+        t1, t2 = make_frame(n)
+        add_contact(gp, gs, dist, cpos, n, t1, t2)
+    for (gp, gc) in mm.capsule_plane:                    # collision_primitive.plane_capsule: one contact per end
+        ppos, pmat = geom_pose(gp)
+        cpos_, cmat = geom_pose(gc)
+        n, axis = pmat[:, :, 2], cmat[:, :, 2]
+        bvec = axis - n * np.einsum('ni,ni->n', n, axis)[:, None]
+        bn = np.linalg.norm(bvec, axis=1)
+        with np.errstate(all='ignore'):
+            bdir = bvec / bn[:, None]
+        alt = np.where(((-0.5 < n[:, 1]) & (n[:, 1] < 0.5))[:, None], np.array([0, 1, 0], dt), np.array([0, 0, 1], dt))
+        bdir = np.where((bn < 0.5)[:, None], alt, bdir).astype(dt)
+        t2 = _cross(n, bdir)
+        seg = axis * mm.geom_size[gc, 1]
+        for off in (seg, -seg):
+            dist, cp = plane_sphere(n, ppos, cpos_ + off, mm.geom_size[gc, 0])
+            add_contact(gp, gc, dist, cp, n, bdir, t2)
+    for (g1, g2) in mm.capsule_capsule:                  # collision_primitive.capsule_capsule
+        p1, m1 = geom_pose(g1)
+        p2, m2 = geom_pose(g2)
+        a1, a2 = m1[:, :, 2] * mm.geom_size[g1, 1], m2[:, :, 2] * mm.geom_size[g2, 1]
+        pt1, pt2 = closest_segment_to_segment_points(p1 - a1, p1 + a1, p2 - a2, p2 + a2)
+        dvec = pt2 - pt1
+        dn = np.linalg.norm(dvec, axis=1)
+        with np.errstate(all='ignore'):
+            n = np.where((dn == 0)[:, None], np.array([1, 0, 0], dt), dvec / dn[:, None]).astype(dt)
+        r1, r2 = mm.geom_size[g1, 0], mm.geom_size[g2, 0]
+        dist = dn - (r1 + r2)
+        cp = pt1 + n * (r1 + dist * dt(0.5))[:, None]
+        t1, t2 = make_frame(n)
+        add_contact(g1, g2, dist, cp, n, t1, t2)
     if not Js:
         return np.zeros((N, 0, m.nv), dt), np.zeros((N, 0), dt), np.zeros((N, 0), dt), meta, contact_dist
     return np.stack(Js, 1), np.stack(Ds, 1), np.stack(arefs, 1), meta, contact_dist
+
+
+def closest_segment_point(a, b, pt):
+    ab = b - a
+    t = np.einsum('ni,ni->n', pt - a, ab) / (np.einsum('ni,ni->n', ab, ab) + 1e-6)
+    return a + np.clip(t, 0.0, 1.0)[:, None] * ab
+
+
+def closest_segment_to_segment_points(a0, a1, b0, b1):
+    """math.closest_segment_to_segment_points: closest points of the two infinite lines, clipped to
+    the segments, then each clipped point re-projected onto the other segment."""
+    da, db = a1 - a0, b1 - b0
+    la, lb = np.linalg.norm(da, axis=1), np.linalg.norm(db, axis=1)
+    dir_a, dir_b = da / la[:, None], db / lb[:, None]
+    ha, hb = la * 0.5, lb * 0.5
+    a_mid, b_mid = a0 + dir_a * ha[:, None], b0 + dir_b * hb[:, None]
+    trans = a_mid - b_mid
+    d_a = np.einsum('ni,ni->n', dir_a, trans)
+    d_b = np.einsum('ni,ni->n', dir_b, trans)
+    dd = np.einsum('ni,ni->n', dir_a, dir_b)
+    denom = 1 - dd * dd
+    t_a = (-d_a + d_b * dd) / (denom + 1e-6)
+    t_b = (d_b + t_a * dd)
+    t_a = np.clip(t_a, -ha, ha)
+    t_b = np.clip(t_b, -hb, hb)
+    best_a = a_mid + dir_a * t_a[:, None]
+    best_b = b_mid + dir_b * t_b[:, None]
+    new_a = closest_segment_point(a0, a1, best_b)
+    new_b = closest_segment_point(b0, b1, best_a)
+    d1 = np.sum((new_a - best_b) ** 2, 1)
+    d2 = np.sum((new_b - best_a) ** 2, 1)
+    best_a2 = np.where((d1 < d2)[:, None], new_a, best_a)
+    best_b2 = np.where((d1 < d2)[:, None], best_b, new_b)
+    return best_a2.astype(a0.dtype), best_b2.astype(a0.dtype)
 
 
 # ----------------------------------------------------------------- solver
@@ -528,6 +638,30 @@ def step(mm: MjxModel, qpos, qvel, ctrl, warm):
     Mh[:, idx, idx] += mm.timestep * mm.dof_damping
     qacc = _chol_solve(Mh, d['qfrc_smooth'] + d['qfrc_constraint'])
     qvel2 = qvel + mm.timestep * qacc
-    qpos2 = qpos + mm.timestep * qvel2
+    qpos2 = integrate_pos(mm, qpos, qvel2)
     d['qacc_euler'] = qacc
     return qpos2.astype(dt), qvel2.astype(dt), d
+
+
+def integrate_pos(mm: MjxModel, qpos, qvel):
+    """mj_integratePos: hinge / slide q += dt v; free joint: position += dt v_lin, quaternion rotated by
+    the body-frame angular velocity over dt (math.quat_integrate) and renormalised."""
+    m, dt = mm.m, mm.dtype
+    if m.nq == m.nv:
+        return qpos + mm.timestep * qvel
+    out = qpos.copy()
+    for j in range(m.njnt):
+        a, i = m.jnt_qposadr[j], m.jnt_dofadr[j]
+        if m.jnt_type[j] == mjcf.JNT_FREE:
+            out[:, a:a + 3] = qpos[:, a:a + 3] + mm.timestep * qvel[:, i:i + 3]
+            w = qvel[:, i + 3:i + 6]
+            wn = np.linalg.norm(w, axis=1)
+            ang = wn * mm.timestep
+            with np.errstate(all='ignore'):
+                axis = np.where((wn > 0)[:, None], w / wn[:, None], np.array([1, 0, 0], dt))
+            ql = np.concatenate([np.cos(ang * 0.5)[:, None], axis * np.sin(ang * 0.5)[:, None]], 1)
+            q = quat_mul(qpos[:, a + 3:a + 7], ql)
+            out[:, a + 3:a + 7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+        else:
+            out[:, a] = qpos[:, a] + mm.timestep * qvel[:, i]
+    return out

@@ -295,9 +295,103 @@ def test_mjcf_parser_rules_and_rejections():
         with pytest.raises(exc):
             mjcf.parse_mjcf(bad)
     free = mjcf.parse_mjcf('<mujoco><worldbody><body name="robot"><freejoint name="robot"/><geom size=".1"/></body></worldbody></mujoco>')
-    with pytest.raises(NotImplementedError):
-        mjcf.compile_spec(free)
+    fm = mjcf.compile_spec(free)                          # free joints compile (groundwork for Doggo) ...
+    assert fm.nq == 7 and fm.nv == 6 and fm.qpos0.tolist() == [0, 0, 0, 1, 0, 0, 0]
+    with pytest.raises(AssertionError, match="planar root"):
+        art_model.lower_art(fm)                           # ... but the kernels of this round refuse them
     # topology the kernels do not cover is refused by the lowering, not silently mis-simulated
     tree = mjcf.parse_mjcf(xml.replace('range="-90 90"', '').replace('<body name="tip" pos="0 0.4 0">', '<body name="side" pos="0.1 0 0"><joint name="s" axis="0 0 1"/><geom size=".02"/><body name="a"><joint name="a1"/><geom size=".02"/></body><body name="b"><joint name="b1"/><geom size=".02"/></body></body><body name="tip" pos="0 0.4 0">'))
     with pytest.raises(AssertionError, match="serial chains"):
         art_model.lower_art(mjcf.compile_spec(tree))
+
+
+# ---------------------------------------------------------------------------
+# Free-joint root and capsule contacts (Doggo groundwork: compiled and restated in the oracle;
+# the CUDA kernels for it are the next row of SURVEY 8f-2)
+# ---------------------------------------------------------------------------
+def test_doggo_description_equals_golden_reference_compile(gold):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_golden_mjcf import constants
+    m = mjcf.compile_spec(mjcf.add_world_geoms(robots.doggo(), 0.5, 0.3, 8))
+    got = constants(m)
+    for k, v in gold['doggo'].items():
+        if isinstance(v, list) and v and not isinstance(v[0], str) and v[0] is not None:
+            np.testing.assert_allclose(np.asarray(got[k], float), np.asarray(v, float), rtol=1e-12, atol=1e-15, err_msg=k)
+    assert (m.nq, m.nv, m.nu) == (38, 37, 12) and m.qpos0[:7].tolist() == [0, 0, 0.3, 1, 0, 0, 0]
+    # <freejoint> ignores the defaults class (stiffness 0.01 / limited); the goal / hazard slides inherit it
+    assert m.jnt_stiffness[0] == 0 and m.jnt_limited[0] == 0
+    assert m.jnt_stiffness[m.jnt_id('goal_x')] == 0.01 and m.jnt_stiffness[m.jnt_id('hip_1_y')] == 0.01
+    assert m.qpos_spring[m.jnt_qposadr[m.jnt_id('ankle_3')]] == pytest.approx(math.radians(-20))
+    # weld-id filters: 14 capsules x floor + 60 capsule pairs (same welded body and weld parent-child excluded)
+    assert len(m.contact_pairs) == 74 and sum(1 for a, b in m.contact_pairs if a == 0) == 14
+
+
+def _free_body(geom, pos=(0., 0., 1.0)):
+    s = mjcf.Spec()
+    s.opt = dict(mjcf.OPT_DEFAULT, timestep=0.001)
+    s.angle = 'radian'
+    s.bodies.append(dict(name='world', parent=-1, pos=(0., 0., 0.), quat=(1., 0., 0., 0.), joints=[],
+                         geoms=[dict(name='floor', type='plane', size=(5., 5., .1))]))
+    s.bodies.append(dict(name='robot', parent=0, pos=pos, quat=(1., 0., 0., 0.), joints=[dict(type='free', name='robot')], geoms=[geom]))
+    return mjcf.compile_spec(s)
+
+
+def test_free_body_falls_and_tumbles_like_a_rigid_body():
+    m = _free_body(dict(type='box', size=(0.05, 0.1, 0.2), density=700.0))
+    mm = mx.MjxModel(m, np.float64, capsules=False)
+    mass, I = m.body_mass[1], np.diag(m.body_inertia_full[1])
+    q = m.qpos0[None].copy(); v = np.zeros((1, 6))
+    v[0, 3:] = [3.0, 0.2, -0.1]          # spin mostly about the LONGEST principal axis... of a box: unstable middle axis is y
+    v[0, :3] = [0.5, 0.0, 2.0]
+    d = mx.forward(mm, q, v, np.zeros((1, 0)), np.zeros((1, 6)))
+    np.testing.assert_allclose(d['qM'][0], np.diag([mass] * 3 + list(I)), atol=1e-14)
+    # linear: gravity only; angular (body frame): Euler's equations  I w' = -(w x I w)
+    w = v[0, 3:]
+    np.testing.assert_allclose(d['qacc'][0, :3], [0, 0, -9.81], atol=1e-10)
+    np.testing.assert_allclose(d['qacc'][0, 3:], -np.cross(w, I * w) / I, rtol=1e-10, atol=1e-12)
+    L0 = mjcf.quat2mat(q[0, 3:7]) @ (I * w)
+    e0 = 0.5 * np.sum(I * w * w)
+    for _ in range(1500):
+        q, v, _ = mx.step(mm, q, v, np.zeros((1, 0)), np.zeros((1, 6)))
+    w = v[0, 3:]
+    L1 = mjcf.quat2mat(q[0, 3:7]) @ (I * w)
+    assert np.linalg.norm(q[0, 3:7]) == pytest.approx(1.0, abs=1e-12)
+    np.testing.assert_allclose(L1, L0, rtol=2e-3, atol=2e-5)            # angular momentum in the world frame
+    assert 0.5 * np.sum(I * w * w) == pytest.approx(e0, rel=5e-3)       # rotational energy
+    assert v[0, 2] == pytest.approx(2.0 - 9.81 * 1.5, rel=1e-9) and q[0, 0] == pytest.approx(0.5 * 1.5, rel=1e-9)
+
+
+def test_capsule_resting_on_the_floor_carries_its_weight():
+    m = _free_body(dict(type='capsule', fromto=(-0.1, 0., 0., 0.1, 0., 0.), size=(0.04,), density=900.0), pos=(0., 0., 0.041))
+    mm = mx.MjxModel(m, np.float64)
+    assert len(mm.capsule_plane) == 1
+    q = m.qpos0[None].copy(); v = np.zeros((1, 6)); warm = np.zeros((1, 6))
+    for _ in range(600):
+        q, v, d = mx.step(mm, q, v, np.zeros((1, 0)), warm)
+        warm = d['qacc']
+    assert np.abs(v).max() < 1e-4 and np.abs(d['qacc']).max() < 1e-3          # at rest
+    assert -0.002 < q[0, 2] - 0.04 < 0                                           # a fraction of a mm of soft penetration
+    # two contacts (the capsule's ends) x 4 pyramid edges; every edge force pushes along n +- mu t, so the normal
+    # components add up to the weight
+    assert d['efc_force'].shape[1] == 8 and (d['efc_force'] > 0).all()
+    assert d['efc_force'].sum() == pytest.approx(m.body_mass[1] * 9.81, rel=2e-3)
+    np.testing.assert_allclose(d['qfrc_constraint'][0, 2], m.body_mass[1] * 9.81, rtol=2e-3)
+
+
+def test_capsule_capsule_closest_points_against_brute_force():
+    rng = np.random.default_rng(0)
+    n = 200
+    a0, a1, b0, b1 = (rng.uniform(-1, 1, (n, 3)) for _ in range(4))
+    pa, pb = mx.closest_segment_to_segment_points(a0, a1, b0, b1)
+    t = np.linspace(0, 1, 201)
+    A = a0[:, None, :] + t[None, :, None] * (a1 - a0)[:, None, :]
+    B = b0[:, None, :] + t[None, :, None] * (b1 - b0)[:, None, :]
+    brute = np.sqrt(((A[:, :, None, :] - B[:, None, :, :]) ** 2).sum(-1)).reshape(n, -1).min(1)
+    got = np.linalg.norm(pa - pb, axis=1)
+    assert (got <= brute + 1e-9).all() and (got >= brute - 0.02).all()          # never worse than the sampled optimum
+    # the returned points lie on their segments
+    for p, s0, s1 in ((pa, a0, a1), (pb, b0, b1)):
+        u = np.einsum('ni,ni->n', p - s0, s1 - s0) / np.einsum('ni,ni->n', s1 - s0, s1 - s0)
+        assert (u > -1e-9).all() and (u < 1 + 1e-9).all()
+        assert np.linalg.norm(np.cross(p - s0, s1 - s0), axis=1).max() < 1e-9

@@ -21,7 +21,7 @@ FIELDS = ("body_parentid body_pos body_quat body_ipos body_mass body_inertia_ful
           "jnt_pos jnt_axis jnt_limited jnt_range jnt_stiffness qpos_spring dof_damping dof_armature dof_invweight0 "
           "geom_type geom_bodyid geom_pos geom_quat geom_size geom_friction geom_margin geom_contype geom_conaffinity "
           "actuator_trnid actuator_gear actuator_ctrllimited actuator_ctrlrange actuator_forcelimited actuator_forcerange "
-          "actuator_gainprm0 actuator_biasprm").split()
+          "actuator_gainprm0 actuator_biasprm qpos0 body_weldid").split()
 
 
 def constants(m):
@@ -33,7 +33,7 @@ def constants(m):
 
 if __name__ == "__main__":
     gold = {}
-    for f, key in robots.ROBOT_FILES.items():
+    for f, key in {**robots.ROBOT_FILES, **robots.GROUNDWORK_FILES}.items():
         spec = mjcf.parse_mjcf(open(os.path.join(REF, f)).read())
         gold[key] = constants(mjcf.compile_spec(mjcf.add_world_geoms(spec, 0.5, 0.3, 8)))
     with open(os.path.join(ROOT, "tests", "golden", "mjcf_constants.json"), "w") as fh:
