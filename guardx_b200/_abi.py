@@ -9,12 +9,12 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-GX_ABI_VERSION = 2
+GX_ABI_VERSION = 3
 GX_MAX_HAZARDS = 32
 GX_MAX_LIDAR_BINS = 64
 
 GX_OK, GX_EINVAL, GX_ECUDA, GX_ENOMEM, GX_ESTATE = 0, -1, -2, -3, -4
-GX_ROBOT_POINT, GX_ROBOT_ART = 0, 1
+GX_ROBOT_POINT, GX_ROBOT_ART, GX_ROBOT_TREE = 0, 1, 2
 
 GX_OBS_ACC = 1 << 0
 GX_OBS_CTRL = 1 << 1
@@ -87,6 +87,7 @@ class GxConfig(C.Structure):
         ("obs_mask", C.c_uint32),
         ("art_nu", C.c_int32),
         ("art_nv", C.c_int32),
+        ("art_nq", C.c_int32),
         ("point", GxPointModel),
     ]
 
@@ -103,6 +104,7 @@ PROTOTYPES = {
     "gx_default_config": (None, [_CFGP]),
     "gx_create": (_I, [_CFGP, _I, C.POINTER(_P)]),
     "gx_create_art": (_I, [_CFGP, _P, _I, C.POINTER(_P)]),
+    "gx_create_tree": (_I, [_CFGP, _P, _I, C.POINTER(_P)]),
     "gx_destroy": (_I, [_P]),
     "gx_obs_dim": (_I, [_P]),
     "gx_act_dim": (_I, [_P]),

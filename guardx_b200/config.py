@@ -93,8 +93,10 @@ DEFAULT = {
 
 # robots this build has dynamics for -> GX_ROBOT_*
 _ROBOTS = {'xmls/point.xml': _abi.GX_ROBOT_POINT, 'xmls/ant.xml': _abi.GX_ROBOT_ART,
-           'xmls/walker.xml': _abi.GX_ROBOT_ART, 'xmls/swimmer.xml': _abi.GX_ROBOT_ART}
-_TASK_ROBOT = {'Point': 'xmls/point.xml', 'Ant': 'xmls/ant.xml', 'Walker': 'xmls/walker.xml', 'Swimmer': 'xmls/swimmer.xml'}
+           'xmls/walker.xml': _abi.GX_ROBOT_ART, 'xmls/swimmer.xml': _abi.GX_ROBOT_ART,
+           'xmls/doggo.xml': _abi.GX_ROBOT_TREE}
+_TASK_ROBOT = {'Point': 'xmls/point.xml', 'Ant': 'xmls/ant.xml', 'Walker': 'xmls/walker.xml', 'Swimmer': 'xmls/swimmer.xml',
+               'Doggo': 'xmls/doggo.xml'}
 
 
 def parse(config: dict) -> dict:
@@ -126,15 +128,14 @@ def configuration(task: str) -> dict:
             'hazards_size': 0.3,
         }
     raise NotImplementedError(
-        f"task {task!r}: built so far are Goal_{{Point,Swimmer,Ant,Walker}}_8Hazards "
-        "(Doggo needs a free-joint root; the Push/Chase/Defense/Ghost entries are rejected by "
-        "the reference Engine itself, engine.py:326-328)")
+        f"task {task!r}: built are Goal_{{Point,Swimmer,Ant,Walker,Doggo}}_8Hazards "
+        "(the Push/Chase/Defense/Ghost entries are rejected by the reference Engine itself, engine.py:326-328)")
 
 
 def compiled_model(cfg: dict):
     """The MuJoCo model World.build() would emit for this config (world.py:104-333), compiled
     by guardx_b200.mjcf -- None for the Point, whose constants are closed-form (point_model)."""
-    if _ROBOTS.get(cfg['robot_base']) != _abi.GX_ROBOT_ART:
+    if _ROBOTS.get(cfg['robot_base']) not in (_abi.GX_ROBOT_ART, _abi.GX_ROBOT_TREE):
         return None
     from . import mjcf, robots
     spec = mjcf.add_world_geoms(robots.robot_spec(cfg['robot_base']), cfg['goal_size'], cfg['hazards_size'],
@@ -216,12 +217,12 @@ def lower(cfg: dict, env_id_offset: int = 0, pool_size: int = 0, model=None) -> 
     c.lidar_exp_gain = float(cfg['lidar_exp_gain'])
     c.goal_min_robot_dist = 3.0  # engine.py:571
     c.opt_timestep = 0.02  # point.xml:3 (mj_model.opt.timestep is a double)
-    if c.robot == _abi.GX_ROBOT_ART:
+    if c.robot in (_abi.GX_ROBOT_ART, _abi.GX_ROBOT_TREE):
         if model is None:
             model = compiled_model(cfg)
-        nv_robot = int(model.nv) - 2 - 2 * int(cfg['hazards_num'])
+        nworld = 2 + 2 * int(cfg['hazards_num'])
         c.opt_timestep = float(model.opt['timestep'])
-        c.art_nu, c.art_nv = int(model.nu), nv_robot
+        c.art_nu, c.art_nv, c.art_nq = int(model.nu), int(model.nv) - nworld, int(model.nq) - nworld
     c.hazards_num = int(cfg['hazards_num'])
     c.lidar_num_bins = int(cfg['lidar_num_bins'])
     c.lidar_alias = 1 if cfg['lidar_alias'] else 0

@@ -16,6 +16,7 @@
 #include "gx_lanes.cuh"
 #include "gx_art.cuh"
 #include "gx_art_launch.h"
+#include "gx_tree_launch.h"
 
 #define GX_API extern "C" __attribute__((visibility("default")))
 
@@ -90,6 +91,9 @@ struct gx_env {
   GxArtModel* art_host;
   GxArtDev art;
   int art_shape;  // 1 ant-like (4 legs x 2 dofs), 2 walker-like (2 x 5), 3 swimmer-like (1 x 2)
+  // general-tree robots (GX_ROBOT_TREE): host + device copy of the model, state, scratch
+  GxTreeModel* tree_host;
+  GxTreeDev tree;
   // gx_rollout_host pipeline: two chunk buffers, a compute and a copy stream
   float* ring[2];
   int ring_steps;
@@ -668,11 +672,17 @@ static int gx_art_shape_of(const GxArtModel* m) {
   return 0;
 }
 
-static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int device, gx_env** out) {
+static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int device, gx_env** out,
+                          const GxTreeModel* h_tree = nullptr) {
   if (!out) return gx_fail(GX_EINVAL, "gx_create: out is NULL");
   *out = nullptr;
   if (h_cfg && (h_cfg->robot == GX_ROBOT_ART) != (h_model != nullptr))
     return gx_fail(GX_EINVAL, "gx_create: GX_ROBOT_ART needs gx_create_art with a model (and only it)");
+  if (h_cfg && (h_cfg->robot == GX_ROBOT_TREE) != (h_tree != nullptr))
+    return gx_fail(GX_EINVAL, "gx_create: GX_ROBOT_TREE needs gx_create_tree with a model (and only it)");
+  if (h_tree && (h_cfg->art_nv != h_tree->nv || h_cfg->art_nu != h_tree->nu || h_cfg->art_nq != h_tree->nq ||
+                 h_tree->nworld != 2 + 2 * h_cfg->hazards_num || h_tree->nv > GX_TREE_MAXV || h_tree->npair > GX_TREE_MAXPAIR))
+    return gx_fail(GX_EINVAL, "gx_create_tree: model and config disagree (nq / nv / nu / hazards) or exceed the build limits");
   if (h_model) {
     int nvr = 3;
     if (h_model->nleg < 1 || h_model->nleg > GX_ART_MAXLEG) return gx_fail(GX_EINVAL, "gx_create_art: nleg out of range");
@@ -701,6 +711,7 @@ static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int
   e->sm_count = prop.multiProcessorCount;
   e->ctr = nullptr; e->have_reset = false; e->stats_on = false; e->stats_age0 = 0;
   e->stage = nullptr;
+  e->tree_host = nullptr; e->tree.m = nullptr; e->tree.tq = nullptr; e->tree.tw = nullptr; e->tree.scratch = nullptr;
   e->art_host = nullptr; e->art.m = nullptr; e->art.aq = nullptr; e->art.nv = 0; e->art.nu = 0; e->art_shape = 0;
   e->lanes_max_envs = 12288;  // measured crossover with the one-thread kernel: 8192 -> 5.7 vs 8.8 us, 16384 -> 9.7 vs 9.1 us
   if (const char* v = getenv("GX_LANES_MAX_ENVS")) e->lanes_max_envs = atoi(v);
@@ -743,6 +754,17 @@ static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int
     e->art.m = dm;
     GX_ALLOC(e->art.aq, sizeof(float) * 3 * (size_t)h_model->nv * cap);
   }
+  if (h_tree) {
+    e->tree_host = new (std::nothrow) GxTreeModel(*h_tree);
+    e->tree.nq = h_tree->nq; e->tree.nv = h_tree->nv; e->tree.nu = h_tree->nu;
+    GxTreeModel* dm = nullptr;
+    GX_ALLOC(dm, sizeof(GxTreeModel));
+    cudaMemcpy(dm, h_tree, sizeof(GxTreeModel), cudaMemcpyHostToDevice);
+    e->tree.m = dm;
+    GX_ALLOC(e->tree.tq, sizeof(float) * 2 * (size_t)(h_tree->nq + 2 * h_tree->nv) * cap);
+    GX_ALLOC(e->tree.tw, sizeof(float) * (size_t)h_tree->nworld * cap);
+    GX_ALLOC(e->tree.scratch, sizeof(float) * (size_t)gx_tree_scratch_floats() * cap);
+  }
 #undef GX_ALLOC
   // never-forwarded mjx.Data carries the identity xmat that put_data copied in
   {
@@ -762,6 +784,11 @@ GX_API int gx_create_art(const gx_config* h_cfg, const GxArtModel* h_model, int 
   return gx_create_impl(h_cfg, h_model, device, out);
 }
 
+GX_API int gx_create_tree(const gx_config* h_cfg, const GxTreeModel* h_model, int device, gx_env** out) {
+  if (!h_model) return gx_fail(GX_EINVAL, "gx_create_tree: model is NULL");
+  return gx_create_impl(h_cfg, nullptr, device, out, h_model);
+}
+
 GX_API int gx_destroy(gx_env* e) {
   if (!e) return GX_OK;
   DeviceGuard guard(e->device);
@@ -769,6 +796,7 @@ GX_API int gx_destroy(gx_env* e) {
   cudaFree(e->s.hz); cudaFree(e->s.ep); cudaFree(e->s.fin); cudaFree(e->s.hx); cudaFree(e->s.hf);
   cudaFree(e->pool); cudaFree(e->pool_tries); cudaFree(e->stats); cudaFree(e->stage); cudaFree(e->ctr);
   cudaFree((void*)e->art.m); cudaFree(e->art.aq); delete e->art_host;
+  cudaFree((void*)e->tree.m); cudaFree(e->tree.tq); cudaFree(e->tree.tw); cudaFree(e->tree.scratch); delete e->tree_host;
   if (e->ring_steps) {
     cudaFree(e->ring[0]); cudaFree(e->ring[1]);
     cudaStreamDestroy(e->rs_compute); cudaStreamDestroy(e->rs_copy);
@@ -780,7 +808,7 @@ GX_API int gx_destroy(gx_env* e) {
 }
 
 GX_API int gx_obs_dim(const gx_env* e) { return e ? e->p.obs_dim : GX_EINVAL; }
-GX_API int gx_act_dim(const gx_env* e) { return e ? (e->art_host ? e->art.nu : 2) : GX_EINVAL; }
+GX_API int gx_act_dim(const gx_env* e) { return e ? (e->art_host ? e->art.nu : (e->tree_host ? e->tree.nu : 2)) : GX_EINVAL; }
 GX_API int gx_env_num(const gx_env* e) { return e ? e->p.n : GX_EINVAL; }
 GX_API int gx_pool_size(const gx_env* e) { return e ? e->p.pool_size : GX_EINVAL; }
 GX_API int gx_aux_dim(const gx_env* e) { return e ? e->p.aux_dim : GX_EINVAL; }
@@ -804,6 +832,15 @@ GX_API int gx_obs_offset(const gx_env* e, uint32_t component) {
 // engine.py:291-297: ctrlrange of the first two actuators, +-inf if not limited
 GX_API int gx_action_bounds(const gx_env* e, float* h_low, float* h_high) {
   if (!e || !h_low || !h_high) return gx_fail(GX_EINVAL, "gx_action_bounds: NULL argument");
+  if (e->tree_host) {
+    for (int i = 0; i < e->tree_host->nv; ++i) {
+      const GxTreeDof& d = e->tree_host->dof[i];
+      if (d.act < 0) continue;
+      h_low[d.act] = d.ctrllimited ? d.ctrl_lo : -INFINITY;
+      h_high[d.act] = d.ctrllimited ? d.ctrl_hi : INFINITY;
+    }
+    return GX_OK;
+  }
   if (e->art_host) {
     const GxArtModel* m = e->art_host;
     auto put = [&](const GxArtDof& d) {
@@ -842,6 +879,15 @@ static int gx_generate_pool(gx_env* e, cudaStream_t st) {
 template <int MODE, bool AR>
 static int gx_art_launch(gx_env* e, cudaStream_t st, const float* layout, const float* action, const float* obs_in,
                          float* obs, float* act_out, float* reward, float* done, float* cost, float* qacc, int32_t* aux = nullptr) {
+  if (e->tree_host) {
+    GxTreeLaunch t;
+    t.p = &e->p; t.s = &e->s; t.t = &e->tree; t.pool = e->pool; t.layout = layout; t.action = action; t.obs_in = obs_in;
+    t.obs = obs; t.act_out = act_out; t.reward = reward; t.done = done; t.cost = cost; t.qacc = qacc; t.aux = aux;
+    t.stats_on = e->stats_on ? 1 : 0; t.mode = MODE; t.autoreset = AR ? 1 : 0; t.stream = st;
+    const cudaError_t err = gx_tree_launch(t);
+    if (err != cudaSuccess) return gx_fail(GX_ECUDA, "gx_tree_kernel launch failed: %s", cudaGetErrorString(err));
+    return GX_OK;
+  }
   GxArtLaunch a;
   a.p = &e->p; a.s = &e->s; a.art = &e->art; a.pool = e->pool; a.layout = layout; a.action = action; a.obs_in = obs_in;
   a.obs = obs; a.act_out = act_out; a.reward = reward; a.done = done; a.cost = cost; a.qacc = qacc; a.aux = aux;
@@ -864,7 +910,7 @@ static int gx_art_step(gx_env* e, cudaStream_t st, const float* action, float* o
 }
 
 static int gx_reset_impl(gx_env* e, const float* layout, float* obs, cudaStream_t st) {
-  if (e->art_host) {
+  if (e->art_host || e->tree_host) {
     if (int rc = gx_art_launch<GX_ART_RESET, false>(e, st, layout, nullptr, nullptr, obs, nullptr, nullptr, nullptr, nullptr, nullptr)) return rc;
     e->have_reset = true;
     return GX_OK;
@@ -915,7 +961,7 @@ static int gx_step_impl(gx_env* e, const float* action, float* obs, float* rewar
   if (reinterpret_cast<uintptr_t>(action) & 7u) return gx_fail(GX_EINVAL, "%s: action must be 8-byte aligned", who);
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (e->art_host) {
+  if (e->art_host || e->tree_host) {
     return gx_art_step(e, st, action, obs, nullptr, reward, done, cost, qacc, autoreset, aux);
   }
   // tile_stores: the caller wants the observation rows to leave as coalesced 128-bit stores
@@ -953,7 +999,7 @@ GX_API int gx_reset_done(gx_env* e, const float* obs_in, float* obs_out, const f
   if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_reset_done: call gx_reset first");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (e->art_host)
+  if (e->art_host || e->tree_host)
     return gx_art_launch<GX_ART_RESET_DONE, false>(e, st, layout, nullptr, obs_in, obs_out, nullptr, nullptr, nullptr, nullptr, nullptr);
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
@@ -968,7 +1014,8 @@ GX_API int gx_reset_done(gx_env* e, const float* obs_in, float* obs_out, const f
 GX_API int gx_get_state(gx_env* e, float* state, void* stream) {
   if (!e || !state) return gx_fail(GX_EINVAL, "gx_get_state: NULL argument");
   DeviceGuard guard(e->device);
-  if (e->art_host) gx_art_get_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, e->art, state);
+  if (e->tree_host) gx_tree_get_state(e->p, e->s, e->tree, state, (cudaStream_t)stream);
+  else if (e->art_host) gx_art_get_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, e->art, state);
   else gx_get_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
   GX_LAUNCH_CHECK("gx_get_state_kernel");
   return GX_OK;
@@ -977,7 +1024,8 @@ GX_API int gx_get_state(gx_env* e, float* state, void* stream) {
 GX_API int gx_set_state(gx_env* e, const float* state, void* stream) {
   if (!e || !state) return gx_fail(GX_EINVAL, "gx_set_state: NULL argument");
   DeviceGuard guard(e->device);
-  if (e->art_host) gx_art_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, e->art, state);
+  if (e->tree_host) gx_tree_set_state(e->p, e->s, e->tree, state, (cudaStream_t)stream);
+  else if (e->art_host) gx_art_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, e->art, state);
   else gx_set_state_kernel<<<div_up(e->p.n, 128), 128, 0, (cudaStream_t)stream>>>(e->p, e->s, state);
   GX_LAUNCH_CHECK("gx_set_state_kernel");
   e->have_reset = true;
@@ -1038,13 +1086,13 @@ GX_API int gx_rollout(gx_env* e, int32_t T, float* obs, float* act, float* rewar
   if (T == 0) return GX_OK;
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (e->art_host) {
+  if (e->art_host || e->tree_host) {
     // one fused step + auto-reset launch per control step, actions drawn in-kernel (the
     // per-step work of a legged robot dwarfs the launch, unlike the Point's)
     if (!obs || !reward || !cost || !done) return gx_fail(GX_EINVAL, "gx_rollout: articulated robots need obs, reward, cost and done buffers");
     const size_t n = (size_t)e->p.n;
     for (int t = 0; t < T; ++t)
-      if (int rc = gx_art_step(e, st, nullptr, obs + (size_t)t * n * e->p.obs_dim, act ? act + (size_t)t * n * e->art.nu : nullptr,
+      if (int rc = gx_art_step(e, st, nullptr, obs + (size_t)t * n * e->p.obs_dim, act ? act + (size_t)t * n * gx_act_dim(e) : nullptr,
                                reward + t * n, done + t * n, cost + t * n, nullptr, true))
         return rc;
     return GX_OK;

@@ -109,14 +109,6 @@ __device__ __forceinline__ GxArtObs gx_art_obs_row(const gx_params& p, const GxS
   return o;
 }
 
-// a_t ~ U(-1,1) for actuator a of env g at step `age` (the synthetic rollouts of
-// BASELINE.json; same stream as the Point kernels: word 3 = GX_STREAM_ACTION + block)
-__device__ __forceinline__ float gx_art_synth_action(const gx_params& p, uint64_t g, uint64_t age, int a) {
-  gx_u32x4 u = gx_philox4x32_10((uint32_t)g, (uint32_t)age, (uint32_t)(age >> 32), GX_STREAM_ACTION + (uint32_t)(a >> 2),
-                                p.seed_lo, p.seed_hi);
-  return gx_uniform(u.v[a & 3], -1.0f, 1.0f);
-}
-
 // MINB = resident 128-thread blocks per SM the register allocation aims for: 2 (no spills,
 // ~250 registers) is fastest while the batch leaves SMs idle anyway; 4 (128 registers, some
 // spills to L1) wins by ~30 % once the grid covers the machine several times (measured:

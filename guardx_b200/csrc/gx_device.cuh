@@ -430,6 +430,14 @@ __device__ __forceinline__ const float* gx_pick_layout(const gx_params& p, const
   return pool + (size_t)idx * p.lay_dim;
 }
 
+// a_t ~ U(-1,1) for actuator a of env g at step `age` (the synthetic rollouts of
+// BASELINE.json; same stream as the Point kernels: word 3 = GX_STREAM_ACTION + block)
+__device__ __forceinline__ float gx_art_synth_action(const gx_params& p, uint64_t g, uint64_t age, int a) {
+  gx_u32x4 u = gx_philox4x32_10((uint32_t)g, (uint32_t)age, (uint32_t)(age >> 32), GX_STREAM_ACTION + (uint32_t)(a >> 2),
+                                p.seed_lo, p.seed_hi);
+  return gx_uniform(u.v[a & 3], -1.0f, 1.0f);
+}
+
 // hazard h of env i: from a layout row (while re-placing) or from the state arrays
 __device__ __forceinline__ void gx_art_hazard(const GxState& s, const float* lay, int i, int h, float& hx, float& hy) {
   if (lay) { hx = lay[4 + 2 * h]; hy = lay[5 + 2 * h]; return; }

@@ -14,7 +14,7 @@ enum { GX_CLS_GOAL = 0, GX_CLS_HAZARD = 1, GX_CLS_ROBOT = 2 };
 
 typedef struct gx_params {
   int32_t n, nh, nb, obs_dim;
-  int32_t nu, nv; /* widths of ctrl and qpos/qvel in the observation (3, 3 for the Point) */
+  int32_t nu, nv, nq; /* widths of ctrl, qvel and qpos in the observation (3, 3, 3 for the Point) */
   int32_t substeps, alias, use_exp, tries;
   int32_t off_ctrl, off_compass, off_glidar, off_hlidar, off_qpos, off_qvel, off_acc, off_vel;
   int32_t lay_dim, state_dim, aux_dim, pool_size;
@@ -51,10 +51,13 @@ static inline const char* gx_lower_config(const gx_config* c, gx_params* p) {
   if (!c) return "null config";
   if (c->abi_version != GX_ABI_VERSION) return "abi_version mismatch";
   if (c->env_num < 1) return "env_num must be >= 1";
-  if (c->robot != GX_ROBOT_POINT && c->robot != GX_ROBOT_ART) return "unknown robot";
-  const int art = c->robot == GX_ROBOT_ART;
+  if (c->robot != GX_ROBOT_POINT && c->robot != GX_ROBOT_ART && c->robot != GX_ROBOT_TREE) return "unknown robot";
+  const int art = c->robot != GX_ROBOT_POINT;
+  const int tree = c->robot == GX_ROBOT_TREE;
+  if (tree && (c->obs_mask & (GX_OBS_ACC | GX_OBS_VEL))) return "observe_vel / observe_acc are not built for general-tree robots";
   if (art && (c->art_nu < 1 || c->art_nv < 3 || c->art_nu > 64 || c->art_nv > 64)) return "art_nu / art_nv out of range";
   p->nu = art ? c->art_nu : 3; p->nv = art ? c->art_nv : 3;
+  p->nq = art ? (c->art_nq > 0 ? c->art_nq : c->art_nv) : 3;
   if (c->hazards_num < 1 || c->hazards_num > GX_MAX_HAZARDS)
     return "hazards_num out of range (the reference crashes for 0: engine.py:370-384)";
   if (c->lidar_num_bins < 1 || c->lidar_num_bins > GX_MAX_LIDAR_BINS)
@@ -76,13 +79,13 @@ static inline const char* gx_lower_config(const gx_config* c, gx_params* p) {
   if (c->obs_mask & GX_OBS_GOAL_COMPASS) { p->off_compass = off; off += 2; }
   if (c->obs_mask & GX_OBS_GOAL_LIDAR) { p->off_glidar = off; off += p->nb; }
   if (c->obs_mask & GX_OBS_HAZARDS_LIDAR) { p->off_hlidar = off; off += p->nb; }
-  if (c->obs_mask & GX_OBS_QPOS) { p->off_qpos = off; off += p->nv; }
+  if (c->obs_mask & GX_OBS_QPOS) { p->off_qpos = off; off += p->nq; }
   if (c->obs_mask & GX_OBS_QVEL) { p->off_qvel = off; off += p->nv; }
   if (c->obs_mask & GX_OBS_VEL) { p->off_vel = off; off += 2; }
   if (off == 0) return "empty observation";
   p->obs_dim = off;
   p->lay_dim = 2 * (2 + p->nh);
-  p->state_dim = art ? 3 * p->nv + 5 + 2 * p->nh : 19 + 2 * p->nh;
+  p->state_dim = tree ? p->nq + 2 * p->nv + 5 + 2 * p->nh + 2 + 2 * p->nh : (art ? 3 * p->nv + 5 + 2 * p->nh : 19 + 2 * p->nh);
   p->aux_dim = 3 + p->nh;
   p->pool_size = c->pool_size > 0 ? c->pool_size : gx_auto_pool_size(c->env_num);
   /* self.dt = mj_model.opt.timestep (a double) * physics_steps_per_control_step (engine.py:235) */
@@ -146,7 +149,7 @@ static inline void gx_fill_default_config(gx_config* c) {
   c->opt_timestep = 0.02;
   c->hazards_num = 8; c->lidar_num_bins = 16; c->lidar_alias = 1;
   c->physics_steps_per_control_step = 1; c->layout_tries = 10; c->pool_size = 0;
-  c->obs_mask = GX_OBS_DEFAULT; c->art_nu = 0; c->art_nv = 0;
+  c->obs_mask = GX_OBS_DEFAULT; c->art_nu = 0; c->art_nv = 0; c->art_nq = 0;
   gx_point_model* pm = &c->point;
   pm->timestep = 0.02f; pm->body_z = 0.1f;
   pm->mass = (float)m; pm->com_x = (float)cx; pm->inertia_zz = (float)izz;

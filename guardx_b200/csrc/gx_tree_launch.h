@@ -1,0 +1,37 @@
+// gx_tree_launch.h -- host-side interface between guardx.cu (C ABI) and gx_tree.cu (internal).
+#ifndef GX_TREE_LAUNCH_H_
+#define GX_TREE_LAUNCH_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/guardx_tree.h"
+
+struct gx_params;
+struct GxState;
+
+struct GxTreeDev {
+  const GxTreeModel* m;
+  float* tq;       // [2 * (nq + 2 nv), cap]
+  float* tw;       // [nworld, cap] goal / hazard slide velocities
+  float* scratch;  // [GXT_SIZE, cap]
+  int nq, nv, nu;
+};
+
+struct GxTreeLaunch {
+  const gx_params* p;
+  const GxState* s;
+  const GxTreeDev* t;
+  const float *pool, *layout, *action, *obs_in;
+  float *obs, *act_out, *reward, *done, *cost, *qacc;
+  int32_t* aux;
+  int stats_on, mode, autoreset;
+  cudaStream_t stream;
+};
+cudaError_t gx_tree_launch(const GxTreeLaunch& a);
+
+void gx_tree_get_state(const gx_params& p, const GxState& s, const GxTreeDev& t, float* out, cudaStream_t st);
+void gx_tree_set_state(const gx_params& p, const GxState& s, const GxTreeDev& t, const float* in, cudaStream_t st);
+int gx_tree_scratch_floats(void);
+
+#endif  // GX_TREE_LAUNCH_H_

@@ -120,6 +120,11 @@ class Engine:
             _abi.check(self._lib, self._lib.gx_create(C.byref(self._gx_config), self.device.index, C.byref(h)),
                        "gx_create")
             self._art_info = None
+        elif self._gx_config.robot == _abi.GX_ROBOT_TREE:
+            from . import tree_model
+            self._art_model, self._art_info = tree_model.lower_tree(self.mj_model)
+            _abi.check(self._lib, self._lib.gx_create_tree(C.byref(self._gx_config), C.byref(self._art_model),
+                                                           self.device.index, C.byref(h)), "gx_create_tree")
         else:
             from . import art_model
             self._art_model, self._art_info = art_model.lower_art(self.mj_model)
@@ -136,7 +141,8 @@ class Engine:
         if self._art_info is None:
             self.robot = _Robot(3, 3, 3, 0.1)  # point.xml: nq = nv = nu = 3, body z 0.1
         else:
-            self.robot = _Robot(self._art_info['nv'], self._art_info['nv'], self._art_info['nu'], self._art_info['z_height'])
+            self.robot = _Robot(self._art_info.get('nq', self._art_info['nv']), self._art_info['nv'], self._art_info['nu'],
+                                self._art_info['z_height'])
         self.dt = float(self._gx_config.opt_timestep) * self.physics_steps_per_control_step
         lo = (C.c_float * self.act_dim)()
         hi = (C.c_float * self.act_dim)()

@@ -14,9 +14,7 @@ from __future__ import annotations
 from .mjcf import Spec, OPT_DEFAULT
 
 ROBOT_FILES = {'xmls/point.xml': 'point', 'xmls/ant.xml': 'ant', 'xmls/walker.xml': 'walker',
-               'xmls/swimmer.xml': 'swimmer'}
-# described and compiled, but without CUDA kernels yet (free-joint root, capsule contacts): groundwork
-GROUNDWORK_FILES = {'xmls/doggo.xml': 'doggo'}
+               'xmls/swimmer.xml': 'swimmer', 'xmls/doggo.xml': 'doggo'}
 
 
 def _spec(timestep, angle='degree'):
@@ -151,7 +149,7 @@ def swimmer() -> Spec:
 def doggo() -> Spec:
     """xmls/doggo.xml: free-joint torso (two 0.075 capsules; the rear one behind a waist hinge), four
     legs of hip-z, hip-y and ankle hinges with joint springs (stiffness 0.01, springref), every geom a
-    colliding capsule; 12 motors, gear 0.02; timestep 0.01.  No CUDA kernels for it yet."""
+    colliding capsule; 12 motors, gear 0.02; timestep 0.01.  Runs on the general-tree kernels (gx_tree.cuh)."""
     s = _spec(0.01)
     s.defaults['joint'] = dict(limited=True, stiffness=0.01)
     s.defaults['geom'] = dict(condim=3, size=(0.032,), type='capsule', density=5.0)
@@ -184,14 +182,12 @@ def doggo() -> Spec:
     return s
 
 
-BUILTIN = {'point': point, 'ant': ant, 'walker': walker, 'swimmer': swimmer}
-GROUNDWORK = {'doggo': doggo}
+BUILTIN = {'point': point, 'ant': ant, 'walker': walker, 'swimmer': swimmer, 'doggo': doggo}
 
 
 def robot_spec(robot_base: str) -> Spec:
     """``robot_base`` as the reference config spells it ('xmls/ant.xml', engine.py:113)."""
     key = ROBOT_FILES.get(robot_base, robot_base)
     if key not in BUILTIN:
-        raise AssertionError(f'robot_base {robot_base!r}: this build has {sorted(ROBOT_FILES)} '
-                             '(Doggo needs a free joint: not built yet)')
+        raise AssertionError(f'robot_base {robot_base!r}: this build has {sorted(ROBOT_FILES)}')
     return BUILTIN[key]()

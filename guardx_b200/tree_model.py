@@ -44,7 +44,7 @@ class GxTreePair(C.Structure):
 
 class GxTreeModel(C.Structure):
     _fields_ = [("nb", I), ("njnt", I), ("nq", I), ("nv", I), ("nu", I), ("ngeom", I), ("npair", I), ("max_iter", I),
-                ("root_free", I), ("nworld", I), ("dt", F), ("grav_z", F), ("tol_scale", F),
+                ("root_free", I), ("nworld", I), ("root_xadr", I), ("root_yadr", I), ("dt", F), ("grav_z", F), ("tol_scale", F),
                 ("world_mass", F * 2), ("world_damping", F), ("world_stiffness", F),
                 ("body", GxTreeBody * MAXB), ("jnt", GxTreeJoint * MAXJ), ("dof", GxTreeDof * MAXV),
                 ("geom", GxTreeGeom * MAXG), ("pair", GxTreePair * MAXPAIR)]
@@ -73,6 +73,10 @@ def lower_tree(m: mjcf.Model) -> tuple[GxTreeModel, dict]:
     out.dt, out.grav_z = dt, m.opt['gravity'][2]
     out.tol_scale = float(m.opt['tolerance']) * m.stat_meaninertia * max(1, m.nv)
     out.root_free = int(m.jnt_type[jnts[0]] == mjcf.JNT_FREE)
+    if out.root_free:      # joint literally named 'robot': x, y, z_height, quaternion
+        out.root_xadr, out.root_yadr = int(m.jnt_qposadr[jnts[0]]), int(m.jnt_qposadr[jnts[0]]) + 1
+    else:
+        out.root_xadr, out.root_yadr = int(m.jnt_qposadr[m.jnt_id('robot_x')]), int(m.jnt_qposadr[m.jnt_id('robot_y')])
     act_of_dof = {int(m.jnt_dofadr[m.actuator_trnid[a]]): a for a in range(m.nu)}
     for k, b in enumerate(robot):
         B = out.body[k]

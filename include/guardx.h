@@ -26,12 +26,13 @@
 #include <stdint.h>
 
 #include "guardx_art.h"
+#include "guardx_tree.h"
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define GX_ABI_VERSION 2
+#define GX_ABI_VERSION 3
 
 #define GX_MAX_HAZARDS 32    /* hazards_num upper bound of this build */
 #define GX_MAX_LIDAR_BINS 64 /* lidar_num_bins upper bound of this build */
@@ -47,7 +48,8 @@ enum {
 /* robot_base (engine.py:113).  Only robots whose dynamics this build implements. */
 enum {
   GX_ROBOT_POINT = 0, /* xmls/point.xml: closed-form 3-DoF dynamics (gx_point_model) */
-  GX_ROBOT_ART = 1    /* articulated planar-root robot (ant / walker / swimmer): gx_create_art + guardx_art.h */
+  GX_ROBOT_ART = 1,   /* articulated planar-root robot (ant / walker / swimmer): gx_create_art + guardx_art.h */
+  GX_ROBOT_TREE = 2   /* general kinematic tree, free-joint root, capsule contacts (doggo): gx_create_tree + guardx_tree.h */
 };
 
 /* observation components, flat order = sorted key order (engine.py:773-777) */
@@ -124,7 +126,8 @@ typedef struct gx_config {
   int32_t pool_size;              /* layout pool entries; 0 = auto (replaces the 1e6-candidate pool, engine.py:263) */
   uint32_t obs_mask;              /* GX_OBS_* */
   int32_t art_nu;                 /* GX_ROBOT_ART: robot.nu (width of 'ctrl' in the observation, engine.py:402-403) */
-  int32_t art_nv;                 /* GX_ROBOT_ART: robot.nq = robot.nv (widths of 'qpos' / 'qvel', engine.py:398-401) */
+  int32_t art_nv;                 /* GX_ROBOT_ART / TREE: robot.nv (width of 'qvel', engine.py:400-401) */
+  int32_t art_nq;                 /* GX_ROBOT_TREE: robot.nq (width of 'qpos'; = art_nv for GX_ROBOT_ART, 0 = same) */
   gx_point_model point;
 } gx_config;
 
@@ -144,6 +147,11 @@ int gx_create(const gx_config* h_cfg, int device, gx_env** out);
  * Every entry point below then works on that robot: action [env_num, nu], qacc
  * [env_num, nv], state rows as documented at gx_get_state, aux rows as for the Point. */
 int gx_create_art(const gx_config* h_cfg, const GxArtModel* h_model, int device, gx_env** out);
+/* Same for cfg->robot == GX_ROBOT_TREE (Doggo): h_model is the compiled general-tree robot (guardx_tree.h).
+ * First version of this path: one thread per env with a global-memory scratch buffer; state rows
+ * qpos[nq] qvel[nv] qacc_warmstart[nv] prev_dist prev_done steps goal[2] hazards[2*nh] world_vel[2+2*nh]
+ * (the goal / hazard slides move when the robot's defaults class gives them a stiffness). */
+int gx_create_tree(const gx_config* h_cfg, const GxTreeModel* h_model, int device, gx_env** out);
 int gx_destroy(gx_env* env);
 
 /* ---- spaces: build_observation_space (engine.py:386-418), action space

@@ -60,6 +60,7 @@ typedef struct GxTreeModel {
   int32_t nb, njnt, nq, nv, nu, ngeom, npair, max_iter;
   int32_t root_free;        /* 1: body 0 has a free joint */
   int32_t nworld;           /* 2 + 2 * hazards_num static-body slide dofs */
+  int32_t root_xadr, root_yadr; /* qpos index the layout's robot x / y go to (layout2qpos, engine.py:623-639) */
   float dt, grav_z, tol_scale;
   float world_mass[2], world_damping, world_stiffness; /* [0] goal, [1] hazards: body mass + armature */
   GxTreeBody body[GX_TREE_MAXB];

@@ -39,9 +39,11 @@ class ArtOracleEngine:
         self.nb = int(self.config['lidar_num_bins'])
         self.substeps = int(self.config['physics_steps_per_control_step'])
         self.robot_body = m.body_id('robot')
-        self.nq_robot = m.nq - 2 - 2 * self.nh   # robot.nq (world.py:436): the robot's own joints
+        self.nq_robot = m.nq - 2 - 2 * self.nh   # robot.nq / robot.nv (world.py:436-437): the robot's own joints
+        self.nv_robot = m.nv - 2 - 2 * self.nh
+        self.free_root = bool((m.jnt_type == 0).any())          # Doggo: free joint named 'robot'
         self.nu = m.nu
-        self.obs_dim = self.nu + 2 + 2 * self.nb + 2 * self.nq_robot
+        self.obs_dim = self.nu + 2 + 2 * self.nb + self.nq_robot + self.nv_robot
         assert self.config['observe_goal_lidar'] and self.config['observe_goal_comp'] and self.config['observe_hazards']
         assert self.config['observe_qpos'] and self.config['observe_qvel'] and self.config['observe_ctrl']
         self.with_vel, self.with_acc = bool(self.config['observe_vel']), bool(self.config['observe_acc'])
@@ -64,7 +66,12 @@ class ArtOracleEngine:
     def layout2qpos(self, layout):
         q = np.zeros((layout.shape[0], self.model.nq), self.dtype)
         q[:, self.qadr['goal_x']] = layout[:, 0]; q[:, self.qadr['goal_y']] = layout[:, 1]
-        q[:, self.qadr['robot_x']] = layout[:, 2]; q[:, self.qadr['robot_y']] = layout[:, 3]
+        if 'robot' in self.qadr:                 # free joint: x, y, z_height, unit quaternion (engine.py:626-631)
+            a = self.qadr['robot']
+            q[:, a] = layout[:, 2]; q[:, a + 1] = layout[:, 3]
+            q[:, a + 2] = self.model.body_pos[self.robot_body][2]; q[:, a + 3] = 1.0
+        else:
+            q[:, self.qadr['robot_x']] = layout[:, 2]; q[:, self.qadr['robot_y']] = layout[:, 3]
         for h in range(self.nh):
             q[:, self.qadr[f'hazard{h}_x']] = layout[:, 4 + 2 * h]; q[:, self.qadr[f'hazard{h}_y']] = layout[:, 5 + 2 * h]
         return q
@@ -99,20 +106,21 @@ class ArtOracleEngine:
         for i in range(n):
             xp, xm = np.ascontiguousarray(xpos[i]), np.ascontiguousarray(xmat[i])
             g, h = np.ascontiguousarray(goal[i]), np.ascontiguousarray(hz[i])
-            self.L.gxo_piece_compass(_p(xp), _p(xm), _p(g), _p(comp))
+            compass, lidar = (self.L.gxo_piece_compass3, self.L.gxo_piece_lidar3) if self.free_root else (self.L.gxo_piece_compass, self.L.gxo_piece_lidar)
+            compass(_p(xp), _p(xm), _p(g), _p(comp))
             obs[i, o:o + 2] = comp
             b = np.zeros(1, np.int32)
-            self.L.gxo_piece_lidar(cfg, _p(xp), _p(xm), _p(g), 1, _p(lid), _p(b))
+            lidar(cfg, _p(xp), _p(xm), _p(g), 1, _p(lid), _p(b))
             obs[i, o + 2:o + 2 + self.nb] = lid; gb[i] = b
             b = np.zeros(self.nh, np.int32)
-            self.L.gxo_piece_lidar(cfg, _p(xp), _p(xm), _p(h), self.nh, _p(lid), _p(b))
+            lidar(cfg, _p(xp), _p(xm), _p(h), self.nh, _p(lid), _p(b))
             obs[i, o + 2 + self.nb:o + 2 + 2 * self.nb] = lid; hb[i] = b
             rxy = np.ascontiguousarray(xp[:2])
             self.L.gxo_piece_cost(cfg, _p(rxy), _p(h), _p(c1))
             cost[i] = c1[0]
         o += 2 + 2 * self.nb
         obs[:, o:o + self.nq_robot] = qpos[:, :self.nq_robot]; o += self.nq_robot
-        obs[:, o:o + self.nq_robot] = qvel[:, :self.nq_robot]
+        obs[:, o:o + self.nv_robot] = qvel[:, :self.nv_robot]
         dist = np.sqrt(((goal - xpos[:, :2]) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
         return obs, cost, dist, dict(goal_bin=gb, hazard_bins=hb, xpos=xpos, xmat=xmat)
 
@@ -171,7 +179,7 @@ class ArtOracleEngine:
         self.prev_dist = dist
         self._obs = obs
         self.last_data = d
-        info = dict(cost=cost, qacc=d['qacc'][:, :self.nq_robot].astype(np.float32), dist=dist, d_dist=d_dist, **extra)
+        info = dict(cost=cost, qacc=d['qacc'][:, :self.nv_robot].astype(np.float32), dist=dist, d_dist=d_dist, **extra)
         return obs, reward, done, info
 
     def reset_done(self, layout):
@@ -203,8 +211,12 @@ class ArtOracleEngine:
         goal = np.stack([self.qpos[:, self.qadr['goal_x']], self.qpos[:, self.qadr['goal_y']]], 1)
         hz = np.concatenate([np.stack([self.qpos[:, self.qadr[f'hazard{h}_x']], self.qpos[:, self.qadr[f'hazard{h}_y']]], 1)
                              for h in range(self.nh)], 1)
-        return np.concatenate([self.qpos[:, :nr], self.qvel[:, :nr], self.warm[:, :nr], self.prev_dist[:, None],
-                               self.done[:, None], self.steps[:, None], goal, hz], 1).astype(np.float32)
+        nvr = self.nv_robot
+        parts = [self.qpos[:, :nr], self.qvel[:, :nvr], self.warm[:, :nvr], self.prev_dist[:, None],
+                 self.done[:, None], self.steps[:, None], goal, hz]
+        if self.free_root:       # general-tree rows also carry the goal / hazard slide velocities
+            parts.append(self.qvel[:, nvr:])
+        return np.concatenate(parts, 1).astype(np.float32)
 
     def round_state_to_fp32(self):
         """Make the float64 state exactly what get_state() hands to the CUDA env (one-step parity

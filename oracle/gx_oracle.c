@@ -182,10 +182,15 @@ static void ego_xy(const gxo_world* d, const float pos[2], float out[2]) {
 
 /* obs_lidar for one object (engine.py:872-899).  Returns the bin index as the
    reference computes it (may equal nb at the fp32 wrap edge). */
+static int lidar_from_ego(const gx_params* p, const float z[2], float* obs);
 static int obs_lidar_one(const gx_params* p, const gxo_world* d, const float pos[2], float* obs) {
-  const int nb = p->nb;
   float z[2];
   ego_xy(d, pos, z);
+  return lidar_from_ego(p, z, obs);
+}
+/* the binning part of obs_lidar (engine.py:877-899) for an egocentric vector z */
+static int lidar_from_ego(const gx_params* p, const float z[2], float* obs) {
+  const int nb = p->nb;
   float dist = gx_sqrt(z[0] * z[0] + z[1] * z[1]);
   float angle = gx_atan2(z[1], z[0]);
   if (angle < 0.0f) angle = angle + GX_TWO_PI_F; /* jnp `%` on [-pi,pi] */
@@ -674,6 +679,30 @@ GXO_API int gxo_piece_lidar(const gx_config* cfg, const float* xpos3, const floa
   gxo_world d; world_from_pose(&d, xpos3, xmat9);
   for (int i = 0; i < p.nb; ++i) obs[i] = 0.0f;
   for (int k = 0; k < npos; ++k) { int b = obs_lidar_one(&p, &d, positions + 2 * k, obs); if (bins) bins[k] = b; }
+  return GX_OK;
+}
+/* ego_xy / obs_compass with the FULL 3-D robot_mat (engine.py:817-826: matmul(world_3vec, robot_mat)[:2],
+   world_3vec = (x, y, 0) - robot_pos): what a free-joint robot (Doggo) needs -- a tilted torso mixes z in */
+static void ego_xy3(const float* xpos3, const float* xmat9, const float pos[2], float out[2]) {
+  float dx = pos[0] - xpos3[0], dy = pos[1] - xpos3[1], dz = 0.0f - xpos3[2];
+  out[0] = dx * xmat9[0] + dy * xmat9[3] + dz * xmat9[6];
+  out[1] = dx * xmat9[1] + dy * xmat9[4] + dz * xmat9[7];
+}
+GXO_API int gxo_piece_lidar3(const gx_config* cfg, const float* xpos3, const float* xmat9,
+                             const float* positions, int npos, float* obs, int32_t* bins) {
+  gx_params p; memset(&p, 0, sizeof p);
+  if (gx_lower_config(cfg, &p)) return GX_EINVAL;
+  for (int i = 0; i < p.nb; ++i) obs[i] = 0.0f;
+  for (int k = 0; k < npos; ++k) {
+    float z[2];
+    ego_xy3(xpos3, xmat9, positions + 2 * k, z);
+    int b = lidar_from_ego(&p, z, obs);
+    if (bins) bins[k] = b;
+  }
+  return GX_OK;
+}
+GXO_API int gxo_piece_compass3(const float* xpos3, const float* xmat9, const float* pos, float* out2) {
+  ego_xy3(xpos3, xmat9, pos, out2);
   return GX_OK;
 }
 /* obs_compass (engine.py:834-844) */

@@ -71,6 +71,6 @@ def test_bad_config_is_rejected_like_the_reference():
     with pytest.raises(AssertionError, match="Bad key"):
         gxconfig.parse({'ghosts_num': 8})
     with pytest.raises(NotImplementedError):
-        gxconfig.lower(gxconfig.parse({'robot_base': 'xmls/doggo.xml'}))
+        gxconfig.lower(gxconfig.parse({'robot_base': 'xmls/barkour_v0/assets/barkour.xml'}))   # not a robot of the JAX Engine's configs
     with pytest.raises(AssertionError):
         gxconfig.lower(gxconfig.parse({'hazards_num': 0}))

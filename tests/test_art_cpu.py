@@ -165,7 +165,9 @@ def test_art_model_lowering_and_rejections():
     am, info = art_model.lower_art(_compile('swimmer'))
     assert info['shape'] == (1, 2, 2) and (am.root_x, am.root_y) == (0, 1) and len(info['ignored_pairs']) == 3
     with pytest.raises(AssertionError):
-        robots.robot_spec('xmls/doggo.xml')
+        robots.robot_spec('xmls/car.xml')              # named by world.py:55, absent from the reference tree
+    with pytest.raises(AssertionError, match='planar root'):
+        art_model.lower_art(_compile('doggo'))         # Doggo goes to the general-tree kernels instead
 
 
 # ---------------------------------------------------------------------------

@@ -33,7 +33,7 @@ def constants(m):
 
 if __name__ == "__main__":
     gold = {}
-    for f, key in {**robots.ROBOT_FILES, **robots.GROUNDWORK_FILES}.items():
+    for f, key in robots.ROBOT_FILES.items():
         spec = mjcf.parse_mjcf(open(os.path.join(REF, f)).read())
         gold[key] = constants(mjcf.compile_spec(mjcf.add_world_geoms(spec, 0.5, 0.3, 8)))
     with open(os.path.join(ROOT, "tests", "golden", "mjcf_constants.json"), "w") as fh:
