@@ -1,9 +1,27 @@
 // General-tree (Doggo) kernels: see gx_tree.cuh / gx_tree_kernels.cuh.
 #include "gx_tree_kernels.cuh"
 
+#include <stdlib.h>
+
+static int gx_tree_shared_limit() {
+  static int limit = -1;
+  if (limit < 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* o = getenv("GUARDX_TREE_SHARED_LIMIT");   // tuning override (tools/bench_art_quick.py)
+    limit = o ? atoi(o) : sms * 96 * 3;   // measured crossover on B200: between 32768 and 65536 envs
+  }
+  return limit;
+}
+
 cudaError_t gx_tree_launch(const GxTreeLaunch& a) {
-  const int n = a.p->n, block = 64, grid = (n + block - 1) / block;
-  const size_t sh = (size_t)block * a.p->obs_dim * sizeof(float);
+  // Up to three waves of 96 envs per SM the mass matrix / factorisation workspace lives in shared memory (64 KB per
+  // 32-thread block, three blocks per SM); larger batches keep it in the global scratch and run more warps.
+  const int n = a.p->n;
+  const int mat_shared = n <= gx_tree_shared_limit();
+  const int block = mat_shared ? 32 : 64, grid = (n + block - 1) / block;
+  const size_t sh = (size_t)block * (a.p->obs_dim + (mat_shared ? GXT_SM_FLOATS : 0)) * sizeof(float);
 #define GX_TREE_GO(MODE, AR)                                                                                  \
   do {                                                                                                        \
     auto kern = gx_tree_kernel<MODE, AR>;                                                                     \
@@ -12,7 +30,7 @@ cudaError_t gx_tree_launch(const GxTreeLaunch& a) {
       if (e_ != cudaSuccess) return e_;                                                                       \
     }                                                                                                         \
     kern<<<grid, block, sh, a.stream>>>(*a.p, *a.s, *a.t, a.pool, a.layout, a.action, a.obs_in, a.obs,        \
-                                        a.act_out, a.reward, a.done, a.cost, a.qacc, a.aux, a.stats_on);      \
+                                        a.act_out, a.reward, a.done, a.cost, a.qacc, a.aux, a.stats_on, mat_shared);      \
   } while (0)
   if (a.mode == GX_ART_RESET) GX_TREE_GO(GX_ART_RESET, false);
   else if (a.mode == GX_ART_RESET_DONE) GX_TREE_GO(GX_ART_RESET_DONE, false);
@@ -28,4 +46,4 @@ void gx_tree_get_state(const gx_params& p, const GxState& s, const GxTreeDev& t,
 void gx_tree_set_state(const gx_params& p, const GxState& s, const GxTreeDev& t, const float* in, cudaStream_t st) {
   gx_tree_set_state_kernel<<<(p.n + 127) / 128, 128, 0, st>>>(p, s, t, in);
 }
-int gx_tree_scratch_floats(void) { return (int)GXT_SIZE; }
+int gx_tree_scratch_floats(void) { return (int)(GXT_SIZE + GXT_SM_FLOATS); }

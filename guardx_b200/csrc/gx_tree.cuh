@@ -21,9 +21,7 @@
 
 // scratch layout (float offsets); NVX = GX_TREE_MAXV
 enum {
-  GXT_M = 0,
-  GXT_H = GXT_M + GX_TREE_MAXV * GX_TREE_MAXV,
-  GXT_J = GXT_H + GX_TREE_MAXV * GX_TREE_MAXV,
+  GXT_J = 0,
   GXT_RD = GXT_J + GX_TREE_NROW * GX_TREE_MAXV,   // row D
   GXT_RA = GXT_RD + GX_TREE_NROW,                 // row aref
   GXT_RJ = GXT_RA + GX_TREE_NROW,                 // row J*qacc - aref
@@ -55,6 +53,16 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 
 #define TS(off) sc[(size_t)(off) * stride]
 
+// The mass matrix M and the factorisation workspace H -- the arrays every inner loop of the Cholesky
+// and of the solves walks through with dependent loads -- live in a SEPARATE, small matrix scratch
+// (`sm`, stride `ms`): shared memory in the kernel (an L2 round trip per dependent load made the first
+// version 5 ms per step), lower triangles packed: 2 x 210 floats per env.
+#define GXT_TRI (GX_TREE_MAXV * (GX_TREE_MAXV + 1) / 2)
+#define GXT_SM_FLOATS (2 * GXT_TRI)
+#define MM(i, j) sm[(size_t)((i) * ((i) + 1) / 2 + (j)) * ms]              /* j <= i */
+#define HH(i, j) sm[(size_t)(GXT_TRI + (i) * ((i) + 1) / 2 + (j)) * ms]    /* j <= i */
+GX_HD int gxt_sym(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
 GX_HD void gxt_get(const float* sc, size_t stride, int off, int n, float* out) {
   for (int k = 0; k < n; ++k) out[k] = TS(off + k);
 }
@@ -62,33 +70,31 @@ GX_HD void gxt_put(float* sc, size_t stride, int off, int n, const float* in) {
   for (int k = 0; k < n; ++k) TS(off + k) = in[k];
 }
 
-// in-place Cholesky of the n x n matrix at `off` (row-major, MAXV pitch), inverse diagonal stored
-GX_HD void gxt_chol(float* sc, size_t stride, int off, int n) {
-  const int P = GX_TREE_MAXV;
+// in-place Cholesky of the packed lower triangle H (n x n), inverse diagonal stored
+GX_HD void gxt_chol(float* sm, size_t ms, int n) {
   for (int j = 0; j < n; ++j) {
-    float d = TS(off + j * P + j);
-    for (int k = 0; k < j; ++k) { const float l = TS(off + j * P + k); d = gx_fma(-l, l, d); }
+    float d = HH(j, j);
+    for (int k = 0; k < j; ++k) { const float l = HH(j, k); d = gx_fma(-l, l, d); }
     const float inv = gx_rsqrt(d);
-    TS(off + j * P + j) = inv;
+    HH(j, j) = inv;
     for (int i = j + 1; i < n; ++i) {
-      float s = TS(off + i * P + j);
-      for (int k = 0; k < j; ++k) s = gx_fma(-TS(off + i * P + k), TS(off + j * P + k), s);
-      TS(off + i * P + j) = s * inv;
+      float s = HH(i, j);
+      for (int k = 0; k < j; ++k) s = gx_fma(-HH(i, k), HH(j, k), s);
+      HH(i, j) = s * inv;
     }
   }
 }
-// solve L L^T x = b in place (x at `xoff`)
-GX_HD void gxt_chol_solve(float* sc, size_t stride, int off, int n, int xoff) {
-  const int P = GX_TREE_MAXV;
+// solve L L^T x = b in place (x at `xoff` of the global scratch)
+GX_HD void gxt_chol_solve(const float* sm, size_t ms, int n, float* sc, size_t stride, int xoff) {
   for (int i = 0; i < n; ++i) {
     float s = TS(xoff + i);
-    for (int k = 0; k < i; ++k) s = gx_fma(-TS(off + i * P + k), TS(xoff + k), s);
-    TS(xoff + i) = s * TS(off + i * P + i);
+    for (int k = 0; k < i; ++k) s = gx_fma(-HH(i, k), TS(xoff + k), s);
+    TS(xoff + i) = s * HH(i, i);
   }
   for (int i = n - 1; i >= 0; --i) {
     float s = TS(xoff + i);
-    for (int k = i + 1; k < n; ++k) s = gx_fma(-TS(off + k * P + i), TS(xoff + k), s);
-    TS(xoff + i) = s * TS(off + i * P + i);
+    for (int k = i + 1; k < n; ++k) s = gx_fma(-HH(k, i), TS(xoff + k), s);
+    TS(xoff + i) = s * HH(i, i);
   }
 }
 
@@ -132,9 +138,10 @@ GX_HD void gxt_make_frame(const float* n, float* t1, float* t2) {
 
 // One mjx.step (or mjx.forward when forward_only).  q [nq], v [nv], warm [nv] are read with stride
 // `ss`; results go to qo, vo (post-step, same stride; untouched when forward_only) and wo (the
-// solver's qacc).  ctrl [nu] is thread-local.  sc: scratch, GXT_SIZE floats with stride `stride`.
+// solver's qacc).  ctrl [nu] is thread-local.  sc: scratch, GXT_SIZE floats with stride `stride`;
+// sm: matrix scratch, GXT_SM_FLOATS floats with stride `ms`.
 GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, const float* warm, size_t ss,
-                        const float* ctrl, float* sc, size_t stride, bool forward_only, float* qo, float* vo,
+                        const float* ctrl, float* sc, size_t stride, float* sm, size_t ms, bool forward_only, float* qo, float* vo,
                         float* wo, GxTreeSnap& snap, int* iters_out) {
   const int nv = m.nv, P = GX_TREE_MAXV;
   // ---------------- kinematics ----------------
@@ -277,7 +284,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
     for (int e = 0; e < 6; ++e) TS(GXT_CFRC + 6 * p + e) += TS(GXT_CFRC + 6 * b + e);
   }
   // ---------------- mass matrix, smooth forces ----------------
-  for (int i = 0; i < nv; ++i) for (int j = 0; j < nv; ++j) TS(GXT_M + i * P + j) = 0.f;
+  for (int i = 0; i < nv; ++i) for (int j = 0; j <= i; ++j) MM(i, j) = 0.f;
   for (int i = 0; i < nv; ++i) {
     const GxTreeDof& D = m.dof[i];
     float I[10], cd[6], f[6], F[6];
@@ -288,10 +295,9 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       float cj[6];
       gxt_get(sc, stride, GXT_CDOF + 6 * j, 6, cj);
       const float mij = gx_dot6(cj, f);
-      TS(GXT_M + i * P + j) = mij;
-      TS(GXT_M + j * P + i) = mij;
+      MM(i, j) = mij;
     }
-    TS(GXT_M + i * P + i) += D.armature;
+    MM(i, i) += D.armature;
     gxt_get(sc, stride, GXT_CFRC + 6 * D.body, 6, F);
     float fs = -(D.damping * v[(size_t)i * ss]) - gx_dot6(cd, F);
     if (D.act >= 0) {
@@ -309,9 +315,9 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       TS(GXT_FS + Jn.dofadr) -= Jn.stiffness * (q[(size_t)Jn.qposadr * ss] - Jn.springref);
   }
   // ---------------- qacc_smooth ----------------
-  for (int i = 0; i < nv; ++i) { for (int j = 0; j < nv; ++j) TS(GXT_H + i * P + j) = TS(GXT_M + i * P + j); TS(GXT_AS + i) = TS(GXT_FS + i); }
-  gxt_chol(sc, stride, GXT_H, nv);
-  gxt_chol_solve(sc, stride, GXT_H, nv, GXT_AS);
+  for (int i = 0; i < nv; ++i) { for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j); TS(GXT_AS + i) = TS(GXT_FS + i); }
+  gxt_chol(sm, ms, nv);
+  gxt_chol_solve(sm, ms, nv, sc, stride, GXT_AS);
   // ---------------- constraint rows: limits, then the active contacts ----------------
   int nrow = 0;
   for (int j = 0; j < m.njnt; ++j) {
@@ -432,7 +438,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       float cost = 0.f;
       for (int i = 0; i < nv; ++i) {
         float s = 0.f;
-        if (usew) { for (int j = 0; j < nv; ++j) s = gx_fma(TS(GXT_M + i * P + j), TS(GXT_QA + j), s); }
+        if (usew) { for (int j = 0; j < nv; ++j) s = gx_fma(sm[(size_t)gxt_sym(i, j) * ms], TS(GXT_QA + j), s); }
         else s = TS(GXT_FS + i);
         TS(GXT_MA + i) = s;
         cost = gx_fma(0.5f * (s - TS(GXT_FS + i)), TS(GXT_QA + i) - TS(GXT_AS + i), cost);
@@ -465,23 +471,23 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       }
       if (finish || !(gx_sqrt(gn) >= m.tol_scale) || iters >= m.max_iter) break;
       // H = M + J^T D J over the active rows; search = H^-1 (-grad)
-      for (int i = 0; i < nv; ++i) for (int j = 0; j <= i; ++j) TS(GXT_H + i * P + j) = TS(GXT_M + i * P + j);
+      for (int i = 0; i < nv; ++i) for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j);
       for (int r = 0; r < nrow; ++r) {
         if (!(TS(GXT_RJ + r) < 0.0f)) continue;
         const float Dr = TS(GXT_RD + r);
         for (int i = 0; i < nv; ++i) {
           const float di = Dr * TS(GXT_J + r * P + i);
           if (di == 0.0f) continue;
-          for (int j = 0; j <= i; ++j) TS(GXT_H + i * P + j) = gx_fma(di, TS(GXT_J + r * P + j), TS(GXT_H + i * P + j));
+          for (int j = 0; j <= i; ++j) HH(i, j) = gx_fma(di, TS(GXT_J + r * P + j), HH(i, j));
         }
       }
-      gxt_chol(sc, stride, GXT_H, nv);
-      gxt_chol_solve(sc, stride, GXT_H, nv, GXT_G);
+      gxt_chol(sm, ms, nv);
+      gxt_chol_solve(sm, ms, nv, sc, stride, GXT_G);
       // line-search quadratics
       float g0 = 0.f, h0 = 0.f, ssq = 0.f;
       for (int i = 0; i < nv; ++i) {
         float s = 0.f;
-        for (int j = 0; j < nv; ++j) s = gx_fma(TS(GXT_M + i * P + j), TS(GXT_G + j), s);
+        for (int j = 0; j < nv; ++j) s = gx_fma(sm[(size_t)gxt_sym(i, j) * ms], TS(GXT_G + j), s);
         TS(GXT_MV + i) = s;
         const float si = TS(GXT_G + i);
         g0 = gx_fma(si, TS(GXT_MA + i) - TS(GXT_FS + i), g0);
@@ -532,12 +538,12 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
   if (forward_only) return;
   // ---------------- euler: (M + dt*damping) qacc = qfrc_smooth + qfrc_constraint ----------------
   for (int i = 0; i < nv; ++i) {
-    for (int j = 0; j <= i; ++j) TS(GXT_H + i * P + j) = TS(GXT_M + i * P + j);
-    TS(GXT_H + i * P + i) = gx_fma(m.dt, m.dof[i].damping, TS(GXT_H + i * P + i));
+    for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j);
+    HH(i, i) = gx_fma(m.dt, m.dof[i].damping, HH(i, i));
     TS(GXT_T + i) = TS(GXT_FS + i) + TS(GXT_FC + i);
   }
-  gxt_chol(sc, stride, GXT_H, nv);
-  gxt_chol_solve(sc, stride, GXT_H, nv, GXT_T);
+  gxt_chol(sm, ms, nv);
+  gxt_chol_solve(sm, ms, nv, sc, stride, GXT_T);
   for (int i = 0; i < nv; ++i) vo[(size_t)i * ss] = gx_fma(m.dt, TS(GXT_T + i), v[(size_t)i * ss]);
   for (int j = 0; j < m.njnt; ++j) {
     const GxTreeJoint& Jn = m.jnt[j];
@@ -564,4 +570,6 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
 }
 
 #undef TS
+#undef MM
+#undef HH
 #endif  // GX_TREE_CUH_

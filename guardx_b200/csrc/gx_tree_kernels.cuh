@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
                                                      float* obs, float* __restrict__ act_out,
                                                      float* __restrict__ reward, float* __restrict__ done,
                                                      float* __restrict__ cost, float* __restrict__ qacc_out,
-                                                     int32_t* __restrict__ aux, int stats_on) {
+                                                     int32_t* __restrict__ aux, int stats_on, int mat_shared) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int wbase = i - lane;
@@ -94,6 +94,13 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
   const int W = a.nq + 2 * a.nv;
   float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
   float* row = tile + (size_t)lane * p.obs_dim;
+  // matrix scratch (M, H packed).  Small batches keep it in shared memory (element k of this thread at
+  // sm[k * blockDim.x]): every load of the factorisation is on the dependent chain, and a shared-memory
+  // round trip is a fifth of an L2 one.  64 KB per 32 threads leaves 96 threads per SM, so batches that
+  // fill the machine several times over use the global scratch instead and hide the latency with warps.
+  float* sm = mat_shared ? gx_smem + (size_t)(blockDim.x >> 5) * 32 * p.obs_dim + threadIdx.x
+                         : a.scratch + (size_t)GXT_SIZE * cap + i;
+  const size_t ms = mat_shared ? (size_t)blockDim.x : cap;
 
   if (MODE == GX_ART_RESET_DONE) {
     if (obs_in != obs) {
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK ^ 1u);
       place(lay, q, v);
       for (int k = 0; k < m.nv; ++k) w[(size_t)k * cap] = 0.0f;     // mjx_reset starts from the pristine mjx_data
-      gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, true, q, v, w, sn, nullptr);
+      gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, true, q, v, w, sn, nullptr);
       GxTreeObs o = gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q, v, cap, row, nullptr);
       prev_dist = o.dist_goal;
       steps = 0.0f;
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         // throw-away step(s) on a scratch copy: the state keeps the un-stepped pose and the stale warm start
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       for (int k = 0; k < p.substeps; ++k) {
         gpre_x = goal.x; gpre_y = goal.y;
         for (int h = 0; h < 2 * p.nh; ++h) hpre[h] = hz[h];
-        gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, false, q, v, w, sn, nullptr);
+        gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, false, q, v, w, sn, nullptr);
         advance_world();
       }
       if (qacc_out) for (int k = 0; k < m.nv; ++k) qacc_out[(size_t)i * m.nv + k] = w[(size_t)k * cap];
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         for (int k = 0; k < m.nu; ++k) ctrl[k] = 0.0f;
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);

@@ -14,7 +14,7 @@ struct GxTreeDev {
   const GxTreeModel* m;
   float* tq;       // [2 * (nq + 2 nv), cap]
   float* tw;       // [nworld, cap] goal / hazard slide velocities
-  float* scratch;  // [GXT_SIZE, cap]
+  float* scratch;  // [GXT_SIZE + GXT_SM_FLOATS, cap]
   int nq, nv, nu;
 };
 

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 from guardx_b200.engine import Engine  # noqa: E402
 
-ROB = {'ant': 'xmls/ant.xml', 'walker': 'xmls/walker.xml', 'swimmer': 'xmls/swimmer.xml'}
+ROB = {'ant': 'xmls/ant.xml', 'walker': 'xmls/walker.xml', 'swimmer': 'xmls/swimmer.xml', 'doggo': 'xmls/doggo.xml'}
 robots = sys.argv[1:] or ['ant', 'walker', 'swimmer']
 for r in robots:
     for n in (4096, 16384, 65536, 262144):
