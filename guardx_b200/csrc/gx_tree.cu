@@ -24,19 +24,24 @@ cudaError_t gx_tree_launch(const GxTreeLaunch& a) {
   const size_t sh = (size_t)block * (a.p->obs_dim + (mat_shared ? GXT_SM_FLOATS : 0)) * sizeof(float);
 #define GX_TREE_GO(MODE, AR)                                                                                  \
   do {                                                                                                        \
-    auto kern = gx_tree_kernel<MODE, AR>;                                                                     \
+    if (mat_shared) GX_TREE_GO2(MODE, AR, true); else GX_TREE_GO2(MODE, AR, false);                           \
+  } while (0)
+#define GX_TREE_GO2(MODE, AR, MSH)                                                                            \
+  do {                                                                                                        \
+    auto kern = gx_tree_kernel<MODE, AR, MSH>;                                                                \
     if (sh > 48 * 1024) {                                                                                     \
       cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);      \
       if (e_ != cudaSuccess) return e_;                                                                       \
     }                                                                                                         \
     kern<<<grid, block, sh, a.stream>>>(*a.p, *a.s, *a.t, a.pool, a.layout, a.action, a.obs_in, a.obs,        \
-                                        a.act_out, a.reward, a.done, a.cost, a.qacc, a.aux, a.stats_on, mat_shared);      \
+                                        a.act_out, a.reward, a.done, a.cost, a.qacc, a.aux, a.stats_on);      \
   } while (0)
   if (a.mode == GX_ART_RESET) GX_TREE_GO(GX_ART_RESET, false);
   else if (a.mode == GX_ART_RESET_DONE) GX_TREE_GO(GX_ART_RESET_DONE, false);
   else if (a.autoreset) GX_TREE_GO(GX_ART_STEP, true);
   else GX_TREE_GO(GX_ART_STEP, false);
 #undef GX_TREE_GO
+#undef GX_TREE_GO2
   return cudaGetLastError();
 }
 

@@ -58,10 +58,12 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 // (`sm`, stride `ms`): shared memory in the kernel (an L2 round trip per dependent load made the first
 // version 5 ms per step), lower triangles packed: 2 x 210 floats per env.
 #define GXT_TRI (GX_TREE_MAXV * (GX_TREE_MAXV + 1) / 2)
-#define GXT_SM_FLOATS (2 * GXT_TRI)
+#define GXT_XS (2 * GXT_TRI)          /* operand vector of the solves, of M*x and of J*x */
+#define GXT_JR (GXT_XS + GX_TREE_MAXV) /* one constraint row staged for the Hessian update */
+#define GXT_SM_FLOATS (2 * GXT_TRI + 2 * GX_TREE_MAXV)
 #define MM(i, j) sm[(size_t)((i) * ((i) + 1) / 2 + (j)) * ms]              /* j <= i */
 #define HH(i, j) sm[(size_t)(GXT_TRI + (i) * ((i) + 1) / 2 + (j)) * ms]    /* j <= i */
-GX_HD int gxt_sym(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+#define XS(i) sm[(size_t)(GXT_XS + (i)) * ms]
 
 GX_HD void gxt_get(const float* sc, size_t stride, int off, int n, float* out) {
   for (int k = 0; k < n; ++k) out[k] = TS(off + k);
@@ -70,32 +72,85 @@ GX_HD void gxt_put(float* sc, size_t stride, int off, int n, const float* in) {
   for (int k = 0; k < n; ++k) TS(off + k) = in[k];
 }
 
+// s - sum_k a[k] b[k], k ascending; elements `ms` apart.  Pointer walks instead of packed-index
+// arithmetic: the factorisation is a third of the kernel's instructions.
+GX_HD float gxt_dotsub(const float* a, const float* b, size_t ms, int n, float s) {
+#pragma unroll 4
+  for (int k = 0; k < n; ++k) s = gx_fma(-a[(size_t)k * ms], b[(size_t)k * ms], s);
+  return s;
+}
 // in-place Cholesky of the packed lower triangle H (n x n), inverse diagonal stored
 GX_HD void gxt_chol(float* sm, size_t ms, int n) {
+  float* rj = sm + (size_t)GXT_TRI * ms;                   // row j of H
   for (int j = 0; j < n; ++j) {
-    float d = HH(j, j);
-    for (int k = 0; k < j; ++k) { const float l = HH(j, k); d = gx_fma(-l, l, d); }
-    const float inv = gx_rsqrt(d);
-    HH(j, j) = inv;
+    const float inv = gx_rsqrt(gxt_dotsub(rj, rj, ms, j, rj[(size_t)j * ms]));
+    rj[(size_t)j * ms] = inv;
+    float* ri = rj + (size_t)(j + 1) * ms;                 // row i = j + 1 ...
     for (int i = j + 1; i < n; ++i) {
-      float s = HH(i, j);
-      for (int k = 0; k < j; ++k) s = gx_fma(-HH(i, k), HH(j, k), s);
-      HH(i, j) = s * inv;
+      ri[(size_t)j * ms] = gxt_dotsub(ri, rj, ms, j, ri[(size_t)j * ms]) * inv;
+      ri += (size_t)(i + 1) * ms;
     }
+    rj += (size_t)(j + 1) * ms;
   }
 }
-// solve L L^T x = b in place (x at `xoff` of the global scratch)
-GX_HD void gxt_chol_solve(const float* sm, size_t ms, int n, float* sc, size_t stride, int xoff) {
+// solve L L^T x = b in place, x = XS(0..n)
+GX_HD void gxt_chol_solve(float* sm, size_t ms, int n) {
+  const float* H = sm + (size_t)GXT_TRI * ms;
+  float* x = sm + (size_t)GXT_XS * ms;
+  const float* ri = H;
   for (int i = 0; i < n; ++i) {
-    float s = TS(xoff + i);
-    for (int k = 0; k < i; ++k) s = gx_fma(-HH(i, k), TS(xoff + k), s);
-    TS(xoff + i) = s * HH(i, i);
+    x[(size_t)i * ms] = gxt_dotsub(ri, x, ms, i, x[(size_t)i * ms]) * ri[(size_t)i * ms];
+    ri += (size_t)(i + 1) * ms;
   }
   for (int i = n - 1; i >= 0; --i) {
-    float s = TS(xoff + i);
-    for (int k = i + 1; k < n; ++k) s = gx_fma(-HH(k, i), TS(xoff + k), s);
-    TS(xoff + i) = s * HH(i, i);
+    float s = x[(size_t)i * ms];
+    const float* dg = H + (size_t)(i * (i + 1) / 2 + i) * ms;   // H(i, i)
+    const float* p = dg + (size_t)(i + 1) * ms;                 // H(i + 1, i)
+#pragma unroll 4
+    for (int k = i + 1; k < n; ++k) { s = gx_fma(-*p, x[(size_t)k * ms], s); p += (size_t)(k + 1) * ms; }
+    x[(size_t)i * ms] = s * *dg;
   }
+}
+// s + sum_i a[i] x[i], i ascending; a: a constraint row in the global scratch, x: matrix scratch.  The loads of a
+// batch are issued together (they are independent; one at a time each costs an L2 round trip).
+GX_HD float gxt_rowdot(const float* a, size_t stride, const float* x, size_t ms, int n, float s) {
+  for (int i = 0; i < n; i += 4) {
+    const float a0 = a[(size_t)i * stride];
+    const float a1 = i + 1 < n ? a[(size_t)(i + 1) * stride] : 0.f;
+    const float a2 = i + 2 < n ? a[(size_t)(i + 2) * stride] : 0.f;
+    const float a3 = i + 3 < n ? a[(size_t)(i + 3) * stride] : 0.f;
+    s = gx_fma(a0, x[(size_t)i * ms], s);
+    if (i + 1 < n) s = gx_fma(a1, x[(size_t)(i + 1) * ms], s);
+    if (i + 2 < n) s = gx_fma(a2, x[(size_t)(i + 2) * ms], s);
+    if (i + 3 < n) s = gx_fma(a3, x[(size_t)(i + 3) * ms], s);
+  }
+  return s;
+}
+// sum_r a[r * pitch] f[r], r ascending (one column of J^T f); same batching
+GX_HD float gxt_coldot(const float* a, size_t pitch, const float* f, size_t stride, int n) {
+  float s = 0.f;
+  for (int r = 0; r < n; r += 4) {
+    const float a0 = a[(size_t)r * pitch], f0 = f[(size_t)r * stride];
+    const float a1 = r + 1 < n ? a[(size_t)(r + 1) * pitch] : 0.f, f1 = r + 1 < n ? f[(size_t)(r + 1) * stride] : 0.f;
+    const float a2 = r + 2 < n ? a[(size_t)(r + 2) * pitch] : 0.f, f2 = r + 2 < n ? f[(size_t)(r + 2) * stride] : 0.f;
+    const float a3 = r + 3 < n ? a[(size_t)(r + 3) * pitch] : 0.f, f3 = r + 3 < n ? f[(size_t)(r + 3) * stride] : 0.f;
+    s = gx_fma(a0, f0, s);
+    if (r + 1 < n) s = gx_fma(a1, f1, s);
+    if (r + 2 < n) s = gx_fma(a2, f2, s);
+    if (r + 3 < n) s = gx_fma(a3, f3, s);
+  }
+  return s;
+}
+// row i of the symmetric packed matrix A (M: sm, H: sm + GXT_TRI * ms) times XS, j ascending
+GX_HD float gxt_symrow(const float* A, const float* x, size_t ms, int n, int i) {
+  const float* r = A + (size_t)(i * (i + 1) / 2) * ms;
+  float s = 0.f;
+#pragma unroll 4
+  for (int j = 0; j <= i; ++j) s = gx_fma(r[(size_t)j * ms], x[(size_t)j * ms], s);
+  const float* p = r + (size_t)(2 * i + 1) * ms;               // A(i + 1, i)
+#pragma unroll 4
+  for (int j = i + 1; j < n; ++j) { s = gx_fma(*p, x[(size_t)j * ms], s); p += (size_t)(j + 1) * ms; }
+  return s;
 }
 
 // closest points of two segments (oracle/mjx_numpy.py closest_segment_to_segment_points)
@@ -315,9 +370,10 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       TS(GXT_FS + Jn.dofadr) -= Jn.stiffness * (q[(size_t)Jn.qposadr * ss] - Jn.springref);
   }
   // ---------------- qacc_smooth ----------------
-  for (int i = 0; i < nv; ++i) { for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j); TS(GXT_AS + i) = TS(GXT_FS + i); }
+  for (int i = 0; i < nv; ++i) { for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j); XS(i) = TS(GXT_FS + i); }
   gxt_chol(sm, ms, nv);
-  gxt_chol_solve(sm, ms, nv, sc, stride, GXT_AS);
+  gxt_chol_solve(sm, ms, nv);
+  for (int i = 0; i < nv; ++i) TS(GXT_AS + i) = XS(i);
   // ---------------- constraint rows: limits, then the active contacts ----------------
   int nrow = 0;
   for (int j = 0; j < m.njnt; ++j) {
@@ -434,18 +490,17 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
     float cost_s = 0.f;
     for (int cnd = 0; cnd < 3; ++cnd) {
       const bool usew = cnd == 1;
-      for (int i = 0; i < nv; ++i) TS(GXT_QA + i) = usew ? warm[(size_t)i * ss] : TS(GXT_AS + i);
+      for (int i = 0; i < nv; ++i) { const float qa = usew ? warm[(size_t)i * ss] : TS(GXT_AS + i); TS(GXT_QA + i) = qa; XS(i) = qa; }
       float cost = 0.f;
       for (int i = 0; i < nv; ++i) {
         float s = 0.f;
-        if (usew) { for (int j = 0; j < nv; ++j) s = gx_fma(sm[(size_t)gxt_sym(i, j) * ms], TS(GXT_QA + j), s); }
+        if (usew) s = gxt_symrow(sm, sm + (size_t)GXT_XS * ms, ms, nv, i);
         else s = TS(GXT_FS + i);
         TS(GXT_MA + i) = s;
         cost = gx_fma(0.5f * (s - TS(GXT_FS + i)), TS(GXT_QA + i) - TS(GXT_AS + i), cost);
       }
       for (int r = 0; r < nrow; ++r) {
-        float s = -TS(GXT_RA + r);
-        for (int i = 0; i < nv; ++i) s = gx_fma(TS(GXT_J + r * P + i), TS(GXT_QA + i), s);
+        const float s = gxt_rowdot(&TS(GXT_J + r * P), stride, &XS(0), ms, nv, -TS(GXT_RA + r));
         TS(GXT_RJ + r) = s;
         if (s < 0.0f) cost = gx_fma(0.5f * TS(GXT_RD + r) * s, s, cost);
       }
@@ -456,16 +511,14 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
     for (int trip = 0; trip < m.max_iter + 2; ++trip) {
       // forces and gradient at the current point
       float gn = 0.f;
-      for (int i = 0; i < nv; ++i) TS(GXT_FC + i) = 0.f;
-      for (int r = 0; r < nrow; ++r) {
+      for (int r = 0; r < nrow; ++r) {          // row forces (0 on inactive rows), parked in the J*search slot
         const float jr = TS(GXT_RJ + r);
-        if (jr < 0.0f) {
-          const float force = -TS(GXT_RD + r) * jr;
-          for (int i = 0; i < nv; ++i) TS(GXT_FC + i) = gx_fma(TS(GXT_J + r * P + i), force, TS(GXT_FC + i));
-        }
+        TS(GXT_RV + r) = jr < 0.0f ? -TS(GXT_RD + r) * jr : 0.0f;
       }
       for (int i = 0; i < nv; ++i) {
-        const float g = TS(GXT_FC + i) - (TS(GXT_MA + i) - TS(GXT_FS + i));   // -gradient
+        const float fc = gxt_coldot(&TS(GXT_J + i), (size_t)P * stride, &TS(GXT_RV), stride, nrow);
+        TS(GXT_FC + i) = fc;
+        const float g = fc - (TS(GXT_MA + i) - TS(GXT_FS + i));   // -gradient
         TS(GXT_G + i) = g;
         gn = gx_fma(g, g, gn);
       }
@@ -475,19 +528,35 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       for (int r = 0; r < nrow; ++r) {
         if (!(TS(GXT_RJ + r) < 0.0f)) continue;
         const float Dr = TS(GXT_RD + r);
+        for (int i = 0; i < nv; i += 4) {         // stage the row: batched loads
+          const float a0 = TS(GXT_J + r * P + i);
+          const float a1 = i + 1 < nv ? TS(GXT_J + r * P + i + 1) : 0.f;
+          const float a2 = i + 2 < nv ? TS(GXT_J + r * P + i + 2) : 0.f;
+          const float a3 = i + 3 < nv ? TS(GXT_J + r * P + i + 3) : 0.f;
+          sm[(size_t)(GXT_JR + i) * ms] = a0;
+          if (i + 1 < nv) sm[(size_t)(GXT_JR + i + 1) * ms] = a1;
+          if (i + 2 < nv) sm[(size_t)(GXT_JR + i + 2) * ms] = a2;
+          if (i + 3 < nv) sm[(size_t)(GXT_JR + i + 3) * ms] = a3;
+        }
+        const float* jrow = sm + (size_t)GXT_JR * ms;
+        float* hrow = sm + (size_t)GXT_TRI * ms;
         for (int i = 0; i < nv; ++i) {
-          const float di = Dr * TS(GXT_J + r * P + i);
-          if (di == 0.0f) continue;
-          for (int j = 0; j <= i; ++j) HH(i, j) = gx_fma(di, TS(GXT_J + r * P + j), HH(i, j));
+          const float di = Dr * jrow[(size_t)i * ms];
+          if (di != 0.0f) {
+#pragma unroll 4
+            for (int j = 0; j <= i; ++j) hrow[(size_t)j * ms] = gx_fma(di, jrow[(size_t)j * ms], hrow[(size_t)j * ms]);
+          }
+          hrow += (size_t)(i + 1) * ms;
         }
       }
+      for (int i = 0; i < nv; ++i) XS(i) = TS(GXT_G + i);
       gxt_chol(sm, ms, nv);
-      gxt_chol_solve(sm, ms, nv, sc, stride, GXT_G);
+      gxt_chol_solve(sm, ms, nv);
+      for (int i = 0; i < nv; ++i) TS(GXT_G + i) = XS(i);
       // line-search quadratics
       float g0 = 0.f, h0 = 0.f, ssq = 0.f;
       for (int i = 0; i < nv; ++i) {
-        float s = 0.f;
-        for (int j = 0; j < nv; ++j) s = gx_fma(sm[(size_t)gxt_sym(i, j) * ms], TS(GXT_G + j), s);
+        const float s = gxt_symrow(sm, sm + (size_t)GXT_XS * ms, ms, nv, i);
         TS(GXT_MV + i) = s;
         const float si = TS(GXT_G + i);
         g0 = gx_fma(si, TS(GXT_MA + i) - TS(GXT_FS + i), g0);
@@ -495,9 +564,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         ssq = gx_fma(si, si, ssq);
       }
       for (int r = 0; r < nrow; ++r) {
-        float s = 0.f;
-        for (int i = 0; i < nv; ++i) s = gx_fma(TS(GXT_J + r * P + i), TS(GXT_G + i), s);
-        TS(GXT_RV + r) = s;
+        TS(GXT_RV + r) = gxt_rowdot(&TS(GXT_J + r * P), stride, &XS(0), ms, nv, 0.f);
       }
       float alpha = 0.f, lo = 0.f, hi = 3.0e38f, slope0 = 0.f;
       for (int ls = 0; ls < 40; ++ls) {
@@ -540,11 +607,11 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
   for (int i = 0; i < nv; ++i) {
     for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j);
     HH(i, i) = gx_fma(m.dt, m.dof[i].damping, HH(i, i));
-    TS(GXT_T + i) = TS(GXT_FS + i) + TS(GXT_FC + i);
+    XS(i) = TS(GXT_FS + i) + TS(GXT_FC + i);
   }
   gxt_chol(sm, ms, nv);
-  gxt_chol_solve(sm, ms, nv, sc, stride, GXT_T);
-  for (int i = 0; i < nv; ++i) vo[(size_t)i * ss] = gx_fma(m.dt, TS(GXT_T + i), v[(size_t)i * ss]);
+  gxt_chol_solve(sm, ms, nv);
+  for (int i = 0; i < nv; ++i) vo[(size_t)i * ss] = gx_fma(m.dt, XS(i), v[(size_t)i * ss]);
   for (int j = 0; j < m.njnt; ++j) {
     const GxTreeJoint& Jn = m.jnt[j];
     if (Jn.type == GX_TJ_FREE) {

@@ -74,7 +74,7 @@ __device__ __forceinline__ void gx_world_dof(const GxTreeModel& m, float M, floa
   q = gx_fma(m.dt, v, q);
 }
 
-template <int MODE, bool AUTORESET>
+template <int MODE, bool AUTORESET, bool MSH>
 __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_params p, const GxState s,
                                                      const GxTreeDev a, const float* __restrict__ pool,
                                                      const float* __restrict__ layout,
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
                                                      float* obs, float* __restrict__ act_out,
                                                      float* __restrict__ reward, float* __restrict__ done,
                                                      float* __restrict__ cost, float* __restrict__ qacc_out,
-                                                     int32_t* __restrict__ aux, int stats_on, int mat_shared) {
+                                                     int32_t* __restrict__ aux, int stats_on) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int wbase = i - lane;
@@ -98,9 +98,10 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
   // sm[k * blockDim.x]): every load of the factorisation is on the dependent chain, and a shared-memory
   // round trip is a fifth of an L2 one.  64 KB per 32 threads leaves 96 threads per SM, so batches that
   // fill the machine several times over use the global scratch instead and hide the latency with warps.
-  float* sm = mat_shared ? gx_smem + (size_t)(blockDim.x >> 5) * 32 * p.obs_dim + threadIdx.x
-                         : a.scratch + (size_t)GXT_SIZE * cap + i;
-  const size_t ms = mat_shared ? (size_t)blockDim.x : cap;
+  // (MSH is a template parameter so that the shared-memory build addresses it with LDS / STS.)
+  float* sm = MSH ? gx_smem + (size_t)(blockDim.x >> 5) * 32 * p.obs_dim + threadIdx.x
+                  : a.scratch + (size_t)GXT_SIZE * cap + i;
+  const size_t ms = MSH ? (size_t)blockDim.x : cap;
 
   if (MODE == GX_ART_RESET_DONE) {
     if (obs_in != obs) {
