@@ -57,10 +57,13 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 // and of the solves walks through with dependent loads -- live in a SEPARATE, small matrix scratch
 // (`sm`, stride `ms`): shared memory in the kernel (an L2 round trip per dependent load made the first
 // version 5 ms per step), lower triangles packed: 2 x 210 floats per env.
-#define GXT_TRI (GX_TREE_MAXV * (GX_TREE_MAXV + 1) / 2)
-#define GXT_XS (2 * GXT_TRI)          /* operand vector of the solves, of M*x and of J*x */
-#define GXT_JR (GXT_XS + GX_TREE_MAXV) /* one constraint row staged for the Hessian update */
-#define GXT_SM_FLOATS (2 * GXT_TRI + 2 * GX_TREE_MAXV)
+// Layout for a model with nv dofs, tri = nv (nv + 1) / 2:  M [tri] | H [tri] | XS [nv] | JR [nv]
+// (sized by the model, not by GX_TREE_MAXV: Doggo's 418 floats let four 32-env blocks share an SM).
+#define GXT_TRI (tri)
+#define GXT_XS (2 * tri)              /* operand vector of the solves, of M*x and of J*x */
+#define GXT_JR (2 * tri + nv)         /* one constraint row staged for the Hessian update */
+#define GXT_SM_FLOATS_OF(nv) ((nv) * ((nv) + 1) + 2 * (nv))
+#define GXT_SM_FLOATS GXT_SM_FLOATS_OF(GX_TREE_MAXV)
 #define MM(i, j) sm[(size_t)((i) * ((i) + 1) / 2 + (j)) * ms]              /* j <= i */
 #define HH(i, j) sm[(size_t)(GXT_TRI + (i) * ((i) + 1) / 2 + (j)) * ms]    /* j <= i */
 #define XS(i) sm[(size_t)(GXT_XS + (i)) * ms]
@@ -81,6 +84,7 @@ GX_HD float gxt_dotsub(const float* a, const float* b, size_t ms, int n, float s
 }
 // in-place Cholesky of the packed lower triangle H (n x n), inverse diagonal stored
 GX_HD void gxt_chol(float* sm, size_t ms, int n) {
+  const int tri = n * (n + 1) / 2;
   float* rj = sm + (size_t)GXT_TRI * ms;                   // row j of H
   for (int j = 0; j < n; ++j) {
     const float inv = gx_rsqrt(gxt_dotsub(rj, rj, ms, j, rj[(size_t)j * ms]));
@@ -95,6 +99,7 @@ GX_HD void gxt_chol(float* sm, size_t ms, int n) {
 }
 // solve L L^T x = b in place, x = XS(0..n)
 GX_HD void gxt_chol_solve(float* sm, size_t ms, int n) {
+  const int tri = n * (n + 1) / 2;
   const float* H = sm + (size_t)GXT_TRI * ms;
   float* x = sm + (size_t)GXT_XS * ms;
   const float* ri = H;
@@ -198,7 +203,7 @@ GX_HD void gxt_make_frame(const float* n, float* t1, float* t2) {
 GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, const float* warm, size_t ss,
                         const float* ctrl, float* sc, size_t stride, float* sm, size_t ms, bool forward_only, float* qo, float* vo,
                         float* wo, GxTreeSnap& snap, int* iters_out) {
-  const int nv = m.nv, P = GX_TREE_MAXV;
+  const int nv = m.nv, P = GX_TREE_MAXV, tri = nv * (nv + 1) / 2;
   // ---------------- kinematics ----------------
   for (int b = 0; b < m.nb; ++b) {
     const GxTreeBody& B = m.body[b];

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
                                                      float* __restrict__ reward, float* __restrict__ done,
                                                      float* __restrict__ cost, float* __restrict__ qacc_out,
                                                      int32_t* __restrict__ aux, int stats_on) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int wbase = i - lane;
   if (wbase >= p.n) return;
@@ -92,15 +92,14 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
   const GxTreeModel& m = *a.m;
   const size_t cap = (size_t)s.cap;
   const int W = a.nq + 2 * a.nv;
-  float* tile = gx_smem + (size_t)warp * 32 * p.obs_dim;
-  float* row = tile + (size_t)lane * p.obs_dim;
-  // matrix scratch (M, H packed).  Small batches keep it in shared memory (element k of this thread at
-  // sm[k * blockDim.x]): every load of the factorisation is on the dependent chain, and a shared-memory
-  // round trip is a fifth of an L2 one.  64 KB per 32 threads leaves 96 threads per SM, so batches that
-  // fill the machine several times over use the global scratch instead and hide the latency with warps.
+  // The observation row is written in place (no staging tile: one 340-byte row per env and per multi-ms step).
+  float* row = obs + (size_t)i * p.obs_dim;
+  // matrix scratch (M, H packed, solve operand, staged constraint row): shared memory (element k of this
+  // thread at sm[k * blockDim.x]) -- every load of the factorisation is on the dependent chain, and a
+  // shared-memory round trip is a fifth of an L2 one.  Doggo: 418 floats per env, 53.5 KB per 32-env block,
+  // four blocks per SM.  MSH = false keeps it in the global scratch (kept for A/B measurements).
   // (MSH is a template parameter so that the shared-memory build addresses it with LDS / STS.)
-  float* sm = MSH ? gx_smem + (size_t)(blockDim.x >> 5) * 32 * p.obs_dim + threadIdx.x
-                  : a.scratch + (size_t)GXT_SIZE * cap + i;
+  float* sm = MSH ? gx_smem + threadIdx.x : a.scratch + (size_t)GXT_SIZE * cap + i;
   const size_t ms = MSH ? (size_t)blockDim.x : cap;
 
   if (MODE == GX_ART_RESET_DONE) {
@@ -247,15 +246,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
     }
     s.d2[i] = make_float4(prev_dist, was_done > 0.0f ? -steps : steps, __uint_as_float((uint32_t)age),
                           __uint_as_float((uint32_t)(age >> 32)));
-    if (MODE == GX_ART_RESET_DONE) {
-      if (was_done > 0.0f) {
-        float* dst = obs + (size_t)i * p.obs_dim;
-        for (int k = 0; k < p.obs_dim; ++k) dst[k] = row[k];
-      }
-    }
   }
-  if (MODE == GX_ART_RESET_DONE) return;
-  gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
 }
 
 // ---- state injection / checkpoint: one row per env =
