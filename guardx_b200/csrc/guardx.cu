@@ -762,7 +762,7 @@ static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int
     cudaMemcpy(dm, h_tree, sizeof(GxTreeModel), cudaMemcpyHostToDevice);
     e->tree.m = dm;
     GX_ALLOC(e->tree.tq, sizeof(float) * 2 * (size_t)(h_tree->nq + 2 * h_tree->nv) * cap);
-    GX_ALLOC(e->tree.tw, sizeof(float) * (size_t)h_tree->nworld * cap);
+    GX_ALLOC(e->tree.tw, sizeof(float) * (size_t)(h_tree->nworld + 2) * cap);   // + z history of ego_vel_acc
     GX_ALLOC(e->tree.scratch, sizeof(float) * (size_t)gx_tree_scratch_floats() * cap);
   }
 #undef GX_ALLOC

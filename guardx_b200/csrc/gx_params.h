@@ -54,7 +54,6 @@ static inline const char* gx_lower_config(const gx_config* c, gx_params* p) {
   if (c->robot != GX_ROBOT_POINT && c->robot != GX_ROBOT_ART && c->robot != GX_ROBOT_TREE) return "unknown robot";
   const int art = c->robot != GX_ROBOT_POINT;
   const int tree = c->robot == GX_ROBOT_TREE;
-  if (tree && (c->obs_mask & (GX_OBS_ACC | GX_OBS_VEL))) return "observe_vel / observe_acc are not built for general-tree robots";
   if (art && (c->art_nu < 1 || c->art_nv < 3 || c->art_nu > 64 || c->art_nv > 64)) return "art_nu / art_nv out of range";
   p->nu = art ? c->art_nu : 3; p->nv = art ? c->art_nv : 3;
   p->nq = art ? (c->art_nq > 0 ? c->art_nq : c->art_nv) : 3;

@@ -6,20 +6,22 @@
 static int gx_tree_shared_limit() {
   static int limit = -1;
   if (limit < 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const char* o = getenv("GUARDX_TREE_SHARED_LIMIT");   // tuning override (tools/bench_art_quick.py)
-    limit = o ? atoi(o) : 0x7fffffff;
+    limit = o ? atoi(o) : sms * 128;
   }
   return limit;
 }
 
 cudaError_t gx_tree_launch(const GxTreeLaunch& a) {
-  // The mass matrix / factorisation workspace lives in shared memory (32-env blocks, 53.5 KB for Doggo, four per
-  // SM).  Measured on B200: faster than the global-scratch build at every batch size (4096 envs 2.4 vs 5.4 ms,
-  // 65 536 envs 10.7 vs 11.7 ms per step); GUARDX_TREE_SHARED_LIMIT=0 selects the global build for A/B runs.
+  // 32-env blocks; Hessian workspace in shared memory.  Up to one wave of four blocks per SM the mass matrix is in
+  // shared memory too (lowest latency per env); beyond, it stays in the global scratch and seven blocks share an SM.
   const int n = a.p->n;
   const int mat_shared = n <= gx_tree_shared_limit();
-  const int block = mat_shared ? 32 : 64, grid = (n + block - 1) / block;
-  const size_t sh = mat_shared ? (size_t)block * GXT_SM_FLOATS_OF(a.t->nv) * sizeof(float) : 0;
+  const int block = 32, grid = (n + block - 1) / block;
+  const size_t sh = (size_t)block * GXT_SM_FLOATS_OF(a.t->nv, mat_shared) * sizeof(float);
 #define GX_TREE_GO(MODE, AR)                                                                                  \
   do {                                                                                                        \
     if (mat_shared) GX_TREE_GO2(MODE, AR, true); else GX_TREE_GO2(MODE, AR, false);                           \
@@ -49,4 +51,4 @@ void gx_tree_get_state(const gx_params& p, const GxState& s, const GxTreeDev& t,
 void gx_tree_set_state(const gx_params& p, const GxState& s, const GxTreeDev& t, const float* in, cudaStream_t st) {
   gx_tree_set_state_kernel<<<(p.n + 127) / 128, 128, 0, st>>>(p, s, t, in);
 }
-int gx_tree_scratch_floats(void) { return (int)(GXT_SIZE + GXT_SM_FLOATS); }
+int gx_tree_scratch_floats(void) { return (int)(GXT_SIZE + GX_TREE_MAXV * (GX_TREE_MAXV + 1) / 2); }

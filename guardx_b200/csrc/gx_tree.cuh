@@ -57,15 +57,16 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 // and of the solves walks through with dependent loads -- live in a SEPARATE, small matrix scratch
 // (`sm`, stride `ms`): shared memory in the kernel (an L2 round trip per dependent load made the first
 // version 5 ms per step), lower triangles packed: 2 x 210 floats per env.
-// Layout for a model with nv dofs, tri = nv (nv + 1) / 2:  M [tri] | H [tri] | XS [nv] | JR [nv]
-// (sized by the model, not by GX_TREE_MAXV: Doggo's 418 floats let four 32-env blocks share an SM).
-#define GXT_TRI (tri)
-#define GXT_XS (2 * tri)              /* operand vector of the solves, of M*x and of J*x */
-#define GXT_JR (2 * tri + nv)         /* one constraint row staged for the Hessian update */
-#define GXT_SM_FLOATS_OF(nv) ((nv) * ((nv) + 1) + 2 * (nv))
-#define GXT_SM_FLOATS GXT_SM_FLOATS_OF(GX_TREE_MAXV)
-#define MM(i, j) sm[(size_t)((i) * ((i) + 1) / 2 + (j)) * ms]              /* j <= i */
-#define HH(i, j) sm[(size_t)(GXT_TRI + (i) * ((i) + 1) / 2 + (j)) * ms]    /* j <= i */
+// Layout for a model with nv dofs, tri = nv (nv + 1) / 2:  H [tri] | XS [nv] | JR [nv] ( | M [tri] )
+// (sized by the model, not by GX_TREE_MAXV).  M is addressed through its own pointer / stride (`mm`, `mms`):
+// behind JR in the same scratch, or in global memory when the launch trades M's latency for occupancy.
+#define GXT_XS (tri)                  /* operand vector of the solves, of M*x and of J*x */
+#define GXT_JR (tri + nv)             /* one constraint row staged for the Hessian update */
+#define GXT_MOFF(nv) ((nv) * ((nv) + 1) / 2 + 2 * (nv))
+#define GXT_SM_FLOATS_OF(nv, with_m) ((nv) * ((nv) + 1) / 2 * ((with_m) ? 2 : 1) + 2 * (nv))
+#define GXT_SM_FLOATS GXT_SM_FLOATS_OF(GX_TREE_MAXV, 1)
+#define MM(i, j) mm[(size_t)((i) * ((i) + 1) / 2 + (j)) * mms]             /* j <= i */
+#define HH(i, j) sm[(size_t)((i) * ((i) + 1) / 2 + (j)) * ms]              /* j <= i */
 #define XS(i) sm[(size_t)(GXT_XS + (i)) * ms]
 
 GX_HD void gxt_get(const float* sc, size_t stride, int off, int n, float* out) {
@@ -84,8 +85,7 @@ GX_HD float gxt_dotsub(const float* a, const float* b, size_t ms, int n, float s
 }
 // in-place Cholesky of the packed lower triangle H (n x n), inverse diagonal stored
 GX_HD void gxt_chol(float* sm, size_t ms, int n) {
-  const int tri = n * (n + 1) / 2;
-  float* rj = sm + (size_t)GXT_TRI * ms;                   // row j of H
+  float* rj = sm;                                          // row j of H
   for (int j = 0; j < n; ++j) {
     const float inv = gx_rsqrt(gxt_dotsub(rj, rj, ms, j, rj[(size_t)j * ms]));
     rj[(size_t)j * ms] = inv;
@@ -100,7 +100,7 @@ GX_HD void gxt_chol(float* sm, size_t ms, int n) {
 // solve L L^T x = b in place, x = XS(0..n)
 GX_HD void gxt_chol_solve(float* sm, size_t ms, int n) {
   const int tri = n * (n + 1) / 2;
-  const float* H = sm + (size_t)GXT_TRI * ms;
+  const float* H = sm;
   float* x = sm + (size_t)GXT_XS * ms;
   const float* ri = H;
   for (int i = 0; i < n; ++i) {
@@ -146,16 +146,29 @@ GX_HD float gxt_coldot(const float* a, size_t pitch, const float* f, size_t stri
   }
   return s;
 }
-// row i of the symmetric packed matrix A (M: sm, H: sm + GXT_TRI * ms) times XS, j ascending
-GX_HD float gxt_symrow(const float* A, const float* x, size_t ms, int n, int i) {
-  const float* r = A + (size_t)(i * (i + 1) / 2) * ms;
+// row i of the symmetric packed matrix A (stride as) times x (stride ms), j ascending
+GX_HD float gxt_symrow(const float* A, size_t as, const float* x, size_t ms, int n, int i) {
+  const float* r = A + (size_t)(i * (i + 1) / 2) * as;
   float s = 0.f;
 #pragma unroll 4
-  for (int j = 0; j <= i; ++j) s = gx_fma(r[(size_t)j * ms], x[(size_t)j * ms], s);
-  const float* p = r + (size_t)(2 * i + 1) * ms;               // A(i + 1, i)
+  for (int j = 0; j <= i; ++j) s = gx_fma(r[(size_t)j * as], x[(size_t)j * ms], s);
+  const float* p = r + (size_t)(2 * i + 1) * as;               // A(i + 1, i)
 #pragma unroll 4
-  for (int j = i + 1; j < n; ++j) { s = gx_fma(*p, x[(size_t)j * ms], s); p += (size_t)(j + 1) * ms; }
+  for (int j = i + 1; j < n; ++j) { s = gx_fma(*p, x[(size_t)j * ms], s); p += (size_t)(j + 1) * as; }
   return s;
+}
+// H := M (packed triangles), loads in batches of 4
+GX_HD void gxt_copy_tri(const float* mm, size_t mms, float* sm, size_t ms, int tri) {
+  for (int k = 0; k < tri; k += 4) {
+    const float a0 = mm[(size_t)k * mms];
+    const float a1 = k + 1 < tri ? mm[(size_t)(k + 1) * mms] : 0.f;
+    const float a2 = k + 2 < tri ? mm[(size_t)(k + 2) * mms] : 0.f;
+    const float a3 = k + 3 < tri ? mm[(size_t)(k + 3) * mms] : 0.f;
+    sm[(size_t)k * ms] = a0;
+    if (k + 1 < tri) sm[(size_t)(k + 1) * ms] = a1;
+    if (k + 2 < tri) sm[(size_t)(k + 2) * ms] = a2;
+    if (k + 3 < tri) sm[(size_t)(k + 3) * ms] = a3;
+  }
 }
 
 // closest points of two segments (oracle/mjx_numpy.py closest_segment_to_segment_points)
@@ -199,9 +212,9 @@ GX_HD void gxt_make_frame(const float* n, float* t1, float* t2) {
 // One mjx.step (or mjx.forward when forward_only).  q [nq], v [nv], warm [nv] are read with stride
 // `ss`; results go to qo, vo (post-step, same stride; untouched when forward_only) and wo (the
 // solver's qacc).  ctrl [nu] is thread-local.  sc: scratch, GXT_SIZE floats with stride `stride`;
-// sm: matrix scratch, GXT_SM_FLOATS floats with stride `ms`.
+// sm: matrix scratch (H | XS | JR), stride `ms`; mm: packed mass matrix, stride `mms`.
 GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, const float* warm, size_t ss,
-                        const float* ctrl, float* sc, size_t stride, float* sm, size_t ms, bool forward_only, float* qo, float* vo,
+                        const float* ctrl, float* sc, size_t stride, float* sm, size_t ms, float* mm, size_t mms, bool forward_only, float* qo, float* vo,
                         float* wo, GxTreeSnap& snap, int* iters_out) {
   const int nv = m.nv, P = GX_TREE_MAXV, tri = nv * (nv + 1) / 2;
   // ---------------- kinematics ----------------
@@ -375,7 +388,8 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       TS(GXT_FS + Jn.dofadr) -= Jn.stiffness * (q[(size_t)Jn.qposadr * ss] - Jn.springref);
   }
   // ---------------- qacc_smooth ----------------
-  for (int i = 0; i < nv; ++i) { for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j); XS(i) = TS(GXT_FS + i); }
+  gxt_copy_tri(mm, mms, sm, ms, tri);
+  for (int i = 0; i < nv; ++i) XS(i) = TS(GXT_FS + i);
   gxt_chol(sm, ms, nv);
   gxt_chol_solve(sm, ms, nv);
   for (int i = 0; i < nv; ++i) TS(GXT_AS + i) = XS(i);
@@ -499,7 +513,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       float cost = 0.f;
       for (int i = 0; i < nv; ++i) {
         float s = 0.f;
-        if (usew) s = gxt_symrow(sm, sm + (size_t)GXT_XS * ms, ms, nv, i);
+        if (usew) s = gxt_symrow(mm, mms, sm + (size_t)GXT_XS * ms, ms, nv, i);
         else s = TS(GXT_FS + i);
         TS(GXT_MA + i) = s;
         cost = gx_fma(0.5f * (s - TS(GXT_FS + i)), TS(GXT_QA + i) - TS(GXT_AS + i), cost);
@@ -529,7 +543,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       }
       if (finish || !(gx_sqrt(gn) >= m.tol_scale) || iters >= m.max_iter) break;
       // H = M + J^T D J over the active rows; search = H^-1 (-grad)
-      for (int i = 0; i < nv; ++i) for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j);
+      gxt_copy_tri(mm, mms, sm, ms, tri);
       for (int r = 0; r < nrow; ++r) {
         if (!(TS(GXT_RJ + r) < 0.0f)) continue;
         const float Dr = TS(GXT_RD + r);
@@ -544,7 +558,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
           if (i + 3 < nv) sm[(size_t)(GXT_JR + i + 3) * ms] = a3;
         }
         const float* jrow = sm + (size_t)GXT_JR * ms;
-        float* hrow = sm + (size_t)GXT_TRI * ms;
+        float* hrow = sm;
         for (int i = 0; i < nv; ++i) {
           const float di = Dr * jrow[(size_t)i * ms];
           if (di != 0.0f) {
@@ -561,7 +575,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       // line-search quadratics
       float g0 = 0.f, h0 = 0.f, ssq = 0.f;
       for (int i = 0; i < nv; ++i) {
-        const float s = gxt_symrow(sm, sm + (size_t)GXT_XS * ms, ms, nv, i);
+        const float s = gxt_symrow(mm, mms, sm + (size_t)GXT_XS * ms, ms, nv, i);
         TS(GXT_MV + i) = s;
         const float si = TS(GXT_G + i);
         g0 = gx_fma(si, TS(GXT_MA + i) - TS(GXT_FS + i), g0);
@@ -609,8 +623,8 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
   for (int i = 0; i < nv; ++i) wo[(size_t)i * ss] = TS(GXT_QA + i);
   if (forward_only) return;
   // ---------------- euler: (M + dt*damping) qacc = qfrc_smooth + qfrc_constraint ----------------
+  gxt_copy_tri(mm, mms, sm, ms, tri);
   for (int i = 0; i < nv; ++i) {
-    for (int j = 0; j <= i; ++j) HH(i, j) = MM(i, j);
     HH(i, i) = gx_fma(m.dt, m.dof[i].damping, HH(i, i));
     XS(i) = TS(GXT_FS + i) + TS(GXT_FC + i);
   }

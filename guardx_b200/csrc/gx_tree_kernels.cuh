@@ -65,6 +65,42 @@ __device__ __forceinline__ GxTreeObs gx_tree_obs_row(const gx_params& p, const G
   return o;
 }
 
+// ego_vel_acc (engine.py:902-929) with the full 3-D xpos / xmat of a general-tree root: finite differences of
+// the root position over Engine._data / _last_data / _last_last_data with the done masking, rotated into the
+// robot frame (world_vec @ xmat, first two components).  x / y history and the flags live in s.hx / s.hf as for
+// the other robots (gx_vel_acc), the z history in zh[0] (last) and zh[cap] (last-last).
+__device__ __forceinline__ int gx_vel_acc3(const gx_params& p, const GxState& s, float* zh, size_t cap, int i,
+                                           const GxTreeSnap& sn, float last_done, float* row) {
+  const float4 h = s.hx[i];
+  const uint32_t f = s.hf[i];
+  const float last_last_done = (f & 1u) ? 1.0f : 0.0f;
+  const int hist = (int)((f >> 1) & 3u);
+  const float cur[3] = {sn.pos[0], sn.pos[1], sn.pos[2]};
+  const float l[3] = {h.x, h.y, zh[0]};
+  const float ll[3] = {hist >= 2 ? h.z : l[0], hist >= 2 ? h.w : l[1], hist >= 2 ? zh[cap] : l[2]};
+  float vw[3], aw[3];
+  for (int k = 0; k < 3; ++k) {
+    float pl = cur[k], pll = cur[k];
+    if (hist >= 1) {
+      if (!(last_done > 0.0f)) pl = l[k];
+      if (hist >= 2) pll = (last_last_done + last_done > 0.0f) ? pl : ll[k];
+    }
+    vw[k] = gx_div(cur[k] - pl, p.ctrl_dt);
+    const float lv = gx_div(pl - pll, p.ctrl_dt);
+    aw[k] = gx_div(vw[k] - lv, p.ctrl_dt);
+  }
+  const float* R = sn.mat;
+  const float vx = vw[0] * R[0] + vw[1] * R[3] + vw[2] * R[6], vy = vw[0] * R[1] + vw[1] * R[4] + vw[2] * R[7];
+  const float ax = aw[0] * R[0] + aw[1] * R[3] + aw[2] * R[6], ay = aw[0] * R[1] + aw[1] * R[4] + aw[2] * R[7];
+  int bad = 0;
+  if (p.off_acc >= 0) { row[p.off_acc] = ax; row[p.off_acc + 1] = ay; bad |= gx_notfinite(ax) | gx_notfinite(ay); }
+  if (p.off_vel >= 0) { row[p.off_vel] = vx; row[p.off_vel + 1] = vy; bad |= gx_notfinite(vx) | gx_notfinite(vy); }
+  s.hx[i] = make_float4(cur[0], cur[1], l[0], l[1]);
+  zh[cap] = l[2]; zh[0] = cur[2];
+  s.hf[i] = (last_done > 0.0f ? 1u : 0u) | ((uint32_t)(hist < 2 ? hist + 1 : 2) << 1);
+  return bad;
+}
+
 // one semi-implicit Euler step of a goal / hazard slide dof (mass + armature M, damping d, stiffness k,
 // spring reference 0): the same arithmetic mjx.step applies to them inside the full model
 __device__ __forceinline__ void gx_world_dof(const GxTreeModel& m, float M, float& q, float& v) {
@@ -74,7 +110,7 @@ __device__ __forceinline__ void gx_world_dof(const GxTreeModel& m, float M, floa
   q = gx_fma(m.dt, v, q);
 }
 
-template <int MODE, bool AUTORESET, bool MSH>
+template <int MODE, bool AUTORESET, bool MSH>   // MSH: mass matrix in shared memory too
 __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_params p, const GxState s,
                                                      const GxTreeDev a, const float* __restrict__ pool,
                                                      const float* __restrict__ layout,
@@ -94,13 +130,15 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
   const int W = a.nq + 2 * a.nv;
   // The observation row is written in place (no staging tile: one 340-byte row per env and per multi-ms step).
   float* row = obs + (size_t)i * p.obs_dim;
-  // matrix scratch (M, H packed, solve operand, staged constraint row): shared memory (element k of this
-  // thread at sm[k * blockDim.x]) -- every load of the factorisation is on the dependent chain, and a
-  // shared-memory round trip is a fifth of an L2 one.  Doggo: 418 floats per env, 53.5 KB per 32-env block,
-  // four blocks per SM.  MSH = false keeps it in the global scratch (kept for A/B measurements).
-  // (MSH is a template parameter so that the shared-memory build addresses it with LDS / STS.)
-  float* sm = MSH ? gx_smem + threadIdx.x : a.scratch + (size_t)GXT_SIZE * cap + i;
-  const size_t ms = MSH ? (size_t)blockDim.x : cap;
+  // matrix scratch (Hessian / Cholesky workspace, solve operand, staged constraint row): shared memory, element k
+  // of this thread at sm[k * blockDim.x] -- every load of the factorisation is on a dependent chain, and a
+  // shared-memory round trip is a fifth of an L2 one.  The packed mass matrix sits behind it (MSH: Doggo 418
+  // floats per env, 53.5 KB per 32-env block, four blocks per SM) or in the global scratch (228 floats, seven
+  // blocks per SM: its loads are independent, so batches that fill the machine trade them for occupancy).
+  float* sm = gx_smem + threadIdx.x;
+  const size_t ms = blockDim.x;
+  float* mm = MSH ? sm + (size_t)GXT_MOFF(a.nv) * ms : a.scratch + (size_t)GXT_SIZE * cap + i;
+  const size_t mms = MSH ? ms : cap;
 
   if (MODE == GX_ART_RESET_DONE) {
     if (obs_in != obs) {
@@ -119,6 +157,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
     float* v2 = q2 + (size_t)a.nq * cap;
     float* w2 = v2 + (size_t)a.nv * cap;
     float* wv = a.tw + i;
+    float* zh = a.tw + (size_t)m.nworld * cap + i;   // z history of ego_vel_acc
     float* sc = a.scratch + i;
     const float4 c2 = s.d2[i];
     float prev_dist = c2.x;
@@ -180,11 +219,17 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK ^ 1u);
       place(lay, q, v);
       for (int k = 0; k < m.nv; ++k) w[(size_t)k * cap] = 0.0f;     // mjx_reset starts from the pristine mjx_data
-      gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, true, q, v, w, sn, nullptr);
+      gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, mm, mms, true, q, v, w, sn, nullptr);
       GxTreeObs o = gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q, v, cap, row, nullptr);
       prev_dist = o.dist_goal;
       steps = 0.0f;
       if (s.ep) s.ep[i] = make_float4(0.f, 0.f, 0.f, s.ep[i].w);
+      if ((p.off_vel >= 0) | (p.off_acc >= 0)) {   // Engine._data.xpos <- reset pose; _last_data stays
+        float4 h = s.hx[i];
+        h.x = sn.pos[0]; h.y = sn.pos[1];
+        s.hx[i] = h;
+        zh[0] = sn.pos[2];
+      }
     } else if (MODE == GX_ART_RESET_DONE) {
       if (was_done > 0.0f) {
         const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK);
@@ -192,7 +237,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         // throw-away step(s) on a scratch copy: the state keeps the un-stepped pose and the stale warm start
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);
@@ -208,12 +253,13 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       for (int k = 0; k < p.substeps; ++k) {
         gpre_x = goal.x; gpre_y = goal.y;
         for (int h = 0; h < 2 * p.nh; ++h) hpre[h] = hz[h];
-        gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, false, q, v, w, sn, nullptr);
+        gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, mm, mms, false, q, v, w, sn, nullptr);
         advance_world();
       }
       if (qacc_out) for (int k = 0; k < m.nv; ++k) qacc_out[(size_t)i * m.nv + k] = w[(size_t)k * cap];
       int32_t* aux_row = aux ? aux + (size_t)i * p.aux_dim : nullptr;
       GxTreeObs o = gx_tree_obs_row(p, s, m, i, gpre_x, gpre_y, hpre, sn, ctrl, q, v, cap, row, aux_row);
+      if ((p.off_vel >= 0) | (p.off_acc >= 0)) o.bad |= gx_vel_acc3(p, s, zh, cap, i, sn, last_done, row);
       const float dist = o.dist_goal;
       const float last = last_done > 0.0f ? dist : last_dist;
       const float d_dist = last - dist;
@@ -237,7 +283,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         for (int k = 0; k < m.nu; ++k) ctrl[k] = 0.0f;
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);

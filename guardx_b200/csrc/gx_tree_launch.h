@@ -13,8 +13,8 @@ struct GxState;
 struct GxTreeDev {
   const GxTreeModel* m;
   float* tq;       // [2 * (nq + 2 nv), cap]
-  float* tw;       // [nworld, cap] goal / hazard slide velocities
-  float* scratch;  // [GXT_SIZE + GXT_SM_FLOATS, cap]
+  float* tw;       // [nworld + 2, cap] goal / hazard slide velocities, z history of ego_vel_acc
+  float* scratch;  // [GXT_SIZE + packed mass matrix, cap]
   int nq, nv, nu;
 };
 

@@ -59,7 +59,7 @@ class ArtOracleEngine:
         self.last_data = None
         # history read by ego_vel_acc (engine.py:902-929): xpos of Engine._data / _last_data, _last_done, and how
         # many of _last_done / _last_last_done are not None yet (update_data, engine.py:426-431)
-        self.hx_data = np.zeros((n, 2), np.float32); self.hx_last = np.zeros((n, 2), np.float32)
+        self.hx_data = np.zeros((n, 3), np.float32); self.hx_last = np.zeros((n, 3), np.float32)
         self.h_last_done = np.zeros(n, np.float32); self.h_depth = 0
 
     # layout rows: goal xy, robot xy, hazard0 xy, ... (same as guardx.h)
@@ -137,7 +137,7 @@ class ArtOracleEngine:
         self.steps[:] = 0
         self._obs = obs
         self.last_data = d
-        self.hx_data = d['xpos'][:, self.robot_body, :2].astype(np.float32)   # Engine._data <- reset data; _last_data stays
+        self.hx_data = d['xpos'][:, self.robot_body, :3].astype(np.float32)   # Engine._data <- reset data; _last_data stays
         return obs
 
     def step(self, action):
@@ -149,14 +149,16 @@ class ArtOracleEngine:
             self.qpos, self.qvel, d = mx.step(self.mm, self.qpos, self.qvel, self.ctrl, self.warm)
             self.warm = d['qacc'].copy()
         vel = acc = None
-        xp = d['xpos'][:, self.robot_body, :2].astype(np.float32)
-        if self.with_vel or self.with_acc:
+        xp = d['xpos'][:, self.robot_body, :3].astype(np.float32)
+        if (self.with_vel or self.with_acc) and self.free_root:
+            vel, acc = self._vel_acc3(d['xmat'][:, self.robot_body].astype(np.float32).reshape(-1, 3, 3), xp)
+        elif self.with_vel or self.with_acc:
             # update_data: _last_last_data <- _last_data <- _data, same for done (engine.py:426-430)
             vel = np.zeros((self.n, 2), np.float32); acc = np.zeros((self.n, 2), np.float32)
             xm = d['xmat'][:, self.robot_body].astype(np.float32).reshape(-1, 9)
             cfg = C.byref(self.gx_config)
             for i in range(self.n):
-                cur, la, ll = (np.ascontiguousarray(a) for a in (xp[i], self.hx_data[i], self.hx_last[i]))
+                cur, la, ll = (np.ascontiguousarray(a[:2]) for a in (xp[i], self.hx_data[i], self.hx_last[i]))
                 v2, a2 = np.zeros(2, np.float32), np.zeros(2, np.float32)
                 self.L.gxo_piece_vel_acc(cfg, _p(np.ascontiguousarray(xm[i])), _p(cur), _p(la), _p(ll), C.c_int(self.h_depth),
                                          C.c_float(float(self.done[i])), C.c_float(float(self.h_last_done[i])), _p(v2), _p(a2))
@@ -181,6 +183,22 @@ class ArtOracleEngine:
         self.last_data = d
         info = dict(cost=cost, qacc=d['qacc'][:, :self.nv_robot].astype(np.float32), dist=dist, d_dist=d_dist, **extra)
         return obs, reward, done, info
+
+    def _vel_acc3(self, xmat, cur):
+        """ego_vel_acc (engine.py:902-929) for a free-joint root: all three components of xpos, full xmat; fp32."""
+        f = np.float32
+        dt = f(float(self.gx_config.opt_timestep) * self.substeps)
+        pl, pll = cur, cur
+        if self.h_depth >= 1:                                   # last_done is not None
+            pl = np.where((self.done > 0)[:, None], cur, self.hx_data)
+            if self.h_depth >= 2:                               # last_last_done is not None
+                pll = np.where((self.h_last_done + self.done > 0)[:, None], pl, self.hx_last)
+        vw = ((cur - pl) / dt).astype(f)
+        lv = ((pl - pll) / dt).astype(f)
+        aw = ((vw - lv) / dt).astype(f)
+        vel = np.einsum('nk,nkj->nj', vw, xmat).astype(f)[:, :2]
+        acc = np.einsum('nk,nkj->nj', aw, xmat).astype(f)[:, :2]
+        return vel, acc
 
     def reset_done(self, layout):
         """Engine.reset_done + mjx_reset_done (engine.py:497-505, 702-731)."""

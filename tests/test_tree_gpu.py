@@ -145,3 +145,37 @@ def test_ant_through_the_general_tree_kernels_equals_the_leg_per_lane_kernels(mo
         close(cpu(rdc[2]), cpu(ia['cost']), 2e-4, 0, f'step {t} cost')
         assert torch.equal(rdc[1], da)
     lib.gx_destroy(h)
+
+
+def test_observe_vel_acc_for_doggo_uses_the_full_3d_pose(mods):
+    """ego_vel_acc (engine.py:902-929) for a free-joint root: finite differences of all three xpos
+    components, rotated by the full xmat (the falling, tilting torso mixes z in); done masking and the
+    None-ness of the first two steps as for the other robots; obs = acc | default | vel."""
+    Engine, Oracle, pool = mods
+    n = 16
+    cfg = {'env_num': n, 'robot_base': 'xmls/doggo.xml', 'num_steps': 6, '_seed': 2, 'observe_vel': True, 'observe_acc': True}
+    g, o = Engine(dict(cfg)), Oracle(dict(cfg), dtype=np.float64)
+    assert g.observation_space.shape == (4 + NU + 34 + NQ + NV,)
+    lay = pool[:n]
+    close(cpu(g.reset(lay)), o.reset(lay), 2e-6, 2e-6, 'reset obs (vel = acc = 0)')
+    rng = np.random.default_rng(5)
+    seen_done, zmix = 0, 0.0
+    k0, k1 = 2, 2 + NU + 34 + NQ
+    for t in range(16):
+        a = rng.uniform(-1.2, 1.2, (n, NU)).astype(np.float32)
+        o.round_state_to_fp32()
+        g.set_state(o.get_state())          # joint state injected; the xpos history evolves on each side
+        og, rg, dg, ig = g.step(torch.from_numpy(a).cuda())
+        oo, ro, do, io = o.step(a)
+        og = cpu(og)
+        close(og[:, k0:k1], oo[:, k0:k1], 5e-5, 5e-5, f'step {t} default part')
+        close(og[:, -2:], oo[:, -2:], 5e-4, 1e-4, f'step {t} vel')          # d(xpos)/dt, dt = 0.01... of fp32 positions
+        close(og[:, :2], oo[:, :2], 5e-2, 1e-3, f'step {t} acc')            # second difference / dt^2
+        assert (cpu(dg) == do).all()
+        seen_done += int(do.sum())
+        zmix = max(zmix, float(np.abs(io['xmat'].reshape(-1, 3, 3)[:, 2, :2]).max()))
+        if do.any():
+            g.set_state(o.get_state())
+            l2 = pool[n * (1 + t % 3):n * (2 + t % 3)]
+            close(cpu(g.reset_done(l2))[:, k0:k1], o.reset_done(l2)[:, k0:k1], 5e-5, 5e-5, 'reset_done obs')
+    assert seen_done >= n and np.abs(oo[:, -2:]).max() > 1e-3 and zmix > 1e-3   # the z row of xmat really took part
