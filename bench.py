@@ -20,7 +20,7 @@ One JSON line on stdout (rank 0).  Keys beyond the driver's contract:
                 e2e.per_step_sync is the blocking one-call-per-step variant
   rollout       the fused multi-step kernel (gx_rollout): T steps per launch,
                 state in registers, vs its own 192-byte I/O-only roofline
-  legged        Goal_Ant_8Hazards, 65536 envs sharded over the ranks (BASELINE configs[3]),
+  legged        Goal_Ant_8Hazards (and legged.doggo: Goal_Doggo_8Hazards), 65536 envs sharded over the ranks (BASELINE configs[3]),
                 the articulated step kernel (leg-per-lane mjx.step with a Newton contact solver)
   sweep         (N=1 only) step-kernel GB/s at larger batches, to show where the
                 kernel sits against the roofline once launch latency is amortised
@@ -459,6 +459,34 @@ def main():
                   "bound": "issue/latency (Newton contact solver per env, ~1.9 k warp-instructions per env-step), "
                            "not HBM", "finite": bool(torch.isfinite(lo['obs']).all().item())}
         del aenv, lo
+        torch.cuda.empty_cache()
+        # Doggo (general-tree kernels): same protocol, 65536 envs in total, steady state (the robot has landed)
+        n_dog, Td = 65536 // world, 10
+        denv = Engine({'env_num': n_dog, 'robot_base': 'xmls/doggo.xml', 'num_steps': 1000, '_seed': 0},
+                      env_id_offset=rank * n_dog)
+        denv.reset()
+        do_ = denv.rollout(Td)
+        for _ in range(3):        # 40 steps: contacts established
+            lib.gx_rollout(denv._h, Td, pr(do_['obs']), pr(do_['act']), pr(do_['reward']), pr(do_['cost']), pr(do_['done']), sp)
+        torch.cuda.synchronize()
+        if barrier:
+            barrier()
+        ev0.record(stream)
+        rc = lib.gx_rollout(denv._h, Td, pr(do_['obs']), pr(do_['act']), pr(do_['reward']), pr(do_['cost']), pr(do_['done']), sp)
+        assert rc == 0, lib.gx_last_error()
+        ev1.record(stream)
+        torch.cuda.synchronize()
+        dt_dog = ev0.elapsed_time(ev1) * 1e-3
+        if dist:
+            t = torch.tensor([dt_dog], device='cuda', dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_dog = float(t.item())
+        legged["doggo"] = {"workload": "Goal_Doggo_8Hazards, 65536 envs in total, same protocol (free-joint root, capsule "
+                                       "contacts, dense Newton per env: one thread per env)",
+                           "envs_per_gpu": n_dog, "steps": Td, "value": world * n_dog * Td / dt_dog, "unit": "env-steps/s",
+                           "us_per_step": 1e6 * dt_dog / Td, "bound": "dependent-issue latency (DESIGN.md 5b), not HBM",
+                           "finite": bool(torch.isfinite(do_['obs']).all().item())}
+        del denv, do_
         torch.cuda.empty_cache()
     clocks = sampler.stop()
 
