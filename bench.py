@@ -297,6 +297,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # stdout carries the JSON line only: NCCL's own banner (NCCL_DEBUG=VERSION / INFO on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

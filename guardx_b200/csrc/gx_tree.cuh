@@ -46,7 +46,8 @@ enum {
   GXT_MV = GXT_G + GX_TREE_MAXV,
   GXT_FC = GXT_MV + GX_TREE_MAXV,                 // qfrc_constraint
   GXT_T = GXT_FC + GX_TREE_MAXV,                  // temp vector
-  GXT_SIZE = GXT_T + GX_TREE_MAXV
+  GXT_AL = GXT_T + GX_TREE_MAXV,                  // compact list of the active rows (indices)
+  GXT_SIZE = GXT_AL + GX_TREE_NROW
 };
 
 struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forward pass (pre-step pose)
@@ -61,7 +62,8 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 // (sized by the model, not by GX_TREE_MAXV).  M is addressed through its own pointer / stride (`mm`, `mms`):
 // behind JR in the same scratch, or in global memory when the launch trades M's latency for occupancy.
 #define GXT_XS (tri)                  /* operand vector of the solves, of M*x and of J*x */
-#define GXT_JR (tri + nv)             /* one constraint row staged for the Hessian update */
+#define GXT_JR (tri + nv)             /* qfrc_constraint (accumulated row by row) */
+#define FCS(i) sm[(size_t)(GXT_JR + (i)) * ms]
 #define GXT_MOFF(nv) ((nv) * ((nv) + 1) / 2 + 2 * (nv))
 #define GXT_SM_FLOATS_OF(nv, with_m) ((nv) * ((nv) + 1) / 2 * ((with_m) ? 2 : 1) + 2 * (nv))
 #define GXT_SM_FLOATS GXT_SM_FLOATS_OF(GX_TREE_MAXV, 1)
@@ -76,24 +78,51 @@ GX_HD void gxt_put(float* sc, size_t stride, int off, int n, const float* in) {
   for (int k = 0; k < n; ++k) TS(off + k) = in[k];
 }
 
-// s - sum_k a[k] b[k], k ascending; elements `ms` apart.  Pointer walks instead of packed-index
-// arithmetic: the factorisation is a third of the kernel's instructions.
+// s - sum_k a[k] b[k]; elements `ms` apart.  Two accumulators (even / odd k): with one or two warps per
+// scheduler the kernel runs at the latency of its dependent chains, so the inner products are written for
+// instruction-level parallelism -- independent chains, loads of a batch issued before its FMAs.
 GX_HD float gxt_dotsub(const float* a, const float* b, size_t ms, int n, float s) {
-#pragma unroll 4
-  for (int k = 0; k < n; ++k) s = gx_fma(-a[(size_t)k * ms], b[(size_t)k * ms], s);
-  return s;
+  float s1 = 0.f;
+  int k = 0;
+  for (; k + 1 < n; k += 2) {
+    const float a0 = a[(size_t)k * ms], a1 = a[(size_t)(k + 1) * ms];
+    const float b0 = b[(size_t)k * ms], b1 = b[(size_t)(k + 1) * ms];
+    s = gx_fma(-a0, b0, s);
+    s1 = gx_fma(-a1, b1, s1);
+  }
+  if (k < n) s = gx_fma(-a[(size_t)k * ms], b[(size_t)k * ms], s);
+  return s + s1;
 }
-// in-place Cholesky of the packed lower triangle H (n x n), inverse diagonal stored
+// in-place Cholesky of the packed lower triangle H (n x n) at sm, inverse diagonal stored.  Left-looking,
+// two rows at a time (they share the loads of row j), two accumulators per row.
 GX_HD void gxt_chol(float* sm, size_t ms, int n) {
   float* rj = sm;                                          // row j of H
   for (int j = 0; j < n; ++j) {
     const float inv = gx_rsqrt(gxt_dotsub(rj, rj, ms, j, rj[(size_t)j * ms]));
     rj[(size_t)j * ms] = inv;
     float* ri = rj + (size_t)(j + 1) * ms;                 // row i = j + 1 ...
-    for (int i = j + 1; i < n; ++i) {
-      ri[(size_t)j * ms] = gxt_dotsub(ri, rj, ms, j, ri[(size_t)j * ms]) * inv;
-      ri += (size_t)(i + 1) * ms;
+    int i = j + 1;
+    for (; i + 1 < n; i += 2) {
+      float* r2 = ri + (size_t)(i + 1) * ms;               // row i + 1
+      float a0 = ri[(size_t)j * ms], a1 = 0.f, b0 = r2[(size_t)j * ms], b1 = 0.f;
+      int k = 0;
+      for (; k + 1 < j; k += 2) {
+        const float l0 = rj[(size_t)k * ms], l1 = rj[(size_t)(k + 1) * ms];
+        const float x0 = ri[(size_t)k * ms], x1 = ri[(size_t)(k + 1) * ms];
+        const float y0 = r2[(size_t)k * ms], y1 = r2[(size_t)(k + 1) * ms];
+        a0 = gx_fma(-x0, l0, a0); a1 = gx_fma(-x1, l1, a1);
+        b0 = gx_fma(-y0, l0, b0); b1 = gx_fma(-y1, l1, b1);
+      }
+      if (k < j) {
+        const float l0 = rj[(size_t)k * ms];
+        a0 = gx_fma(-ri[(size_t)k * ms], l0, a0);
+        b0 = gx_fma(-r2[(size_t)k * ms], l0, b0);
+      }
+      ri[(size_t)j * ms] = (a0 + a1) * inv;
+      r2[(size_t)j * ms] = (b0 + b1) * inv;
+      ri = r2 + (size_t)(i + 2) * ms;
     }
+    if (i < n) ri[(size_t)j * ms] = gxt_dotsub(ri, rj, ms, j, ri[(size_t)j * ms]) * inv;
     rj += (size_t)(j + 1) * ms;
   }
 }
@@ -108,54 +137,61 @@ GX_HD void gxt_chol_solve(float* sm, size_t ms, int n) {
     ri += (size_t)(i + 1) * ms;
   }
   for (int i = n - 1; i >= 0; --i) {
-    float s = x[(size_t)i * ms];
+    float s = x[(size_t)i * ms], s1 = 0.f;
     const float* dg = H + (size_t)(i * (i + 1) / 2 + i) * ms;   // H(i, i)
     const float* p = dg + (size_t)(i + 1) * ms;                 // H(i + 1, i)
-#pragma unroll 4
-    for (int k = i + 1; k < n; ++k) { s = gx_fma(-*p, x[(size_t)k * ms], s); p += (size_t)(k + 1) * ms; }
-    x[(size_t)i * ms] = s * *dg;
+    int k = i + 1;
+    for (; k + 1 < n; k += 2) {
+      const float* p1 = p + (size_t)(k + 1) * ms;               // H(k + 1, i)
+      const float h0 = *p, h1 = *p1;
+      s = gx_fma(-h0, x[(size_t)k * ms], s);
+      s1 = gx_fma(-h1, x[(size_t)(k + 1) * ms], s1);
+      p = p1 + (size_t)(k + 2) * ms;
+    }
+    if (k < n) s = gx_fma(-*p, x[(size_t)k * ms], s);
+    x[(size_t)i * ms] = (s + s1) * *dg;
   }
 }
-// s + sum_i a[i] x[i], i ascending; a: a constraint row in the global scratch, x: matrix scratch.  The loads of a
-// batch are issued together (they are independent; one at a time each costs an L2 round trip).
+// One constraint row (global scratch) into registers: every load is in flight before the first use, so a row
+// costs ONE L2 round trip (loaded a few elements at a time each batch paid its own ~400 cycles; the ncu source
+// page showed the first FMA after each batch as the hottest instructions of the kernel).  Compile-time indices.
+GX_HD void gxt_row_load(const float* a, size_t stride, int n, float (&row)[GX_TREE_MAXV]) {
+#pragma unroll
+  for (int i = 0; i < GX_TREE_MAXV; ++i) row[i] = i < n ? a[(size_t)i * stride] : 0.f;
+}
+// s + sum_i a[i] x[i]; a: a constraint row in the global scratch, x: matrix scratch
 GX_HD float gxt_rowdot(const float* a, size_t stride, const float* x, size_t ms, int n, float s) {
-  for (int i = 0; i < n; i += 4) {
-    const float a0 = a[(size_t)i * stride];
-    const float a1 = i + 1 < n ? a[(size_t)(i + 1) * stride] : 0.f;
-    const float a2 = i + 2 < n ? a[(size_t)(i + 2) * stride] : 0.f;
-    const float a3 = i + 3 < n ? a[(size_t)(i + 3) * stride] : 0.f;
-    s = gx_fma(a0, x[(size_t)i * ms], s);
-    if (i + 1 < n) s = gx_fma(a1, x[(size_t)(i + 1) * ms], s);
-    if (i + 2 < n) s = gx_fma(a2, x[(size_t)(i + 2) * ms], s);
-    if (i + 3 < n) s = gx_fma(a3, x[(size_t)(i + 3) * ms], s);
+  float row[GX_TREE_MAXV], s1 = 0.f;
+  gxt_row_load(a, stride, n, row);
+#pragma unroll
+  for (int i = 0; i < GX_TREE_MAXV; i += 2) {
+    if (i < n) s = gx_fma(row[i], x[(size_t)i * ms], s);
+    if (i + 1 < n) s1 = gx_fma(row[i + 1], x[(size_t)(i + 1) * ms], s1);
   }
-  return s;
-}
-// sum_r a[r * pitch] f[r], r ascending (one column of J^T f); same batching
-GX_HD float gxt_coldot(const float* a, size_t pitch, const float* f, size_t stride, int n) {
-  float s = 0.f;
-  for (int r = 0; r < n; r += 4) {
-    const float a0 = a[(size_t)r * pitch], f0 = f[(size_t)r * stride];
-    const float a1 = r + 1 < n ? a[(size_t)(r + 1) * pitch] : 0.f, f1 = r + 1 < n ? f[(size_t)(r + 1) * stride] : 0.f;
-    const float a2 = r + 2 < n ? a[(size_t)(r + 2) * pitch] : 0.f, f2 = r + 2 < n ? f[(size_t)(r + 2) * stride] : 0.f;
-    const float a3 = r + 3 < n ? a[(size_t)(r + 3) * pitch] : 0.f, f3 = r + 3 < n ? f[(size_t)(r + 3) * stride] : 0.f;
-    s = gx_fma(a0, f0, s);
-    if (r + 1 < n) s = gx_fma(a1, f1, s);
-    if (r + 2 < n) s = gx_fma(a2, f2, s);
-    if (r + 3 < n) s = gx_fma(a3, f3, s);
-  }
-  return s;
+  return s + s1;
 }
 // row i of the symmetric packed matrix A (stride as) times x (stride ms), j ascending
 GX_HD float gxt_symrow(const float* A, size_t as, const float* x, size_t ms, int n, int i) {
   const float* r = A + (size_t)(i * (i + 1) / 2) * as;
-  float s = 0.f;
-#pragma unroll 4
-  for (int j = 0; j <= i; ++j) s = gx_fma(r[(size_t)j * as], x[(size_t)j * ms], s);
+  float s = 0.f, s1 = 0.f;
+  int j = 0;
+  for (; j + 1 <= i; j += 2) {
+    const float a0 = r[(size_t)j * as], a1 = r[(size_t)(j + 1) * as];
+    s = gx_fma(a0, x[(size_t)j * ms], s);
+    s1 = gx_fma(a1, x[(size_t)(j + 1) * ms], s1);
+  }
+  if (j <= i) s = gx_fma(r[(size_t)j * as], x[(size_t)j * ms], s);
   const float* p = r + (size_t)(2 * i + 1) * as;               // A(i + 1, i)
-#pragma unroll 4
-  for (int j = i + 1; j < n; ++j) { s = gx_fma(*p, x[(size_t)j * ms], s); p += (size_t)(j + 1) * as; }
-  return s;
+  j = i + 1;
+  for (; j + 1 < n; j += 2) {
+    const float* p1 = p + (size_t)(j + 1) * as;
+    const float a0 = *p, a1 = *p1;
+    s = gx_fma(a0, x[(size_t)j * ms], s);
+    s1 = gx_fma(a1, x[(size_t)(j + 1) * ms], s1);
+    p = p1 + (size_t)(j + 2) * as;
+  }
+  if (j < n) s = gx_fma(*p, x[(size_t)j * ms], s);
+  return s + s1;
 }
 // H := M (packed triangles), loads in batches of 4
 GX_HD void gxt_copy_tri(const float* mm, size_t mms, float* sm, size_t ms, int tri) {
@@ -503,7 +539,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
   }
   // ---------------- solver.solve: Newton on the primal cost (dense) ----------------
   int iters = 0;
-  for (int i = 0; i < nv; ++i) { TS(GXT_QA + i) = TS(GXT_AS + i); TS(GXT_FC + i) = 0.f; }
+  for (int i = 0; i < nv; ++i) { TS(GXT_QA + i) = TS(GXT_AS + i); FCS(i) = 0.f; }
   if (nrow > 0) {
     // cost of a candidate (and its M*qacc, J*qacc - aref): 0 = smooth, 1 = warm start
     float cost_s = 0.f;
@@ -530,61 +566,65 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
     for (int trip = 0; trip < m.max_iter + 2; ++trip) {
       // forces and gradient at the current point
       float gn = 0.f;
-      for (int r = 0; r < nrow; ++r) {          // row forces (0 on inactive rows), parked in the J*search slot
-        const float jr = TS(GXT_RJ + r);
-        TS(GXT_RV + r) = jr < 0.0f ? -TS(GXT_RD + r) * jr : 0.0f;
+      // active rows (J qacc - aref < 0): compact index list, then qfrc_constraint = J^T f row by row
+      int nact = 0;
+      for (int r = 0; r < nrow; r += 4) {
+        const float j0 = TS(GXT_RJ + r);
+        const float j1 = r + 1 < nrow ? TS(GXT_RJ + r + 1) : 0.f;
+        const float j2 = r + 2 < nrow ? TS(GXT_RJ + r + 2) : 0.f;
+        const float j3 = r + 3 < nrow ? TS(GXT_RJ + r + 3) : 0.f;
+        if (j0 < 0.0f) { TS(GXT_AL + nact) = (float)r; ++nact; }
+        if (j1 < 0.0f) { TS(GXT_AL + nact) = (float)(r + 1); ++nact; }
+        if (j2 < 0.0f) { TS(GXT_AL + nact) = (float)(r + 2); ++nact; }
+        if (j3 < 0.0f) { TS(GXT_AL + nact) = (float)(r + 3); ++nact; }
+      }
+      for (int i = 0; i < nv; ++i) FCS(i) = 0.f;
+      for (int k = 0; k < nact; ++k) {
+        const int r = (int)TS(GXT_AL + k);
+        float row[GX_TREE_MAXV];
+        gxt_row_load(&TS(GXT_J + r * P), stride, nv, row);
+        const float force = -TS(GXT_RD + r) * TS(GXT_RJ + r);
+#pragma unroll
+        for (int i = 0; i < GX_TREE_MAXV; ++i) if (i < nv) FCS(i) = gx_fma(row[i], force, FCS(i));
       }
       for (int i = 0; i < nv; ++i) {
-        const float fc = gxt_coldot(&TS(GXT_J + i), (size_t)P * stride, &TS(GXT_RV), stride, nrow);
-        TS(GXT_FC + i) = fc;
-        const float g = fc - (TS(GXT_MA + i) - TS(GXT_FS + i));   // -gradient
-        TS(GXT_G + i) = g;
+        const float g = FCS(i) - (TS(GXT_MA + i) - TS(GXT_FS + i));   // -gradient
+        XS(i) = g;                                                    // right-hand side of the Newton solve
         gn = gx_fma(g, g, gn);
       }
       if (finish || !(gx_sqrt(gn) >= m.tol_scale) || iters >= m.max_iter) break;
       // H = M + J^T D J over the active rows; search = H^-1 (-grad)
       gxt_copy_tri(mm, mms, sm, ms, tri);
-      for (int r = 0; r < nrow; ++r) {
-        if (!(TS(GXT_RJ + r) < 0.0f)) continue;
+      for (int k = 0; k < nact; ++k) {
+        const int r = (int)TS(GXT_AL + k);
+        float row[GX_TREE_MAXV];
+        gxt_row_load(&TS(GXT_J + r * P), stride, nv, row);
         const float Dr = TS(GXT_RD + r);
-        for (int i = 0; i < nv; i += 4) {         // stage the row: batched loads
-          const float a0 = TS(GXT_J + r * P + i);
-          const float a1 = i + 1 < nv ? TS(GXT_J + r * P + i + 1) : 0.f;
-          const float a2 = i + 2 < nv ? TS(GXT_J + r * P + i + 2) : 0.f;
-          const float a3 = i + 3 < nv ? TS(GXT_J + r * P + i + 3) : 0.f;
-          sm[(size_t)(GXT_JR + i) * ms] = a0;
-          if (i + 1 < nv) sm[(size_t)(GXT_JR + i + 1) * ms] = a1;
-          if (i + 2 < nv) sm[(size_t)(GXT_JR + i + 2) * ms] = a2;
-          if (i + 3 < nv) sm[(size_t)(GXT_JR + i + 3) * ms] = a3;
-        }
-        const float* jrow = sm + (size_t)GXT_JR * ms;
-        float* hrow = sm;
-        for (int i = 0; i < nv; ++i) {
-          const float di = Dr * jrow[(size_t)i * ms];
-          if (di != 0.0f) {
-#pragma unroll 4
-            for (int j = 0; j <= i; ++j) hrow[(size_t)j * ms] = gx_fma(di, jrow[(size_t)j * ms], hrow[(size_t)j * ms]);
+#pragma unroll
+        for (int i = 0; i < GX_TREE_MAXV; ++i) {
+          if (i < nv) {
+            const float di = Dr * row[i];
+            if (di != 0.0f) {
+              float* hrow = sm + (size_t)(i * (i + 1) / 2) * ms;
+#pragma unroll
+              for (int j = 0; j <= i; ++j) hrow[(size_t)j * ms] = gx_fma(di, row[j], hrow[(size_t)j * ms]);
+            }
           }
-          hrow += (size_t)(i + 1) * ms;
         }
       }
-      for (int i = 0; i < nv; ++i) XS(i) = TS(GXT_G + i);
       gxt_chol(sm, ms, nv);
       gxt_chol_solve(sm, ms, nv);
-      for (int i = 0; i < nv; ++i) TS(GXT_G + i) = XS(i);
       // line-search quadratics
       float g0 = 0.f, h0 = 0.f, ssq = 0.f;
       for (int i = 0; i < nv; ++i) {
         const float s = gxt_symrow(mm, mms, sm + (size_t)GXT_XS * ms, ms, nv, i);
         TS(GXT_MV + i) = s;
-        const float si = TS(GXT_G + i);
+        const float si = XS(i);
         g0 = gx_fma(si, TS(GXT_MA + i) - TS(GXT_FS + i), g0);
         h0 = gx_fma(si, s, h0);
         ssq = gx_fma(si, si, ssq);
       }
-      for (int r = 0; r < nrow; ++r) {
-        TS(GXT_RV + r) = gxt_rowdot(&TS(GXT_J + r * P), stride, &XS(0), ms, nv, 0.f);
-      }
+      for (int r = 0; r < nrow; ++r) TS(GXT_RV + r) = gxt_rowdot(&TS(GXT_J + r * P), stride, &XS(0), ms, nv, 0.f);
       float alpha = 0.f, lo = 0.f, hi = 3.0e38f, slope0 = 0.f;
       for (int ls = 0; ls < 40; ++ls) {
         float d1 = gx_fma(alpha, h0, g0), d2 = h0;
@@ -608,7 +648,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       }
       float qq = 0.f;
       for (int i = 0; i < nv; ++i) {
-        const float qa = gx_fma(alpha, TS(GXT_G + i), TS(GXT_QA + i));
+        const float qa = gx_fma(alpha, XS(i), TS(GXT_QA + i));
         TS(GXT_QA + i) = qa;
         TS(GXT_MA + i) = gx_fma(alpha, TS(GXT_MV + i), TS(GXT_MA + i));
         qq = gx_fma(qa, qa, qq);
@@ -626,7 +666,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
   gxt_copy_tri(mm, mms, sm, ms, tri);
   for (int i = 0; i < nv; ++i) {
     HH(i, i) = gx_fma(m.dt, m.dof[i].damping, HH(i, i));
-    XS(i) = TS(GXT_FS + i) + TS(GXT_FC + i);
+    XS(i) = TS(GXT_FS + i) + FCS(i);
   }
   gxt_chol(sm, ms, nv);
   gxt_chol_solve(sm, ms, nv);

@@ -110,7 +110,7 @@ __device__ __forceinline__ void gx_world_dof(const GxTreeModel& m, float M, floa
   q = gx_fma(m.dt, v, q);
 }
 
-template <int MODE, bool AUTORESET, bool MSH>   // MSH: mass matrix in shared memory too
+template <int MODE, bool AUTORESET>
 __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_params p, const GxState s,
                                                      const GxTreeDev a, const float* __restrict__ pool,
                                                      const float* __restrict__ layout,
@@ -130,15 +130,15 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
   const int W = a.nq + 2 * a.nv;
   // The observation row is written in place (no staging tile: one 340-byte row per env and per multi-ms step).
   float* row = obs + (size_t)i * p.obs_dim;
-  // matrix scratch (Hessian / Cholesky workspace, solve operand, staged constraint row): shared memory, element k
-  // of this thread at sm[k * blockDim.x] -- every load of the factorisation is on a dependent chain, and a
-  // shared-memory round trip is a fifth of an L2 one.  The packed mass matrix sits behind it (MSH: Doggo 418
-  // floats per env, 53.5 KB per 32-env block, four blocks per SM) or in the global scratch (228 floats, seven
-  // blocks per SM: its loads are independent, so batches that fill the machine trade them for occupancy).
+  // matrix scratch (Hessian / Cholesky workspace, solve operand, qfrc_constraint, packed mass matrix): shared
+  // memory, element k of this thread at sm[k * blockDim.x] -- every load of the factorisation is on a dependent
+  // chain, and a shared-memory round trip is a fifth of an L2 one.  Doggo: 418 floats per env, 53.5 KB per 32-env
+  // block, four blocks per SM.  (Leaving M in the global scratch -- 7 blocks per SM -- measured slower once the
+  // constraint rows went through registers: gx_tree_step takes M's pointer / stride separately for that experiment.)
   float* sm = gx_smem + threadIdx.x;
   const size_t ms = blockDim.x;
-  float* mm = MSH ? sm + (size_t)GXT_MOFF(a.nv) * ms : a.scratch + (size_t)GXT_SIZE * cap + i;
-  const size_t mms = MSH ? ms : cap;
+  float* mm = sm + (size_t)GXT_MOFF(a.nv) * ms;
+  const size_t mms = ms;
 
   if (MODE == GX_ART_RESET_DONE) {
     if (obs_in != obs) {
@@ -293,45 +293,6 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
     s.d2[i] = make_float4(prev_dist, was_done > 0.0f ? -steps : steps, __uint_as_float((uint32_t)age),
                           __uint_as_float((uint32_t)(age >> 32)));
   }
-}
-
-// ---- state injection / checkpoint: one row per env =
-//      qpos[nq] qvel[nv] qacc_warmstart[nv] prev_dist prev_done steps goal[2] hazards[2*nh] world_vel[2+2*nh]
-__global__ void gx_tree_get_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxTreeDev a, float* out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
-  float* o = out + (size_t)i * p.state_dim;
-  const size_t cap = (size_t)s.cap;
-  const int W = a.nq + 2 * a.nv;
-  for (int k = 0; k < W; ++k) o[k] = a.tq[(size_t)k * cap + i];
-  o += W;
-  const float4 c = s.d2[i];
-  o[0] = c.x; o[1] = (__float_as_uint(c.y) >> 31) ? 1.0f : 0.0f; o[2] = fabsf(c.y);
-  const float2 g = s.goal[i];
-  o[3] = g.x; o[4] = g.y;
-  for (int h = 0; h < p.nh; ++h) gx_art_hazard(s, nullptr, i, h, o[5 + 2 * h], o[6 + 2 * h]);
-  for (int k = 0; k < 2 + 2 * p.nh; ++k) o[5 + 2 * p.nh + k] = a.tw[(size_t)k * cap + i];
-}
-
-__global__ void gx_tree_set_state_kernel(const __grid_constant__ gx_params p, const GxState s, const GxTreeDev a, const float* in) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n) return;
-  const float* o = in + (size_t)i * p.state_dim;
-  const size_t cap = (size_t)s.cap;
-  const int W = a.nq + 2 * a.nv;
-  for (int k = 0; k < W; ++k) a.tq[(size_t)k * cap + i] = o[k];
-  o += W;
-  const float4 c = s.d2[i];
-  s.d2[i] = make_float4(o[0], o[1] > 0.0f ? -o[2] : o[2], c.z, c.w);
-  s.goal[i] = make_float2(o[3], o[4]);
-  for (int k = 0; k < s.nh2; ++k) {
-    float4 h;
-    h.x = o[5 + 4 * k]; h.y = o[6 + 4 * k];
-    h.z = (2 * k + 1 < p.nh) ? o[7 + 4 * k] : 0.0f;
-    h.w = (2 * k + 1 < p.nh) ? o[8 + 4 * k] : 0.0f;
-    s.hz[(size_t)k * cap + i] = h;
-  }
-  for (int k = 0; k < 2 + 2 * p.nh; ++k) a.tw[(size_t)k * cap + i] = o[5 + 2 * p.nh + k];
 }
 
 #endif  // GX_TREE_KERNELS_CUH_

@@ -29,6 +29,11 @@ struct GxTreeLaunch {
   cudaStream_t stream;
 };
 cudaError_t gx_tree_launch(const GxTreeLaunch& a);
+// one kernel instantiation per translation unit (gx_tree_k*.cu), so that `make -j` compiles them in parallel
+cudaError_t gx_tree_go_reset(const GxTreeLaunch& a, int grid, int block, size_t sh);
+cudaError_t gx_tree_go_reset_done(const GxTreeLaunch& a, int grid, int block, size_t sh);
+cudaError_t gx_tree_go_step(const GxTreeLaunch& a, int grid, int block, size_t sh);
+cudaError_t gx_tree_go_step_autoreset(const GxTreeLaunch& a, int grid, int block, size_t sh);
 
 void gx_tree_get_state(const gx_params& p, const GxState& s, const GxTreeDev& t, float* out, cudaStream_t st);
 void gx_tree_set_state(const gx_params& p, const GxState& s, const GxTreeDev& t, const float* in, cudaStream_t st);
