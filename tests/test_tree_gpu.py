@@ -179,3 +179,38 @@ def test_observe_vel_acc_for_doggo_uses_the_full_3d_pose(mods):
             l2 = pool[n * (1 + t % 3):n * (2 + t % 3)]
             close(cpu(g.reset_done(l2))[:, k0:k1], o.reset_done(l2)[:, k0:k1], 5e-5, 5e-5, 'reset_done obs')
     assert seen_done >= n and np.abs(oo[:, -2:]).max() > 1e-3 and zmix > 1e-3   # the z row of xmat really took part
+
+
+def test_doggo_host_buffer_paths_and_batch_independence(mods):
+    """Engine.rollout_host (pipelined H2D / kernels / D2H) == T x Engine.step_host for Doggo; and an env's
+    trajectory does not depend on the batch it sits in (first rows of a 2 000-env batch == a 96-env batch,
+    bit for bit: one thread per env, no cross-env arithmetic, results independent of block / SM placement)."""
+    Engine, _, pool = mods
+    n, T = 96, 6
+    cfg = {'env_num': n, 'robot_base': 'xmls/doggo.xml', 'num_steps': 4, '_seed': 8}
+    a_env, b_env = Engine(dict(cfg)), Engine(dict(cfg))
+    a_env.reset(); b_env.reset()
+    od = a_env.obs_flat_size
+    h_act = torch.empty(T, n, NU).uniform_(-1, 1).pin_memory()
+    h_obs = torch.empty(T, n, od).pin_memory()
+    h_r, h_d, h_c = (torch.empty(T, n).pin_memory() for _ in range(3))
+    a_env.rollout_host(h_act, h_obs, h_r, h_d, h_c)
+    h_out = torch.empty(n * (od + 3)).pin_memory()
+    for t in range(T):
+        b_env.step_host(h_act[t], h_out, auto_reset_done=True)
+        assert torch.equal(h_out[:n * od].view(n, od), h_obs[t])
+        assert torch.equal(h_out[n * od + n:n * od + 2 * n], h_d[t])
+    assert torch.isfinite(h_obs).all() and h_d.sum() >= n
+    big = 2000
+    s_env = Engine({'env_num': n, 'robot_base': 'xmls/doggo.xml', 'num_steps': 1000, '_seed': 1})
+    l_env = Engine({'env_num': big, 'robot_base': 'xmls/doggo.xml', 'num_steps': 1000, '_seed': 1})
+    lay_s = pool[:n]
+    lay_l = np.concatenate([lay_s] + [pool[:big - n]], 0)
+    os_, ol = s_env.reset(lay_s), l_env.reset(lay_l)
+    assert torch.equal(os_, ol[:n])
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    for t in range(10):
+        act = torch.empty(big, NU, device='cuda').uniform_(-1, 1, generator=gen)
+        o1, r1, d1, i1 = s_env.step(act[:n].contiguous())
+        o2, r2, d2, i2 = l_env.step(act)
+        assert torch.equal(o1, o2[:n]) and torch.equal(r1, r2[:n]) and torch.equal(i1['cost'], i2['cost'][:n])
