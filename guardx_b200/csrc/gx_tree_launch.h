@@ -30,6 +30,21 @@ struct GxTreeLaunch {
 };
 cudaError_t gx_tree_launch(const GxTreeLaunch& a);
 // one kernel instantiation per translation unit (gx_tree_k*.cu), so that `make -j` compiles them in parallel
+// shared-memory carve-out (percent of the SM array) that fits the blocks one SM will actually hold
+static inline int gx_tree_carveout(int grid, size_t sh) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int per_sm = (grid + sms - 1) / sms;
+  const int fit = (int)((227 * 1024) / (sh + 1024));
+  if (per_sm > fit) per_sm = fit;
+  if (per_sm < 1) per_sm = 1;
+  const int pct = (int)((100 * (size_t)per_sm * (sh + 1024) + 228 * 1024 - 1) / (228 * 1024));
+  return pct > 100 ? 100 : pct;
+}
 cudaError_t gx_tree_go_reset(const GxTreeLaunch& a, int grid, int block, size_t sh);
 cudaError_t gx_tree_go_reset_done(const GxTreeLaunch& a, int grid, int block, size_t sh);
 cudaError_t gx_tree_go_step(const GxTreeLaunch& a, int grid, int block, size_t sh);
