@@ -176,7 +176,7 @@ def reference_arm(args, rank, world):
         "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------ our arm
@@ -269,6 +269,18 @@ class GraphedSteps:
         return ev0.elapsed_time(ev1) * 1e-3
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -279,6 +291,13 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-legged", action="store_true", help="skip the ant / 65536-env measurement")
     args = ap.parse_args()
+
+    # stdout carries the ONE JSON line and nothing else: native libraries (NCCL prints its version banner with
+    # printf on some boxes) get fd 2 while the run lasts; the line itself is written to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -297,8 +316,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # stdout carries the JSON line only: NCCL's own banner (NCCL_DEBUG=VERSION / INFO on some boxes) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -571,7 +588,7 @@ def main():
             line["sweep"] = sweep
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if dist:
         dist.barrier()
         dist.destroy_process_group()
