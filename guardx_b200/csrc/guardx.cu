@@ -881,7 +881,7 @@ static int gx_art_launch(gx_env* e, cudaStream_t st, const float* layout, const 
                          float* obs, float* act_out, float* reward, float* done, float* cost, float* qacc, int32_t* aux = nullptr) {
   if (e->tree_host) {
     GxTreeLaunch t;
-    t.p = &e->p; t.s = &e->s; t.t = &e->tree; t.pool = e->pool; t.layout = layout; t.action = action; t.obs_in = obs_in;
+    t.p = &e->p; t.s = &e->s; t.t = &e->tree; t.host_model = e->tree_host; t.pool = e->pool; t.layout = layout; t.action = action; t.obs_in = obs_in;
     t.obs = obs; t.act_out = act_out; t.reward = reward; t.done = done; t.cost = cost; t.qacc = qacc; t.aux = aux;
     t.stats_on = e->stats_on ? 1 : 0; t.mode = MODE; t.autoreset = AR ? 1 : 0; t.stream = st;
     const cudaError_t err = gx_tree_launch(t);

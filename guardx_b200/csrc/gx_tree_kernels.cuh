@@ -112,7 +112,8 @@ __device__ __forceinline__ void gx_world_dof(const GxTreeModel& m, float M, floa
 
 template <int MODE, bool AUTORESET>
 __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_params p, const GxState s,
-                                                     const GxTreeDev a, const float* __restrict__ pool,
+                                                     const GxTreeDev a, const __grid_constant__ GxTreeModel mdl,
+                                                     const float* __restrict__ pool,
                                                      const float* __restrict__ layout,
                                                      const float* __restrict__ action, const float* obs_in,
                                                      float* obs, float* __restrict__ act_out,
@@ -125,7 +126,9 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
   if (wbase >= p.n) return;
   const int rows = min(32, p.n - wbase);
   const bool live = i < p.n;
-  const GxTreeModel& m = *a.m;
+  // The model travels as a kernel parameter: every read of it is a uniform constant-bank load instead of a global
+  // load that competes with the scratch for the small L1 (the model is read ~2 k times per env-step).
+  const GxTreeModel& m = mdl;
   const size_t cap = (size_t)s.cap;
   const int W = a.nq + 2 * a.nv;
   // The observation row is written in place (no staging tile: one 340-byte row per env and per multi-ms step).

@@ -22,6 +22,7 @@ struct GxTreeLaunch {
   const gx_params* p;
   const GxState* s;
   const GxTreeDev* t;
+  const GxTreeModel* host_model;   // passed to the kernels BY VALUE (11 KB of kernel parameters = constant bank)
   const float *pool, *layout, *action, *obs_in;
   float *obs, *act_out, *reward, *done, *cost, *qacc;
   int32_t* aux;
