@@ -54,13 +54,12 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 
 #define TS(off) sc[(size_t)(off) * stride]
 
-// The mass matrix M and the factorisation workspace H -- the arrays every inner loop of the Cholesky
-// and of the solves walks through with dependent loads -- live in a SEPARATE, small matrix scratch
-// (`sm`, stride `ms`): shared memory in the kernel (an L2 round trip per dependent load made the first
-// version 5 ms per step), lower triangles packed: 2 x 210 floats per env.
-// Layout for a model with nv dofs, tri = nv (nv + 1) / 2:  H [tri] | XS [nv] | JR [nv] ( | M [tri] )
-// (sized by the model, not by GX_TREE_MAXV).  M is addressed through its own pointer / stride (`mm`, `mms`):
-// behind JR in the same scratch, or in global memory when the launch trades M's latency for occupancy.
+// The arrays every inner loop of the Cholesky, of the solves and of the Hessian update walks through with
+// dependent loads live in a SEPARATE, small matrix scratch (`sm`, stride `ms`): shared memory in the kernel (an
+// L2 round trip per dependent load made the first version 5 ms per step), lower triangles packed.
+// Layout for a model with nv dofs, tri = nv (nv + 1) / 2:  H [tri] | XS [nv] | FC [nv] | M [tri]
+// (sized by the model, not by GX_TREE_MAXV: 418 floats per env for Doggo).  M is addressed through its own
+// pointer / stride (`mm`, `mms`) so that a launch can place it elsewhere (global memory was tried: slower).
 #define GXT_XS (tri)                  /* operand vector of the solves, of M*x and of J*x */
 #define GXT_JR (tri + nv)             /* qfrc_constraint (accumulated row by row) */
 #define FCS(i) sm[(size_t)(GXT_JR + (i)) * ms]
