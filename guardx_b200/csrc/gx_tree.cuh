@@ -54,6 +54,13 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 
 #define TS(off) sc[(size_t)(off) * stride]
 
+// The constraint rows J (region GXT_J = the first NROW * MAXV floats of every env's scratch) are stored in groups
+// of four dofs: group g of row r of this env at jrows4[(r * MAXV / 4 + g) * stride], so a row is five 128-bit loads
+// (20 scalar loads with their address arithmetic were 18 % of the kernel's instructions).
+struct alignas(16) gxt_f4 { float x, y, z, w; };
+#define JQ(r, g) reinterpret_cast<gxt_f4*>(jrows)[(size_t)((r) * (GX_TREE_MAXV / 4) + (g)) * stride]
+#define JE(r, i) (&JQ(r, (i) >> 2).x)[(i) & 3]
+
 // The arrays every inner loop of the Cholesky, of the solves and of the Hessian update walks through with
 // dependent loads live in a SEPARATE, small matrix scratch (`sm`, stride `ms`): shared memory in the kernel (an
 // L2 round trip per dependent load made the first version 5 ms per step), lower triangles packed.
@@ -154,14 +161,18 @@ GX_HD void gxt_chol_solve(float* sm, size_t ms, int n) {
 // One constraint row (global scratch) into registers: every load is in flight before the first use, so a row
 // costs ONE L2 round trip (loaded a few elements at a time each batch paid its own ~400 cycles; the ncu source
 // page showed the first FMA after each batch as the hottest instructions of the kernel).  Compile-time indices.
-GX_HD void gxt_row_load(const float* a, size_t stride, int n, float (&row)[GX_TREE_MAXV]) {
+GX_HD void gxt_row_load(const float* jrows, size_t stride, int r, float (&row)[GX_TREE_MAXV]) {
+  const gxt_f4* p = reinterpret_cast<const gxt_f4*>(jrows) + (size_t)(r * (GX_TREE_MAXV / 4)) * stride;
 #pragma unroll
-  for (int i = 0; i < GX_TREE_MAXV; ++i) row[i] = i < n ? a[(size_t)i * stride] : 0.f;
+  for (int g = 0; g < GX_TREE_MAXV / 4; ++g) {
+    const gxt_f4 v = p[(size_t)g * stride];
+    row[4 * g] = v.x; row[4 * g + 1] = v.y; row[4 * g + 2] = v.z; row[4 * g + 3] = v.w;
+  }
 }
-// s + sum_i a[i] x[i]; a: a constraint row in the global scratch, x: matrix scratch
-GX_HD float gxt_rowdot(const float* a, size_t stride, const float* x, size_t ms, int n, float s) {
+// s + sum_i J[r][i] x[i]; x: matrix scratch
+GX_HD float gxt_rowdot(const float* jrows, size_t stride, int r, const float* x, size_t ms, int n, float s) {
   float row[GX_TREE_MAXV], s1 = 0.f;
-  gxt_row_load(a, stride, n, row);
+  gxt_row_load(jrows, stride, r, row);
 #pragma unroll
   for (int i = 0; i < GX_TREE_MAXV; i += 2) {
     if (i < n) s = gx_fma(row[i], x[(size_t)i * ms], s);
@@ -249,9 +260,9 @@ GX_HD void gxt_make_frame(const float* n, float* t1, float* t2) {
 // solver's qacc).  ctrl [nu] is thread-local.  sc: scratch, GXT_SIZE floats with stride `stride`;
 // sm: matrix scratch (H | XS | JR), stride `ms`; mm: packed mass matrix, stride `mms`.
 GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, const float* warm, size_t ss,
-                        const float* ctrl, float* sc, size_t stride, float* sm, size_t ms, float* mm, size_t mms, bool forward_only, float* qo, float* vo,
+                        const float* ctrl, float* sc, size_t stride, float* jrows, float* sm, size_t ms, float* mm, size_t mms, bool forward_only, float* qo, float* vo,
                         float* wo, GxTreeSnap& snap, int* iters_out) {
-  const int nv = m.nv, P = GX_TREE_MAXV, tri = nv * (nv + 1) / 2;
+  const int nv = m.nv, tri = nv * (nv + 1) / 2;
   // ---------------- kinematics ----------------
   for (int b = 0; b < m.nb; ++b) {
     const GxTreeBody& B = m.body[b];
@@ -440,8 +451,8 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
     const float sgn = dmin < dmax ? 1.0f : -1.0f;
     const float imp = gx_art_imp(Jn.imp, pos);
     const float Rr = gx_max(gx_div(Jn.invw * (1.0f - imp), imp), GX_ART_MINVAL);
-    for (int i = 0; i < nv; ++i) TS(GXT_J + nrow * P + i) = 0.f;
-    TS(GXT_J + nrow * P + Jn.dofadr) = sgn;
+    for (int g = 0; g < GX_TREE_MAXV / 4; ++g) JQ(nrow, g) = gxt_f4{0.f, 0.f, 0.f, 0.f};
+    JE(nrow, Jn.dofadr) = sgn;
     TS(GXT_RD + nrow) = gx_rcp(Rr);
     TS(GXT_RA + nrow) = -Jn.b * (sgn * v[(size_t)Jn.dofadr * ss]) - Jn.k * imp * pos;
     ++nrow;
@@ -527,11 +538,11 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
           jn = sgn * gx_dot3(nrm, jp); j1 = sgn * gx_dot3(t1, jp); j2 = sgn * gx_dot3(t2, jp);
         }
         const float r0 = gx_fma(Pr.mu, j1, jn), r1 = gx_fma(-Pr.mu, j1, jn), r2 = gx_fma(Pr.mu, j2, jn), r3 = gx_fma(-Pr.mu, j2, jn);
-        TS(GXT_J + (nrow + 0) * P + i) = r0; TS(GXT_J + (nrow + 1) * P + i) = r1;
-        TS(GXT_J + (nrow + 2) * P + i) = r2; TS(GXT_J + (nrow + 3) * P + i) = r3;
+        JE(nrow + 0, i) = r0; JE(nrow + 1, i) = r1; JE(nrow + 2, i) = r2; JE(nrow + 3, i) = r3;
         const float vi = v[(size_t)i * ss];
         vel[0] = gx_fma(r0, vi, vel[0]); vel[1] = gx_fma(r1, vi, vel[1]); vel[2] = gx_fma(r2, vi, vel[2]); vel[3] = gx_fma(r3, vi, vel[3]);
       }
+      for (int i = nv; i < GX_TREE_MAXV; ++i) { JE(nrow + 0, i) = 0.f; JE(nrow + 1, i) = 0.f; JE(nrow + 2, i) = 0.f; JE(nrow + 3, i) = 0.f; }
       for (int r = 0; r < 4; ++r) { TS(GXT_RD + nrow + r) = Dv; TS(GXT_RA + nrow + r) = -Pr.b * vel[r] - kp; }
       nrow += 4;
     }
@@ -554,7 +565,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         cost = gx_fma(0.5f * (s - TS(GXT_FS + i)), TS(GXT_QA + i) - TS(GXT_AS + i), cost);
       }
       for (int r = 0; r < nrow; ++r) {
-        const float s = gxt_rowdot(&TS(GXT_J + r * P), stride, &XS(0), ms, nv, -TS(GXT_RA + r));
+        const float s = gxt_rowdot(jrows, stride, r, &XS(0), ms, nv, -TS(GXT_RA + r));
         TS(GXT_RJ + r) = s;
         if (s < 0.0f) cost = gx_fma(0.5f * TS(GXT_RD + r) * s, s, cost);
       }
@@ -581,7 +592,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       for (int k = 0; k < nact; ++k) {
         const int r = (int)TS(GXT_AL + k);
         float row[GX_TREE_MAXV];
-        gxt_row_load(&TS(GXT_J + r * P), stride, nv, row);
+        gxt_row_load(jrows, stride, r, row);
         const float force = -TS(GXT_RD + r) * TS(GXT_RJ + r);
 #pragma unroll
         for (int i = 0; i < GX_TREE_MAXV; ++i) if (i < nv) FCS(i) = gx_fma(row[i], force, FCS(i));
@@ -597,7 +608,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       for (int k = 0; k < nact; ++k) {
         const int r = (int)TS(GXT_AL + k);
         float row[GX_TREE_MAXV];
-        gxt_row_load(&TS(GXT_J + r * P), stride, nv, row);
+        gxt_row_load(jrows, stride, r, row);
         const float Dr = TS(GXT_RD + r);
 #pragma unroll
         for (int i = 0; i < GX_TREE_MAXV; ++i) {
@@ -623,7 +634,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         h0 = gx_fma(si, s, h0);
         ssq = gx_fma(si, si, ssq);
       }
-      for (int r = 0; r < nrow; ++r) TS(GXT_RV + r) = gxt_rowdot(&TS(GXT_J + r * P), stride, &XS(0), ms, nv, 0.f);
+      for (int r = 0; r < nrow; ++r) TS(GXT_RV + r) = gxt_rowdot(jrows, stride, r, &XS(0), ms, nv, 0.f);
       float alpha = 0.f, lo = 0.f, hi = 3.0e38f, slope0 = 0.f;
       for (int ls = 0; ls < 40; ++ls) {
         float d1 = gx_fma(alpha, h0, g0), d2 = h0;

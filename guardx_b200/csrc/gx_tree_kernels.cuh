@@ -162,6 +162,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
     float* wv = a.tw + i;
     float* zh = a.tw + (size_t)m.nworld * cap + i;   // z history of ego_vel_acc
     float* sc = a.scratch + i;
+    float* jrows = a.scratch + (size_t)4 * i;   // this env's slot in the float4-grouped constraint rows (region GXT_J)
     const float4 c2 = s.d2[i];
     float prev_dist = c2.x;
     float was_done = (__float_as_uint(c2.y) >> 31) ? 1.0f : 0.0f;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK ^ 1u);
       place(lay, q, v);
       for (int k = 0; k < m.nv; ++k) w[(size_t)k * cap] = 0.0f;     // mjx_reset starts from the pristine mjx_data
-      gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, mm, mms, true, q, v, w, sn, nullptr);
+      gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, true, q, v, w, sn, nullptr);
       GxTreeObs o = gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q, v, cap, row, nullptr);
       prev_dist = o.dist_goal;
       steps = 0.0f;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         // throw-away step(s) on a scratch copy: the state keeps the un-stepped pose and the stale warm start
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       for (int k = 0; k < p.substeps; ++k) {
         gpre_x = goal.x; gpre_y = goal.y;
         for (int h = 0; h < 2 * p.nh; ++h) hpre[h] = hz[h];
-        gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, sm, ms, mm, mms, false, q, v, w, sn, nullptr);
+        gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, false, q, v, w, sn, nullptr);
         advance_world();
       }
       if (qacc_out) for (int k = 0; k < m.nv; ++k) qacc_out[(size_t)i * m.nv + k] = w[(size_t)k * cap];
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         for (int k = 0; k < m.nu; ++k) ctrl[k] = 0.0f;
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);

@@ -15,7 +15,7 @@ extern "C" int tree_emu_step(const GxTreeModel* m, int n, float* q, float* v, fl
     GxTreeSnap sn;
     int it = 0;
     std::vector<float> qo(qe, qe + m->nq), vo(ve, ve + m->nv), wo(m->nv);
-    gx_tree_step(*m, qe, ve, we, 1, ctrl + (size_t)e * m->nu, sc.data(), 1, sm.data(), 1, sm.data() + GXT_MOFF(m->nv), 1, forward_only != 0, qo.data(), vo.data(), wo.data(), sn, &it);
+    gx_tree_step(*m, qe, ve, we, 1, ctrl + (size_t)e * m->nu, sc.data(), 1, sc.data(), sm.data(), 1, sm.data() + GXT_MOFF(m->nv), 1, forward_only != 0, qo.data(), vo.data(), wo.data(), sn, &it);
     for (int k = 0; k < m->nq; ++k) qe[k] = qo[k];
     for (int k = 0; k < m->nv; ++k) { ve[k] = vo[k]; we[k] = wo[k]; }
     if (snap12) { for (int k = 0; k < 3; ++k) snap12[12 * e + k] = sn.pos[k]; for (int k = 0; k < 9; ++k) snap12[12 * e + 3 + k] = sn.mat[k]; }
