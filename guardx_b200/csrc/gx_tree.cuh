@@ -60,6 +60,9 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 struct alignas(16) gxt_f4 { float x, y, z, w; };
 #define JQ(r, g) reinterpret_cast<gxt_f4*>(jrows)[(size_t)((r) * (GX_TREE_MAXV / 4) + (g)) * stride]
 #define JE(r, i) (&JQ(r, (i) >> 2).x)[(i) & 3]
+// Per-row scalars (regions GXT_RD .. GXT_RV, 4 * NROW floats) as one group per row: x = D, y = aref,
+// z = J qacc - aref, w = J search -- the line-search loops read a row with one 128-bit load.
+#define RQ(r) reinterpret_cast<gxt_f4*>(jrows + (size_t)GXT_RD * stride)[(size_t)(r) * stride]
 
 // The arrays every inner loop of the Cholesky, of the solves and of the Hessian update walks through with
 // dependent loads live in a SEPARATE, small matrix scratch (`sm`, stride `ms`): shared memory in the kernel (an
@@ -453,8 +456,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
     const float Rr = gx_max(gx_div(Jn.invw * (1.0f - imp), imp), GX_ART_MINVAL);
     for (int g = 0; g < GX_TREE_MAXV / 4; ++g) JQ(nrow, g) = gxt_f4{0.f, 0.f, 0.f, 0.f};
     JE(nrow, Jn.dofadr) = sgn;
-    TS(GXT_RD + nrow) = gx_rcp(Rr);
-    TS(GXT_RA + nrow) = -Jn.b * (sgn * v[(size_t)Jn.dofadr * ss]) - Jn.k * imp * pos;
+    RQ(nrow) = gxt_f4{gx_rcp(Rr), -Jn.b * (sgn * v[(size_t)Jn.dofadr * ss]) - Jn.k * imp * pos, 0.f, 0.f};
     ++nrow;
   }
   int ncon = 0;
@@ -543,7 +545,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         vel[0] = gx_fma(r0, vi, vel[0]); vel[1] = gx_fma(r1, vi, vel[1]); vel[2] = gx_fma(r2, vi, vel[2]); vel[3] = gx_fma(r3, vi, vel[3]);
       }
       for (int i = nv; i < GX_TREE_MAXV; ++i) { JE(nrow + 0, i) = 0.f; JE(nrow + 1, i) = 0.f; JE(nrow + 2, i) = 0.f; JE(nrow + 3, i) = 0.f; }
-      for (int r = 0; r < 4; ++r) { TS(GXT_RD + nrow + r) = Dv; TS(GXT_RA + nrow + r) = -Pr.b * vel[r] - kp; }
+      for (int r = 0; r < 4; ++r) RQ(nrow + r) = gxt_f4{Dv, -Pr.b * vel[r] - kp, 0.f, 0.f};
       nrow += 4;
     }
   }
@@ -565,9 +567,10 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         cost = gx_fma(0.5f * (s - TS(GXT_FS + i)), TS(GXT_QA + i) - TS(GXT_AS + i), cost);
       }
       for (int r = 0; r < nrow; ++r) {
-        const float s = gxt_rowdot(jrows, stride, r, &XS(0), ms, nv, -TS(GXT_RA + r));
-        TS(GXT_RJ + r) = s;
-        if (s < 0.0f) cost = gx_fma(0.5f * TS(GXT_RD + r) * s, s, cost);
+        const gxt_f4 rq = RQ(r);
+        const float s = gxt_rowdot(jrows, stride, r, &XS(0), ms, nv, -rq.y);
+        RQ(r).z = s;
+        if (s < 0.0f) cost = gx_fma(0.5f * rq.x * s, s, cost);
       }
       if (cnd == 0) cost_s = cost;
       else if (cnd == 1 && cost < cost_s) break;
@@ -579,10 +582,10 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
       // active rows (J qacc - aref < 0): compact index list, then qfrc_constraint = J^T f row by row
       int nact = 0;
       for (int r = 0; r < nrow; r += 4) {
-        const float j0 = TS(GXT_RJ + r);
-        const float j1 = r + 1 < nrow ? TS(GXT_RJ + r + 1) : 0.f;
-        const float j2 = r + 2 < nrow ? TS(GXT_RJ + r + 2) : 0.f;
-        const float j3 = r + 3 < nrow ? TS(GXT_RJ + r + 3) : 0.f;
+        const float j0 = RQ(r).z;
+        const float j1 = r + 1 < nrow ? RQ(r + 1).z : 0.f;
+        const float j2 = r + 2 < nrow ? RQ(r + 2).z : 0.f;
+        const float j3 = r + 3 < nrow ? RQ(r + 3).z : 0.f;
         if (j0 < 0.0f) { TS(GXT_AL + nact) = (float)r; ++nact; }
         if (j1 < 0.0f) { TS(GXT_AL + nact) = (float)(r + 1); ++nact; }
         if (j2 < 0.0f) { TS(GXT_AL + nact) = (float)(r + 2); ++nact; }
@@ -593,7 +596,8 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         const int r = (int)TS(GXT_AL + k);
         float row[GX_TREE_MAXV];
         gxt_row_load(jrows, stride, r, row);
-        const float force = -TS(GXT_RD + r) * TS(GXT_RJ + r);
+        const gxt_f4 rq = RQ(r);
+        const float force = -rq.x * rq.z;
 #pragma unroll
         for (int i = 0; i < GX_TREE_MAXV; ++i) if (i < nv) FCS(i) = gx_fma(row[i], force, FCS(i));
       }
@@ -609,7 +613,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         const int r = (int)TS(GXT_AL + k);
         float row[GX_TREE_MAXV];
         gxt_row_load(jrows, stride, r, row);
-        const float Dr = TS(GXT_RD + r);
+        const float Dr = RQ(r).x;
 #pragma unroll
         for (int i = 0; i < GX_TREE_MAXV; ++i) {
           if (i < nv) {
@@ -634,13 +638,14 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         h0 = gx_fma(si, s, h0);
         ssq = gx_fma(si, si, ssq);
       }
-      for (int r = 0; r < nrow; ++r) TS(GXT_RV + r) = gxt_rowdot(jrows, stride, r, &XS(0), ms, nv, 0.f);
+      for (int r = 0; r < nrow; ++r) RQ(r).w = gxt_rowdot(jrows, stride, r, &XS(0), ms, nv, 0.f);
       float alpha = 0.f, lo = 0.f, hi = 3.0e38f, slope0 = 0.f;
       for (int ls = 0; ls < 40; ++ls) {
         float d1 = gx_fma(alpha, h0, g0), d2 = h0;
         for (int r = 0; r < nrow; ++r) {
-          const float jv = TS(GXT_RV + r), x = gx_fma(alpha, jv, TS(GXT_RJ + r));
-          if (x < 0.0f) { const float dj = TS(GXT_RD + r) * jv; d1 = gx_fma(dj, x, d1); d2 = gx_fma(dj, jv, d2); }
+          const gxt_f4 rq = RQ(r);
+          const float jv = rq.w, x = gx_fma(alpha, jv, rq.z);
+          if (x < 0.0f) { const float dj = rq.x * jv; d1 = gx_fma(dj, x, d1); d2 = gx_fma(dj, jv, d2); }
         }
         if (ls == 0) slope0 = d1;
         if (!(d1 < 0.0f || d1 > 0.0f)) break;
@@ -650,7 +655,8 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         if (bad) nxt = hi < 3.0e38f ? 0.5f * (lo + hi) : 2.0f * gx_max(lo, 1.0f);
         int changed = bad ? 1 : 0;
         for (int r = 0; r < nrow && !changed; ++r) {
-          const float jv = TS(GXT_RV + r), jr = TS(GXT_RJ + r);
+          const gxt_f4 rq = RQ(r);
+          const float jv = rq.w, jr = rq.z;
           changed |= (gx_fma(alpha, jv, jr) < 0.0f) != (gx_fma(nxt, jv, jr) < 0.0f);
         }
         alpha = nxt;
@@ -663,7 +669,7 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
         TS(GXT_MA + i) = gx_fma(alpha, TS(GXT_MV + i), TS(GXT_MA + i));
         qq = gx_fma(qa, qa, qq);
       }
-      for (int r = 0; r < nrow; ++r) TS(GXT_RJ + r) = gx_fma(alpha, TS(GXT_RV + r), TS(GXT_RJ + r));
+      for (int r = 0; r < nrow; ++r) { const gxt_f4 rq = RQ(r); RQ(r).z = gx_fma(alpha, rq.w, rq.z); }
       ++iters;
       const float improvement = -0.5f * alpha * slope0;   // decrease predicted by the line-search model (see gx_art.cuh)
       if (!(improvement >= m.tol_scale) || !(alpha * alpha * ssq > 1e-12f * qq)) finish = true;
