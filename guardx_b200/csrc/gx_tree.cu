@@ -3,7 +3,8 @@
 
 cudaError_t gx_tree_launch(const GxTreeLaunch& a) {
   // 32-env blocks; Hessian workspace + mass matrix in shared memory (53.5 KB per block for Doggo, four blocks per SM)
-  const int n = a.p->n, block = 32, grid = (n + block - 1) / block;
+  static_assert(GXT_DEVICE_MS == 32, "gx_tree kernels run one 32-lane warp per block");
+  const int n = a.p->n, block = GXT_DEVICE_MS, grid = (n + block - 1) / block;
   const size_t sh = (size_t)block * GXT_SM_FLOATS_OF(a.t->nv, 1) * sizeof(float);
   if (a.mode == GX_ART_RESET) return gx_tree_go_reset(a, grid, block, sh);
   if (a.mode == GX_ART_RESET_DONE) return gx_tree_go_reset_done(a, grid, block, sh);

@@ -58,6 +58,7 @@ struct GxTreeSnap { float pos[3], mat[9]; };   // root xpos / xmat of the forwar
 // of four dofs: group g of row r of this env at jrows4[(r * MAXV / 4 + g) * stride], so a row is five 128-bit loads
 // (20 scalar loads with their address arithmetic were 18 % of the kernel's instructions).
 struct alignas(16) gxt_f4 { float x, y, z, w; };
+#define GXT_DEVICE_MS 32   /* threads per block of the kernels = lanes the matrix scratch is interleaved over */
 #define JQ(r, g) reinterpret_cast<gxt_f4*>(jrows)[(size_t)((r) * (GX_TREE_MAXV / 4) + (g)) * stride]
 #define JE(r, i) (&JQ(r, (i) >> 2).x)[(i) & 3]
 // Per-row scalars (regions GXT_RD .. GXT_RV, 4 * NROW floats) as one group per row: x = D, y = aref,
@@ -263,9 +264,18 @@ GX_HD void gxt_make_frame(const float* n, float* t1, float* t2) {
 // solver's qacc).  ctrl [nu] is thread-local.  sc: scratch, GXT_SIZE floats with stride `stride`;
 // sm: matrix scratch (H | XS | JR), stride `ms`; mm: packed mass matrix, stride `mms`.
 GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, const float* warm, size_t ss,
-                        const float* ctrl, float* sc, size_t stride, float* jrows, float* sm, size_t ms, float* mm, size_t mms, bool forward_only, float* qo, float* vo,
+                        const float* ctrl, float* sc, size_t stride, float* jrows, float* sm, size_t ms_arg, float* mm, size_t mms_arg, bool forward_only, float* qo, float* vo,
                         float* wo, GxTreeSnap& snap, int* iters_out) {
   const int nv = m.nv, tri = nv * (nv + 1) / 2;
+#ifdef __CUDA_ARCH__
+  // One warp per block: the matrix scratch is interleaved over exactly 32 lanes.  A compile-time stride turns every
+  // shared-memory access into base + immediate, and -- what matters -- lets the compiler see that hrow[j] and hrow[j']
+  // never alias, so the loads of the unrolled Hessian update / Cholesky are no longer serialised behind the stores.
+  constexpr size_t ms = GXT_DEVICE_MS, mms = GXT_DEVICE_MS;
+  (void)ms_arg; (void)mms_arg;
+#else
+  const size_t ms = ms_arg, mms = mms_arg;
+#endif
   // ---------------- kinematics ----------------
   for (int b = 0; b < m.nb; ++b) {
     const GxTreeBody& B = m.body[b];
