@@ -412,8 +412,15 @@ GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, co
   for (int b = m.nb - 1; b >= 1; --b) {
     const int p = m.body[b].parent;
     if (p < 0) continue;
-    for (int e = 0; e < 10; ++e) TS(GXT_CRB + 10 * p + e) += TS(GXT_CRB + 10 * b + e);
-    for (int e = 0; e < 6; ++e) TS(GXT_CFRC + 6 * p + e) += TS(GXT_CFRC + 6 * b + e);
+    // all 32 loads first (a read-modify-write per element would wait for each load: the compiler may not move a
+    // load above a store that could alias it)
+    float cb[10], cp[10], fb[6], fp[6];
+    gxt_get(sc, stride, GXT_CRB + 10 * b, 10, cb); gxt_get(sc, stride, GXT_CRB + 10 * p, 10, cp);
+    gxt_get(sc, stride, GXT_CFRC + 6 * b, 6, fb); gxt_get(sc, stride, GXT_CFRC + 6 * p, 6, fp);
+    for (int e = 0; e < 10; ++e) cp[e] += cb[e];
+    for (int e = 0; e < 6; ++e) fp[e] += fb[e];
+    gxt_put(sc, stride, GXT_CRB + 10 * p, 10, cp);
+    gxt_put(sc, stride, GXT_CFRC + 6 * p, 6, fp);
   }
   // ---------------- mass matrix, smooth forces ----------------
   for (int i = 0; i < nv; ++i) for (int j = 0; j <= i; ++j) MM(i, j) = 0.f;
