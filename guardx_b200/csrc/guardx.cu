@@ -756,7 +756,7 @@ static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int
   }
   if (h_tree) {
     e->tree_host = new (std::nothrow) GxTreeModel(*h_tree);
-    e->tree.nq = h_tree->nq; e->tree.nv = h_tree->nv; e->tree.nu = h_tree->nu;
+    e->tree.nq = h_tree->nq; e->tree.nv = h_tree->nv; e->tree.nu = h_tree->nu; e->tree.scratch_floats = gx_tree_scratch_floats();
     GxTreeModel* dm = nullptr;
     GX_ALLOC(dm, sizeof(GxTreeModel));
     cudaMemcpy(dm, h_tree, sizeof(GxTreeModel), cudaMemcpyHostToDevice);

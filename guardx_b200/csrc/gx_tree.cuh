@@ -3,7 +3,7 @@
 //
 // First version, written for coverage rather than speed: ONE THREAD PER ENV, every per-env
 // array (mass matrix, Hessian, constraint Jacobian, body quantities) in a scratch buffer in
-// global memory, interleaved over envs (element k of env e at scratch[k * stride + e], so a
+// global memory, interleaved over the 32 envs of a block (element k of lane l at chunk[k * stride + l], so a
 // warp's accesses coalesce).  The algorithm is the dense pipeline of oracle/mjx_numpy.py --
 // kinematics, composite inertias (frame centred on the root body), RNE bias, Cholesky, limit and
 // pyramidal contact rows for the ACTIVE candidates only, Newton with warm start and exact line
@@ -264,17 +264,17 @@ GX_HD void gxt_make_frame(const float* n, float* t1, float* t2) {
 // solver's qacc).  ctrl [nu] is thread-local.  sc: scratch, GXT_SIZE floats with stride `stride`;
 // sm: matrix scratch (H | XS | JR), stride `ms`; mm: packed mass matrix, stride `mms`.
 GX_HD void gx_tree_step(const GxTreeModel& m, const float* q, const float* v, const float* warm, size_t ss,
-                        const float* ctrl, float* sc, size_t stride, float* jrows, float* sm, size_t ms_arg, float* mm, size_t mms_arg, bool forward_only, float* qo, float* vo,
+                        const float* ctrl, float* sc, size_t stride_arg, float* jrows, float* sm, size_t ms_arg, float* mm, size_t mms_arg, bool forward_only, float* qo, float* vo,
                         float* wo, GxTreeSnap& snap, int* iters_out) {
   const int nv = m.nv, tri = nv * (nv + 1) / 2;
 #ifdef __CUDA_ARCH__
   // One warp per block: the matrix scratch is interleaved over exactly 32 lanes.  A compile-time stride turns every
   // shared-memory access into base + immediate, and -- what matters -- lets the compiler see that hrow[j] and hrow[j']
   // never alias, so the loads of the unrolled Hessian update / Cholesky are no longer serialised behind the stores.
-  constexpr size_t ms = GXT_DEVICE_MS, mms = GXT_DEVICE_MS;
-  (void)ms_arg; (void)mms_arg;
+  constexpr size_t ms = GXT_DEVICE_MS, mms = GXT_DEVICE_MS, stride = GXT_DEVICE_MS;   // (the global scratch too: one chunk per block)
+  (void)ms_arg; (void)mms_arg; (void)stride_arg;
 #else
-  const size_t ms = ms_arg, mms = mms_arg;
+  const size_t ms = ms_arg, mms = mms_arg, stride = stride_arg;
 #endif
   // ---------------- kinematics ----------------
   for (int b = 0; b < m.nb; ++b) {

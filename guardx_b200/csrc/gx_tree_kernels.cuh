@@ -161,8 +161,11 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
     float* w2 = v2 + (size_t)a.nv * cap;
     float* wv = a.tw + i;
     float* zh = a.tw + (size_t)m.nworld * cap + i;   // z history of ego_vel_acc
-    float* sc = a.scratch + i;
-    float* jrows = a.scratch + (size_t)4 * i;   // this env's slot in the float4-grouped constraint rows (region GXT_J)
+    // global scratch: one chunk of (floats per env) x 32 per block, element k of lane l at chunk[k * 32 + l] -- coalesced,
+    // and the stride is a compile-time constant (loads at different constant offsets can pass earlier stores)
+    float* chunk = a.scratch + (size_t)blockIdx.x * a.scratch_floats * GXT_DEVICE_MS;
+    float* sc = chunk + lane;
+    float* jrows = chunk + 4 * lane;            // this env's slot in the float4-grouped constraint rows (region GXT_J)
     const float4 c2 = s.d2[i];
     float prev_dist = c2.x;
     float was_done = (__float_as_uint(c2.y) >> 31) ? 1.0f : 0.0f;
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK ^ 1u);
       place(lay, q, v);
       for (int k = 0; k < m.nv; ++k) w[(size_t)k * cap] = 0.0f;     // mjx_reset starts from the pristine mjx_data
-      gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, true, q, v, w, sn, nullptr);
+      gx_tree_step(m, q, v, w, cap, ctrl, sc, GXT_DEVICE_MS, jrows, sm, ms, mm, mms, true, q, v, w, sn, nullptr);
       GxTreeObs o = gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q, v, cap, row, nullptr);
       prev_dist = o.dist_goal;
       steps = 0.0f;
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         // throw-away step(s) on a scratch copy: the state keeps the un-stepped pose and the stale warm start
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, GXT_DEVICE_MS, jrows, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
       for (int k = 0; k < p.substeps; ++k) {
         gpre_x = goal.x; gpre_y = goal.y;
         for (int h = 0; h < 2 * p.nh; ++h) hpre[h] = hz[h];
-        gx_tree_step(m, q, v, w, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, false, q, v, w, sn, nullptr);
+        gx_tree_step(m, q, v, w, cap, ctrl, sc, GXT_DEVICE_MS, jrows, sm, ms, mm, mms, false, q, v, w, sn, nullptr);
         advance_world();
       }
       if (qacc_out) for (int k = 0; k < m.nv; ++k) qacc_out[(size_t)i * m.nv + k] = w[(size_t)k * cap];
@@ -287,7 +290,7 @@ __global__ void __launch_bounds__(64) gx_tree_kernel(const __grid_constant__ gx_
         for (int k = 0; k < m.nu; ++k) ctrl[k] = 0.0f;
         const float* qs = q; const float* vs = v; const float* ws = w;
         for (int k = 0; k < p.substeps; ++k) {
-          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, cap, jrows, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
+          gx_tree_step(m, qs, vs, ws, cap, ctrl, sc, GXT_DEVICE_MS, jrows, sm, ms, mm, mms, false, q2, v2, w2, sn, nullptr);
           qs = q2; vs = v2; ws = w2;
         }
         gx_tree_obs_row(p, s, m, i, goal.x, goal.y, hz, sn, ctrl, q2, v2, cap, row, nullptr);

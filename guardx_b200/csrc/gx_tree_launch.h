@@ -14,8 +14,9 @@ struct GxTreeDev {
   const GxTreeModel* m;
   float* tq;       // [2 * (nq + 2 nv), cap]
   float* tw;       // [nworld + 2, cap] goal / hazard slide velocities, z history of ego_vel_acc
-  float* scratch;  // [GXT_SIZE + packed mass matrix, cap]
+  float* scratch;  // one chunk [scratch_floats, 32] per 32-env block
   int nq, nv, nu;
+  int scratch_floats;   // floats of global scratch per env (gx_tree_scratch_floats())
 };
 
 struct GxTreeLaunch {
