@@ -1,14 +1,16 @@
 // gx_tree.cuh -- mjx.step for a GENERAL kinematic tree (free-joint or jointed root, hinge / slide
 // joints, capsule / sphere contacts with the floor and with each other): the Doggo path.
 //
-// First version, written for coverage rather than speed: ONE THREAD PER ENV, every per-env
-// array (mass matrix, Hessian, constraint Jacobian, body quantities) in a scratch buffer in
-// global memory, interleaved over the 32 envs of a block (element k of lane l at chunk[k * stride + l], so a
-// warp's accesses coalesce).  The algorithm is the dense pipeline of oracle/mjx_numpy.py --
-// kinematics, composite inertias (frame centred on the root body), RNE bias, Cholesky, limit and
-// pyramidal contact rows for the ACTIVE candidates only, Newton with warm start and exact line
-// search, implicit-damping Euler, quaternion integration.  A warp-per-env version with the
-// matrices in shared memory is the obvious next step.
+// ONE THREAD PER ENV (the dense 19 x 19 solve does not split over a fixed lane count the way the star robots do).
+// Per-env data: the big arrays (constraint Jacobian, body quantities, solver vectors) in a scratch buffer in global
+// memory, interleaved over the 32 envs of a block (element k of lane l at chunk[k * stride + l], so a warp's
+// accesses coalesce; constraint rows and per-row scalars in 128-bit groups); the Hessian / Cholesky workspace, the
+// solve operand, qfrc_constraint and the mass matrix in a small matrix scratch (shared memory in the kernels).
+// Both strides are compile-time constants on the device: with runtime strides the compiler cannot reorder a load
+// past a store that might alias it, which serialised every read-modify-write chain.
+// The algorithm is the dense pipeline of oracle/mjx_numpy.py -- kinematics, composite inertias (frame centred on
+// the root body), RNE bias, Cholesky, limit and pyramidal contact rows for the ACTIVE candidates only, Newton with
+// warm start and exact line search, implicit-damping Euler, quaternion integration.
 //
 // Like gx_art.cuh this header also compiles as plain C++ (tests/emu/) for CPU-side checks.
 #ifndef GX_TREE_CUH_
