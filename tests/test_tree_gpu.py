@@ -214,3 +214,34 @@ def test_doggo_host_buffer_paths_and_batch_independence(mods):
         o1, r1, d1, i1 = s_env.step(act[:n].contiguous())
         o2, r2, d2, i2 = l_env.step(act)
         assert torch.equal(o1, o2[:n]) and torch.equal(r1, r2[:n]) and torch.equal(i1['cost'], i2['cost'][:n])
+
+
+def test_doggo_step_replays_from_a_cuda_graph(mods):
+    """The Doggo kernels take the compiled model (11 KB) as a by-value kernel parameter; a captured step must
+    replay with it: graph replays == eager gx_step_autoreset calls, bit for bit."""
+    import ctypes as C
+    Engine, _, _ = mods
+    n = 160
+    cfg = {'env_num': n, 'robot_base': 'xmls/doggo.xml', 'num_steps': 5, '_seed': 4}
+    a_env, b_env = Engine(dict(cfg)), Engine(dict(cfg))
+    a_env.reset(); b_env.reset()
+    act = torch.empty(n, NU, device='cuda').uniform_(-1, 1)
+    obs = torch.empty(n, 85, device='cuda'); rdc = torch.empty(3, n, device='cuda')
+    p = lambda t_: C.c_void_p(t_.data_ptr())
+    lib = a_env._lib
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        sp = C.c_void_p(side.cuda_stream)
+        with torch.cuda.graph(g, stream=side):
+            lib.gx_step_autoreset(a_env._h, p(act), p(obs), p(rdc[0]), p(rdc[1]), p(rdc[2]), sp)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for t in range(8):                       # capture does not execute: both envs start from the same state
+        act.uniform_(-1, 1)
+        g.replay()
+        torch.cuda.synchronize()
+        o, r, d, i = b_env.step_autoreset(act)
+        assert torch.equal(o, obs) and torch.equal(r, rdc[0]) and torch.equal(d, rdc[1]) and torch.equal(i['cost'], rdc[2])
+    assert torch.isfinite(obs).all()
