@@ -25,9 +25,17 @@ One JSON line on stdout (rank 0).  Keys beyond the driver's contract:
   sweep         (N=1 only) step-kernel GB/s at larger batches, to show where the
                 kernel sits against the roofline once launch latency is amortised
 
-L2 policy: every timed step touches a batch whose state, actions and output
-buffers have not been touched for R-1 steps, where R batches x ~1.3 MB exceed the
-126 MB L2 (config.l2 says so); the L2-resident number is reported beside it.
+Timing (the same whatever --steps K is): a WINDOW is exactly K fused step launches; a timed
+REGION is M back-to-back windows, M chosen so that a region lasts >= 20 ms; REGIONS (7) regions
+are measured and the MEDIAN is reported (min / max beside it), so ms_per_step x steps = one
+window.  Every region is a chain of CUDA graphs; all regions, their L2 flushes and their
+CUDA events are enqueued while the GPU is still busy with an untimed replay, so neither
+graph-launch latency nor the host is inside a timed region.
+
+L2 policy: every region starts after a 512 MB write (L2 flush, outside the events) and every
+timed step touches a batch whose state, actions and output buffers have not been touched for
+R-1 steps, where R batches x ~1.5 MB exceed twice the 126 MB L2 (config.l2 says so); the
+L2-resident number is reported beside it.
 """
 from __future__ import annotations
 
@@ -47,7 +55,10 @@ ENVS_PER_GPU = 4096
 ALG_BYTES_STEP = 348      # single-step API contract
 ALG_BYTES_ROLLOUT = 192   # multi-step kernel, I/O only
 L2_BYTES = 126e6
-LANES_TRAFFIC_4096 = 626688   # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/)
+FLUSH_BYTES = 512 << 20       # written before every timed region: evicts the L2
+REGION_SECONDS = 0.025        # a timed region lasts at least this long, whatever --steps is
+MAX_REGION_STEPS = 1 << 16    # graph nodes per region (bounds capture time when --steps is huge)
+REGIONS = 7                   # regions measured; the median is reported
 TASK = "Goal_Point_8Hazards"
 
 
@@ -228,45 +239,79 @@ def time_steps(torch, lib, batches, steps, stream, barrier=None):
     return ev0.elapsed_time(ev1) * 1e-3
 
 
-class GraphedSteps:
-    """EXACTLY K fused step launches as CUDA graphs (chunks of <= 2048 kernel
-    nodes).  Legal because every counter the kernels use lives in device memory."""
+class Regions:
+    """A timed REGION = `S` fused step launches (S = M windows x K steps) as a chain of CUDA
+    graphs (<= 2048 kernel nodes each; every chunk is its own graph, so the round-robin over
+    the batches runs on unbroken from the first step of a region to the last).  Legal because
+    every counter the kernels use lives in device memory.
 
-    def __init__(self, torch, lib, batches, steps, chunk=2048):
-        self.torch = torch
-        self.plan = []
+    measure(): one untimed replay keeps the GPU busy while ALL regions are enqueued --
+    flush (512 MB write, evicts the 126 MB L2), event, graphs, event, flush, ... -- so that
+    neither the host nor the graph-launch latency is inside a region."""
+
+    def __init__(self, torch, issue, S, flush_buf, chunk=2048):
+        self.torch, self.S, self.flush_buf = torch, S, flush_buf
+        self.graphs = []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         sp = C.c_void_p(side.cuda_stream)
-        q, r = divmod(steps, chunk)
-        done = 0
         with torch.cuda.stream(side):
-            for size, reps in ((chunk, q), (r, 1)):
-                if size == 0 or reps == 0:
-                    continue
+            for c0 in range(0, S, chunk):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=side):
-                    issue_steps(lib, batches, size, sp, t0=done)
-                self.plan.append((g, reps))
-                done += size * reps
+                    issue(sp, c0, min(chunk, S - c0))
+                self.graphs.append(g)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
 
-    def run(self, stream, barrier=None):
+    def replay(self):
+        for g in self.graphs:
+            g.replay()
+
+    def measure(self, stream, regions, barrier=None, flush=True):
         torch = self.torch
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(regions)]
         if barrier:
             barrier()
         torch.cuda.synchronize()
-        ev0.record(stream)
-        for g, reps in self.plan:
-            for _ in range(reps):
-                g.replay()
-        ev1.record(stream)
+        self.replay()                      # untimed: the GPU is busy while everything below is enqueued
+        for r, (e0, e1) in enumerate(evs):
+            if flush and self.flush_buf is not None:
+                self.flush_buf.fill_(float(r))
+            e0.record(stream)
+            self.replay()
+            e1.record(stream)
         torch.cuda.synchronize()
         if barrier:
             barrier()
-        return ev0.elapsed_time(ev1) * 1e-3
+        return [e0.elapsed_time(e1) * 1e-3 for e0, e1 in evs]
+
+
+def max_over_ranks(torch, dist, times):
+    """device-timed durations: MAX over the ranks, element by element"""
+    if dist is None:
+        return list(times)
+    t = torch.tensor(times, device='cuda', dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def median(xs):
+    s = sorted(xs)
+    return s[len(s) // 2] if len(s) % 2 else 0.5 * (s[len(s) // 2 - 1] + s[len(s) // 2])
+
+
+def load_traffic(kernel_prefix, envs):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary of
+    THIS build (profiles/traffic.json, written by tools/ncu_summary.py); None if there is none."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        for row in json.load(f):
+            if row.get("kernel", "").startswith(kernel_prefix) and row.get("envs") == envs:
+                return row.get("dram_bytes_per_launch"), row.get("source")
+    return None, None
 
 
 _REAL_STDOUT = None
@@ -290,6 +335,7 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU (default: BASELINE configs[1])")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-legged", action="store_true", help="skip the ant / 65536-env measurement")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the PPO-Lagrangian section")
     args = ap.parse_args()
 
     # stdout carries the ONE JSON line and nothing else: native libraries (NCCL prints its version banner with
@@ -327,7 +373,7 @@ def main():
     K = args.steps
     stream = torch.cuda.current_stream()
 
-    # ---- batches: R independent n-env batches, working set > L2 -------------
+    # ---- batches: R independent n-env batches, working set > 2 x L2 -----------
     od = 43
     per_batch = n * (116 + 4 * (od + 3)) + 8 * n * 8   # state + outputs + 8 action slices
     R = int(L2_BYTES * 2.0 / per_batch) + 1
@@ -337,34 +383,41 @@ def main():
     for b in batches:
         b.env.stats_reset()   # in-kernel episode statistics on (what ppo_train.py:370-376 does on the host)
     working_set = R * per_batch
+    flush_buf = torch.empty(FLUSH_BYTES // 4, device='cuda')
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # ---- value: K steps as a CUDA graph, cold-L2 round-robin ---------------
-    time_steps(torch, lib, batches, warmup, stream)                   # warm-up (>= 3 steps)
-    graphed = GraphedSteps(torch, lib, batches, K)
-    graphed.run(stream)                                                # one untimed replay
-    dt = graphed.run(stream, barrier)
+    # ---- value: regions of M windows x K steps, CUDA graphs, cold L2 -------
+    time_steps(torch, lib, batches, max(warmup, R), stream)            # warm-up (>= 3 steps, every batch once)
+    est = max_over_ranks(torch, dist, [time_steps(torch, lib, batches, 256, stream) / 256])[0]   # stream launches: >= graph time
+    m_cap = max(1, MAX_REGION_STEPS // K)
+    M = max(1, min(int(REGION_SECONDS / (K * est * 0.6)) + 1, m_cap))
+    issue = lambda sp, t0, steps: issue_steps(lib, batches, steps, sp, t0=t0)
+    for attempt in range(4):
+        reg = Regions(torch, issue, M * K, flush_buf)
+        region_s = max_over_ranks(torch, dist, reg.measure(stream, REGIONS, barrier))
+        dt = median(region_s)                                         # one region = M windows = S steps
+        del reg
+        if dt >= 0.8 * REGION_SECONDS or M >= m_cap:
+            break
+        M = max(M + 1, min(int(M * REGION_SECONDS / dt) + 1, m_cap))  # identical on every rank (dt is the max over ranks)
+    S = M * K
     # per-epoch statistics all-reduce (replaces mpi_statistics_scalar), inside the job but not the hot loop
     stats = torch.stack([b.env.stats() for b in batches]).sum(0)
     gxd.allreduce_stats(stats)   # NCCL all-reduce of the 8-double episode statistics vector
-    if dist:
-        t = torch.tensor([dt], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    value = world * n * K / dt
-    # ---- the same K steps launched one by one from Python (no graph) -------
-    dt_stream = time_steps(torch, lib, batches, K, stream, barrier)
-    # ---- same graph over one batch only (L2-resident state) ----------------
-    graphed_hot = GraphedSteps(torch, lib, batches[:1], K)
-    graphed_hot.run(stream)
-    dt_hot = graphed_hot.run(stream, barrier)
-    del graphed_hot
+    value = world * n * S / dt
+    # ---- the same steps launched one by one from Python (no graph) ----------
+    Ss = max(K, 2000)
+    dt_stream = max_over_ranks(torch, dist, [time_steps(torch, lib, batches, Ss, stream, barrier)])[0]
+    # ---- same graph chain over one batch only (L2-resident state) ----------
+    hot = Regions(torch, lambda sp, t0, steps: issue_steps(lib, batches[:1], steps, sp, t0=t0), S, None)
+    dt_hot = median(max_over_ranks(torch, dist, hot.measure(stream, 5, barrier, flush=False)))
+    del hot
 
     # ---- e2e: host buffers through Engine.step_host -----------------------
     h_act = torch.empty(8, n, 2).uniform_(-1, 1).pin_memory()
     h_out = torch.empty(n * (od + 3)).pin_memory()
-    Ke = max(50, min(K, 1000))
+    Ke = max(200, min(K, 1000))
 
     def e2e_loop(k):
         for t in range(k):
@@ -377,11 +430,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_loop(Ke)
-    dt_e2e = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([dt_e2e], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_e2e = float(t.item())
+    dt_e2e = max_over_ranks(torch, dist, [time.perf_counter() - t0])[0]
     e2e_sync_value = world * n * Ke / dt_e2e
 
     # ---- e2e, pipelined: the same host-buffer steps through gx_rollout_host --
@@ -391,7 +440,7 @@ def main():
     hp_act = torch.empty(Tp, n, 2).uniform_(-1, 1).pin_memory()
     hp_obs = torch.empty(Tp, n, od).pin_memory()
     hp_r, hp_d, hp_c = (torch.empty(Tp, n).pin_memory() for _ in range(3))
-    reps_p = max(2, min(40, (K + Tp - 1) // Tp))
+    reps_p = 8
 
     Rp = min(R, 8)   # PCIe, not L2, bounds this path; 8 batches keep every call on a different env state
 
@@ -408,11 +457,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     e2e_pipe(reps_p)
-    dt_pipe = time.perf_counter() - t0
-    if dist:
-        t = torch.tensor([dt_pipe], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_pipe = float(t.item())
+    dt_pipe = max_over_ranks(torch, dist, [time.perf_counter() - t0])[0]
     e2e_value = world * n * Tp * reps_p / dt_pipe
     del hp_obs
 
@@ -431,7 +476,7 @@ def main():
 
     for _ in range(3):
         rollout_once()
-    reps = max(3, min(40, K // T + 1))
+    reps = 40
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record(stream)
@@ -439,78 +484,62 @@ def main():
         rollout_once()
     ev1.record(stream)
     torch.cuda.synchronize()
-    dt_ro = ev0.elapsed_time(ev1) * 1e-3
-    if dist:
-        t = torch.tensor([dt_ro], device='cuda', dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_ro = float(t.item())
+    dt_ro = max_over_ranks(torch, dist, [ev0.elapsed_time(ev1) * 1e-3])[0]
     ro_value = world * n * T * reps / dt_ro
-    # ---- BASELINE configs[3]: legged robot (ant), 65536 envs sharded over the ranks --------
+    del ro_obs, ro_rcd, ro_act
+    # ---- BASELINE configs[3]: legged robots, 65536 envs sharded over the ranks ----------
     legged = None
     if not args.no_legged:
-        n_leg = 65536 // world
-        Tl = 30
-        aenv = Engine({'env_num': n_leg, 'robot_base': 'xmls/ant.xml', 'num_steps': 1000, '_seed': 0},
-                      env_id_offset=rank * n_leg)
-        aenv.reset()
-        aenv.stats_reset()
-        lo = aenv.rollout(Tl)      # warm-up + buffers (obs [T, n, 64] etc.)
-        torch.cuda.synchronize()
-        if barrier:
-            barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        rc = lib.gx_rollout(aenv._h, Tl, pr(lo['obs']), pr(lo['act']), pr(lo['reward']), pr(lo['cost']), pr(lo['done']), sp)
-        assert rc == 0, lib.gx_last_error()
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        dt_leg = ev0.elapsed_time(ev1) * 1e-3
-        if dist:
-            t = torch.tensor([dt_leg], device='cuda', dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt_leg = float(t.item())
+        def legged_run(xml, n_leg, T_, settle):
+            env = Engine({'env_num': n_leg, 'robot_base': xml, 'num_steps': 1000, '_seed': 0}, env_id_offset=rank * n_leg)
+            env.reset()
+            env.stats_reset()
+            lo = env.rollout(T_)      # warm-up + buffers
+            args_ = (env._h, T_, pr(lo['obs']), pr(lo['act']), pr(lo['reward']), pr(lo['cost']), pr(lo['done']), sp)
+            for _ in range(settle):   # contacts established
+                lib.gx_rollout(*args_)
+            torch.cuda.synchronize()
+            if barrier:
+                barrier()
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                rc = lib.gx_rollout(*args_)
+                assert rc == 0, lib.gx_last_error()
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e-3)
+            d_ = median(max_over_ranks(torch, dist, ts))
+            fin = bool(torch.isfinite(lo['obs']).all().item())
+            del env, lo
+            torch.cuda.empty_cache()
+            return d_, fin
+
+        n_leg, Tl = 65536 // world, 64
+        dt_leg, fin = legged_run('xmls/ant.xml', n_leg, Tl, 0)
         leg_bytes = 4 * (2 * 3 * 11 + 8 + 2 + 16 + 64 + 3)   # q,v,warm r+w | d2 r+w | goal | hazards | obs | r,c,d
         legged = {"workload": "Goal_Ant_8Hazards, 65536 envs in total, random actions drawn in-kernel, fused step + "
                               "auto-reset, one launch per step (BASELINE.json configs[3])",
                   "envs_per_gpu": n_leg, "steps": Tl, "value": world * n_leg * Tl / dt_leg, "unit": "env-steps/s",
                   "us_per_step": 1e6 * dt_leg / Tl, "scaling": "strong", "alg_bytes_per_env_step": leg_bytes,
                   "achieved_gbs": n_leg * Tl * leg_bytes / dt_leg / 1e9,
-                  "bound": "issue/latency (Newton contact solver per env, ~1.9 k warp-instructions per env-step), "
-                           "not HBM", "finite": bool(torch.isfinite(lo['obs']).all().item())}
-        del aenv, lo
-        torch.cuda.empty_cache()
-        # Doggo (general-tree kernels): same protocol, 65536 envs in total, steady state (the robot has landed)
-        n_dog, Td = 65536 // world, 10
-        denv = Engine({'env_num': n_dog, 'robot_base': 'xmls/doggo.xml', 'num_steps': 1000, '_seed': 0},
-                      env_id_offset=rank * n_dog)
-        denv.reset()
-        do_ = denv.rollout(Td)
-        for _ in range(3):        # 40 steps: contacts established
-            lib.gx_rollout(denv._h, Td, pr(do_['obs']), pr(do_['act']), pr(do_['reward']), pr(do_['cost']), pr(do_['done']), sp)
-        torch.cuda.synchronize()
-        if barrier:
-            barrier()
-        ev0.record(stream)
-        rc = lib.gx_rollout(denv._h, Td, pr(do_['obs']), pr(do_['act']), pr(do_['reward']), pr(do_['cost']), pr(do_['done']), sp)
-        assert rc == 0, lib.gx_last_error()
-        ev1.record(stream)
-        torch.cuda.synchronize()
-        dt_dog = ev0.elapsed_time(ev1) * 1e-3
-        if dist:
-            t = torch.tensor([dt_dog], device='cuda', dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt_dog = float(t.item())
+                  "bound": "issue/latency (Newton contact solver per env), not HBM", "finite": fin}
+        Td = 10
+        dt_dog, fin = legged_run('xmls/doggo.xml', n_leg, Td, 3)
         legged["doggo"] = {"workload": "Goal_Doggo_8Hazards, 65536 envs in total, same protocol (free-joint root, capsule "
-                                       "contacts, dense Newton per env: one thread per env)",
-                           "envs_per_gpu": n_dog, "steps": Td, "value": world * n_dog * Td / dt_dog, "unit": "env-steps/s",
+                                       "contacts, dense Newton per env)",
+                           "envs_per_gpu": n_leg, "steps": Td, "value": world * n_leg * Td / dt_dog, "unit": "env-steps/s",
                            "us_per_step": 1e6 * dt_dog / Td, "bound": "dependent-issue latency (DESIGN.md 5b), not HBM",
-                           "finite": bool(torch.isfinite(do_['obs']).all().item())}
-        del denv, do_
-        torch.cuda.empty_cache()
+                           "finite": fin}
+    # ---- BASELINE configs[4]: PPO-Lagrangian rollout + update, env on the CUDA kernels ----
+    ppo = None
+    if not args.no_ppo:
+        ppo = ppo_section(torch, dist, rank, world, local_rank)
     clocks = sampler.stop()
 
     # the dominant kernel's average duration over the timed region (one launch per step)
-    step_us = 1e6 * dt / K
+    step_us = 1e6 * dt / S
     achieved = n * ALG_BYTES_STEP / (step_us * 1e-6) / 1e9
 
     sweep = None
@@ -520,15 +549,16 @@ def main():
             per = big * (116 + 4 * (od + 3)) + 8 * big * 2
             Rb = max(2, int(L2_BYTES * 2.0 / per) + 1)
             bl = [Batch(Engine, torch, big, 0, seed=100 + k, n_act=2, pool_size=pool_size) for k in range(Rb)]
-            time_steps(torch, lib, bl, 5 * Rb, stream)
-            kk = 30 * Rb
-            gs = GraphedSteps(torch, lib, bl, kk)
-            gs.run(stream)
-            d = gs.run(stream)
+            e_ = time_steps(torch, lib, bl, 4 * Rb, stream) / (4 * Rb)
+            kk = max(2 * Rb, min(4096, int(REGION_SECONDS / e_) + 1))
+            gs = Regions(torch, lambda sp_, t0, steps: issue_steps(lib, bl, steps, sp_, t0=t0), kk, flush_buf)
+            ds = gs.measure(stream, 5)
+            d = median(ds)
             del gs
             gbs = big * ALG_BYTES_STEP * kk / d / 1e9
-            sweep.append({"envs": big, "batches": Rb, "us_per_step": 1e6 * d / kk,
-                          "env_steps_per_s": big * kk / d, "achieved_gbs": gbs, "frac": gbs / hbm_peak})
+            sweep.append({"envs": big, "batches": Rb, "steps_per_region": kk, "us_per_step": 1e6 * d / kk,
+                          "env_steps_per_s": big * kk / d, "achieved_gbs": gbs, "frac": gbs / hbm_peak,
+                          "region_ms_min_max": [1e3 * min(ds), 1e3 * max(ds)]})
             del bl
             torch.cuda.empty_cache()
 
@@ -544,34 +574,35 @@ def main():
                     "single_thread": rate1}
 
     if rank == 0:
+        kname = "gx_step_lanes_kernel" if n <= 12288 else "gx_step_kernel"
+        traffic, traffic_src = load_traffic(kname, n)
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
-            "steps": K, "warmup": warmup, "ms_per_step": 1e3 * dt / K, "higher_is_better": True,
+            "steps": K, "warmup": warmup, "ms_per_step": 1e3 * dt / S, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(n, world, "CUDA: fused step + auto-reset (gx_step_autoreset), one kernel "
-                                                     "launch per step, the K launches replayed as CUDA graphs of <= 2048 "
-                                                     "nodes, in-kernel episode statistics"),
-                           l2=f"cold: {R} independent {n}-env batches stepped round-robin, working set "
-                              f"{working_set / 1e6:.0f} MB > 126 MB L2; value_l2_resident is the single-batch loop"),
-            "value_l2_resident": world * n * K / dt_hot,
-            "value_stream_launch": world * n * K / dt_stream,
+                                                     "launch per step, replayed as CUDA graphs, in-kernel episode statistics"),
+                           l2=f"cold: 512 MB flush before every region; {R} independent {n}-env batches stepped "
+                              f"round-robin, working set {working_set / 1e6:.0f} MB > 2 x 126 MB L2",
+                           timing=f"window = {K} steps; region = {M} windows = {S} launches back to back; "
+                                  f"{REGIONS} regions, median reported; events enqueued behind an untimed replay"),
+            "timing": {"windows_per_region": M, "launches_per_region": S, "regions": REGIONS,
+                       "region_ms_median": 1e3 * dt, "region_ms_min": 1e3 * min(region_s), "region_ms_max": 1e3 * max(region_s),
+                       "window_ms": 1e3 * dt / M},
+            "value_l2_resident": world * n * S / dt_hot,
+            "value_stream_launch": world * n * Ss / dt_stream,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4,
                     "d2h_bytes_per_step": n * (od + 3) * 4, "steps": Tp * reps_p,
-                    "path": "Engine.rollout_host -> gx_rollout_host: every step's action comes from pinned host "
-                            "memory (H2D) and every step's obs|reward|done|cost lands in pinned host memory (D2H); "
-                            "chunks of steps are pipelined over a compute and a copy stream; timed on the host "
-                            "clock around the calls, results read on the host",
                     "per_step_sync": {"value": e2e_sync_value, "steps": Ke,
-                                      "path": "Engine.step_host -> gx_step_host: H2D action -> fused step+auto-reset "
-                                              "-> D2H -> stream sync, one blocking call per step (what a policy in "
-                                              "the loop needs)"}},
-            "gpu_launches": K,
+                                      "path": "Engine.step_host: one blocking call per step (policy in the loop)"},
+                    "path": "Engine.rollout_host -> gx_rollout_host: every step's action from pinned host memory, every "
+                            "step's obs|reward|done|cost into pinned host memory, chunks pipelined over two streams; "
+                            "host clock around the calls, results read on the host"},
+            "gpu_launches": S,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": LANES_TRAFFIC_4096 if n == 4096 else None,
-                         "traffic_source": "profiles/r1_prof_lanes_4096_summary.txt: dram read 626.7 KB + write 0 KB per "
-                                           "launch under ncu --set full (the 0.9 MB of outputs stay in the 126 MB L2 "
-                                           "within one launch)", "kernel": "gx_step_lanes_kernel<true,true>",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kname + "<true,true>" if n <= 12288 else kname,
                          "alg_bytes_per_env_step": ALG_BYTES_STEP, "envs_per_launch": n,
                          "us_per_launch": step_us, "peak_source": peak_src,
                          "note": "latency-bound at 4096 envs (1.4 MB per launch, one dependent chain per env); "
@@ -582,6 +613,8 @@ def main():
                         "frac": ro_value / world * ALG_BYTES_ROLLOUT / 1e9 / hbm_peak},
             "episode_stats": gxd.episode_summary(stats.tolist()),
         }
+        if ppo is not None:
+            line["ppo_lag"] = ppo
         if legged is not None:
             line["legged"] = legged
         if sweep is not None:
@@ -592,6 +625,35 @@ def main():
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ppo_section(torch, dist, rank, world, local_rank):
+    """BASELINE.json configs[4]: PPO-Lagrangian on Goal_Point_8Hazards, 4096 envs per GPU, max_ep_len 200
+    (ppo_train.py:354-417 rollout + :314-348 update).  Returns env-steps/s of the rollout alone (policy forward +
+    sample + env step + buffer writes, replayed as a CUDA graph) and of whole epochs (rollout + GAE + update)."""
+    from guardx_b200 import make, ppo_lag
+    n, T, epochs = 4096, 200, 3
+    env = make(TASK, env_num=n, seed=rank, max_ep_len=T)
+    cfg = ppo_lag.PPOLagConfig(epochs=epochs, max_ep_len=T, target_cost=0.0)
+    ac, log = ppo_lag.ppo_lag(env, cfg)
+    torch.cuda.synchronize()
+    per_epoch = (log[-1]['Time'] - log[0]['Time']) / (epochs - 1)     # epoch 0 carries the warm-up
+    roll = ppo_lag.RolloutTimer(env, ac, T)
+    ts = []
+    for _ in range(5):
+        ts.append(roll.run())
+    dt_roll = median(max_over_ranks(torch, dist, ts))
+    per_epoch = max_over_ranks(torch, dist, [per_epoch])[0]
+    out = {"workload": f"PPO-Lagrangian, {TASK}, {n} envs per GPU, {T} steps per epoch (BASELINE.json configs[4])",
+           "rollout": {"value": world * n * T / dt_roll, "unit": "env-steps/s", "us_per_step": 1e6 * dt_roll / T,
+                       "how": roll.how},
+           "rollout_plus_update": {"value": world * n * T / per_epoch, "unit": "env-steps/s", "epoch_s": per_epoch,
+                                   "how": "rollout + GAE kernels + 80/80/80 full-batch Adam iterations (torch), gradient "
+                                          "all-reduce over NCCL"},
+           "last_epoch": {k: log[-1][k] for k in ("EpRet", "EpCost", "Lambda", "KL", "StopIter") if k in log[-1]}}
+    del env
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

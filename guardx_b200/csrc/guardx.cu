@@ -86,7 +86,7 @@ struct gx_env {
   // staging for gx_step_host
   float* stage;  // [n*act_dim | n*obs_dim | n | n | n]
   // gx_step_host zero-copy route: cached mapping of the caller's pinned buffers
-  const float *zc_act, *zc_dact; float *zc_obs, *zc_dobs, *zc_dr, *zc_dd, *zc_dc; bool zc_ok;
+  const float* zc_dact; float *zc_dobs, *zc_dr, *zc_dd, *zc_dc; bool zc_ok;
   // articulated robots (GX_ROBOT_ART): host + device copy of the model, joint-state SoA
   GxArtModel* art_host;
   GxArtDev art;
@@ -1158,14 +1158,14 @@ GX_API int gx_step_host(gx_env* e, const float* h_action, float* h_obs, float* h
   // Zero-copy route (pinned, mapped buffers): ONE launch, the kernel reads the actions from and
   // writes obs | reward | done | cost to host memory itself -- the PCIe writes overlap the
   // computation and the two copy-engine hand-offs disappear (4096 envs: 49.9 -> 40.6 us per step).
-  // The pointer check is cached on the (action, obs) pair of the previous call.
-  if (h_action != e->zc_act || h_obs != e->zc_obs) {
+  // All five pointers are looked up on EVERY call (a few 100 ns each): a cached mapping would go
+  // stale when the caller frees a pinned buffer and a pageable one lands at the same address.
+  {
     const void *da, *dob, *dr, *dd, *dc;
     e->zc_ok = gx_host_mapped(h_action, &da) && gx_host_mapped(h_obs, &dob) && gx_host_mapped(h_reward, &dr) &&
                gx_host_mapped(h_done, &dd) && gx_host_mapped(h_cost, &dc) &&
                !(reinterpret_cast<uintptr_t>(da) & 7u);
     if (e->zc_ok) { e->zc_dact = (const float*)da; e->zc_dobs = (float*)dob; e->zc_dr = (float*)dr; e->zc_dd = (float*)dd; e->zc_dc = (float*)dc; }
-    e->zc_act = h_action; e->zc_obs = h_obs;
   }
   if (e->zc_ok && !getenv("GX_NO_ZERO_COPY")) {
     if (int rc = gx_step_impl(e, e->zc_dact, e->zc_dobs, e->zc_dr, e->zc_dd, e->zc_dc, nullptr, nullptr, stream,
@@ -1222,40 +1222,64 @@ GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h
     // ~8 MB of output per chunk keeps the copy engine near its large-transfer rate
     int S = (int)((8u << 20) / (sizeof(float) * (od + 3) * n));
     S = S < 1 ? 1 : (S > 64 ? 64 : S);
-    for (int k = 0; k < 2; ++k) GX_CUDA(cudaMalloc((void**)&e->ring[k], sizeof(float) * per_step * S));
-    GX_CUDA(cudaStreamCreateWithFlags(&e->rs_compute, cudaStreamNonBlocking));
-    GX_CUDA(cudaStreamCreateWithFlags(&e->rs_copy, cudaStreamNonBlocking));
-    GX_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
-    for (int k = 0; k < 2; ++k) {
-      GX_CUDA(cudaEventCreateWithFlags(&e->ev_computed[k], cudaEventDisableTiming));
-      GX_CUDA(cudaEventCreateWithFlags(&e->ev_copied[k], cudaEventDisableTiming));
+    // build everything in locals and commit to the handle only when all of it exists
+    float* ring[2] = {nullptr, nullptr};
+    cudaStream_t sc = nullptr, sy = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaError_t err = cudaSuccess;
+    for (int k = 0; k < 2 && err == cudaSuccess; ++k) err = cudaMalloc((void**)&ring[k], sizeof(float) * per_step * S);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&sy, cudaStreamNonBlocking);
+    for (int k = 0; k < 5 && err == cudaSuccess; ++k) err = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+    if (err != cudaSuccess) {
+      for (int k = 0; k < 5; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+      if (sc) cudaStreamDestroy(sc);
+      if (sy) cudaStreamDestroy(sy);
+      for (int k = 0; k < 2; ++k) if (ring[k]) cudaFree(ring[k]);
+      cudaGetLastError();
+      return gx_fail(GX_ECUDA, "gx_rollout_host: pipeline setup failed: %s", cudaGetErrorString(err));
     }
+    e->ring[0] = ring[0]; e->ring[1] = ring[1];
+    e->rs_compute = sc; e->rs_copy = sy;
+    e->ev_in = ev[0]; e->ev_computed[0] = ev[1]; e->ev_computed[1] = ev[2]; e->ev_copied[0] = ev[3]; e->ev_copied[1] = ev[4];
     e->ring_steps = S;
   }
   const int S = e->ring_steps;
-  GX_CUDA(cudaEventRecord(e->ev_in, user));
-  GX_CUDA(cudaStreamWaitEvent(e->rs_compute, e->ev_in, 0));
+  // any failure below drains both pipeline streams before returning, so that no D2H copy into the
+  // caller's buffers is still in flight when the caller sees the error
+  int rc = GX_OK;
+  auto cu = [&](cudaError_t err, const char* what) {
+    if (rc == GX_OK && err != cudaSuccess) rc = gx_fail(GX_ECUDA, "gx_rollout_host: %s failed: %s", what, cudaGetErrorString(err));
+    return rc == GX_OK;
+  };
   int chunk = 0;
-  for (int t0 = 0; t0 < T; t0 += S, ++chunk) {
+  if (cu(cudaEventRecord(e->ev_in, user), "cudaEventRecord")) cu(cudaStreamWaitEvent(e->rs_compute, e->ev_in, 0), "cudaStreamWaitEvent");
+  for (int t0 = 0; t0 < T && rc == GX_OK; t0 += S, ++chunk) {
     const int k = chunk & 1, s_now = (T - t0 < S) ? (T - t0) : S;
     float* d_obs = e->ring[k];
     float* d_rew = d_obs + od * n * S;
     float* d_done = d_rew + n * S;
     float* d_cost = d_done + n * S;
     float* d_act = d_cost + n * S;
-    if (chunk >= 2) GX_CUDA(cudaStreamWaitEvent(e->rs_compute, e->ev_copied[k], 0));
-    GX_CUDA(cudaMemcpyAsync(d_act, h_action + ad * n * t0, sizeof(float) * ad * n * s_now, cudaMemcpyHostToDevice, e->rs_compute));
-    for (int t = 0; t < s_now; ++t)
-      if (int rc = gx_step_impl(e, d_act + ad * n * t, d_obs + od * n * t, d_rew + n * t, d_done + n * t, d_cost + n * t,
-                                nullptr, nullptr, e->rs_compute, true, "gx_rollout_host"))
-        return rc;
-    GX_CUDA(cudaEventRecord(e->ev_computed[k], e->rs_compute));
-    GX_CUDA(cudaStreamWaitEvent(e->rs_copy, e->ev_computed[k], 0));
-    GX_CUDA(cudaMemcpyAsync(h_obs + od * n * t0, d_obs, sizeof(float) * od * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
-    GX_CUDA(cudaMemcpyAsync(h_reward + n * t0, d_rew, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
-    GX_CUDA(cudaMemcpyAsync(h_done + n * t0, d_done, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
-    GX_CUDA(cudaMemcpyAsync(h_cost + n * t0, d_cost, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy));
-    GX_CUDA(cudaEventRecord(e->ev_copied[k], e->rs_copy));
+    if (chunk >= 2 && !cu(cudaStreamWaitEvent(e->rs_compute, e->ev_copied[k], 0), "cudaStreamWaitEvent")) break;
+    if (!cu(cudaMemcpyAsync(d_act, h_action + ad * n * t0, sizeof(float) * ad * n * s_now, cudaMemcpyHostToDevice, e->rs_compute), "H2D copy")) break;
+    for (int t = 0; t < s_now && rc == GX_OK; ++t)
+      rc = gx_step_impl(e, d_act + ad * n * t, d_obs + od * n * t, d_rew + n * t, d_done + n * t, d_cost + n * t,
+                        nullptr, nullptr, e->rs_compute, true, "gx_rollout_host");
+    if (rc != GX_OK) break;
+    if (!cu(cudaEventRecord(e->ev_computed[k], e->rs_compute), "cudaEventRecord")) break;
+    if (!cu(cudaStreamWaitEvent(e->rs_copy, e->ev_computed[k], 0), "cudaStreamWaitEvent")) break;
+    cu(cudaMemcpyAsync(h_obs + od * n * t0, d_obs, sizeof(float) * od * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy), "D2H copy");
+    cu(cudaMemcpyAsync(h_reward + n * t0, d_rew, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy), "D2H copy");
+    cu(cudaMemcpyAsync(h_done + n * t0, d_done, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy), "D2H copy");
+    cu(cudaMemcpyAsync(h_cost + n * t0, d_cost, sizeof(float) * n * s_now, cudaMemcpyDeviceToHost, e->rs_copy), "D2H copy");
+    if (!cu(cudaEventRecord(e->ev_copied[k], e->rs_copy), "cudaEventRecord")) break;
+  }
+  if (rc != GX_OK) {
+    cudaStreamSynchronize(e->rs_compute);
+    cudaStreamSynchronize(e->rs_copy);
+    cudaGetLastError();
+    return rc;
   }
   // the caller's stream (and the host) see the finished rollout
   GX_CUDA(cudaStreamWaitEvent(user, e->ev_copied[(chunk - 1) & 1], 0));

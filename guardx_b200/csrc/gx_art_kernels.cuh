@@ -250,7 +250,10 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ai = m.root.dof[r].act;
-      if (ai >= 0) cr[r] = action ? action[(size_t)i * nu + ai] : gx_art_synth_action(p, g, age, ai);
+      if (ai >= 0) {
+        cr[r] = action ? action[(size_t)i * nu + ai] : gx_art_synth_action(p, g, age, ai);
+        if (act_out && live && lane == 0) act_out[(size_t)i * nu + ai] = cr[r];   // actuated root dof (none of the shipped xmls has one)
+      }
     }
 #pragma unroll
     for (int j = 0; j < LPL; ++j) {

@@ -19,6 +19,12 @@ import torch
 N_EPISODES, SUM_RET, SUM_COST, SUM_LEN, SUM_RET2, SUM_COST2, TOTAL_COST, TOTAL_STEPS = range(8)
 
 
+def rank() -> int:
+    """proc_id() (mpi_tools.py:38-40); 0 without a process group."""
+    import torch.distributed as dist
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 def shard(total_envs: int, rank: int, world: int) -> tuple[int, int]:
     """(local env count, global id of local env 0) for a contiguous block split."""
     assert 0 <= rank < world and total_envs >= world

@@ -305,8 +305,13 @@ class Engine:
         _abi.check(L, L.gx_rollout(self._h, T, self._ptr(out.get("obs")), self._ptr(out.get("act")),
                                    self._ptr(out.get("reward")), self._ptr(out.get("cost")),
                                    self._ptr(out.get("done")), self._stream()), "gx_rollout")
-        if "obs" in out:
-            self._obs = out["obs"][-1]
+        # Engine._obs / _done / _reward describe the LAST step: keep them current when the rollout
+        # produced them, otherwise invalidate them so that a following reset_done() / done_indices()
+        # asserts instead of working on pre-rollout tensors
+        self._obs = out["obs"][-1] if "obs" in out else None
+        self._done = out["done"][-1] if "done" in out else None
+        self._reward = out["reward"][-1] if "reward" in out else None
+        self._info = None
         return out
 
     # ------------------------------------------------- state / diagnostics

@@ -201,6 +201,35 @@ class GraphedRolloutStep:
             self.graph.replay()
 
 
+class RolloutTimer:
+    """Times ONE epoch's rollout (T steps: policy forward + sample, env step + auto-reset, the
+    eight buffer writes) with CUDA events on the current stream; used by bench.py."""
+
+    how = "policy forward + Gaussian sample + gx_step_autoreset + 8 buffer writes per step, one CUDA graph replayed T times"
+
+    def __init__(self, env, ac, T):
+        N, dev = env.env_num, env.device
+        f = lambda *s: torch.empty(*s, device=dev)
+        self.T, self.env = T, env
+        self.buf = dict(obs=f(T, N, env.observation_space.shape[0]), act=f(T, N, env.action_space.shape[0]), rew=f(T, N),
+                        cost=f(T, N), done=f(T, N), val=f(T, N), cval=f(T, N), logp=f(T, N))
+        env.reset()
+        env.stats_reset()
+        self.step = GraphedRolloutStep(env, ac, self.buf)
+        self.step.run(env.reset(), T)      # warm-up
+        torch.cuda.synchronize(dev)
+
+    def run(self) -> float:
+        o = self.env.reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(self.env.device)
+        e0.record()
+        self.step.run(o, self.T)
+        e1.record()
+        torch.cuda.synchronize(self.env.device)
+        return e0.elapsed_time(e1) * 1e-3
+
+
 def ppo_lag(env, cfg: PPOLagConfig | None = None, ac: ActorCritic | None = None):
     """Train on ``env`` (a guardx_b200.Engine).  Returns (actor_critic, per-epoch log)."""
     cfg = cfg or PPOLagConfig()
@@ -209,6 +238,9 @@ def ppo_lag(env, cfg: PPOLagConfig | None = None, ac: ActorCritic | None = None)
     obs_dim, act_dim = env.observation_space.shape[0], env.action_space.shape[0]
     ac = ac or ActorCritic(obs_dim, act_dim, cfg.hidden_sizes).to(dev)
     gxd.sync_params(ac)
+    # ppo_train.py:257: seed += 10000 * proc_id() -- AFTER the parameters are shared, so that every rank
+    # explores with its own noise stream on identical weights
+    torch.manual_seed(cfg.seed + 10000 * gxd.rank())
     pi_opt = torch.optim.Adam(ac.pi_params(), lr=cfg.pi_lr)
     v_opt = torch.optim.Adam(ac.v.parameters(), lr=cfg.vf_lr)
     vc_opt = torch.optim.Adam(ac.vc.parameters(), lr=cfg.vf_lr)
@@ -249,7 +281,9 @@ def ppo_lag(env, cfg: PPOLagConfig | None = None, ac: ActorCritic | None = None)
         gxd.allreduce_stats(stats)
         summ = gxd.episode_summary(stats.tolist())
         # episodes cut by the epoch end count with what they accumulated (ppo_train.py:392-396 logs them too)
-        ep_cost = summ['EpCost'] if summ['Episodes'] > 0 else float(buf['cost'].sum(0).mean())
+        # (no finished episode anywhere: the mean accumulated cost per env, summed over ALL ranks so that
+        # every rank applies the same multiplier update)
+        ep_cost = summ['EpCost'] if summ['Episodes'] > 0 else float(gxd.global_mean(buf['cost'].sum(0).mean()))
         info = ppo_update(ac, pi_opt, v_opt, vc_opt, data, cfg, lmd)
         lmd = max(0.0, lmd + cfg.lam_lr * (ep_cost - cfg.target_cost))     # trpolag.py:466-471
         row = dict(Epoch=epoch, Lambda=lmd, Time=time.time() - t_start, EpCostUsed=ep_cost,

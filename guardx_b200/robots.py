@@ -1,7 +1,7 @@
 """Built-in robot descriptions (what ``Robot(robot_base)`` loads in the reference,
 world.py:422-445): the kinematic trees, geoms and actuators of the planar-root robots of
 ``safe_rl_envs/xmls``, written as ``mjcf.Spec`` builders so that no XML file is needed at
-run time.  ``tests/test_mjcf.py`` checks each one against ``mjcf.parse_mjcf`` of the
+run time.  ``tests/test_art_cpu.py`` checks each one against ``mjcf.parse_mjcf`` of the
 reference's own file when ``/root/reference`` is present, and against committed golden
 constants otherwise.
 

@@ -30,9 +30,11 @@
  *     tests/golden/refsrc_*.npz, tests/test_oracle_golden.py);
  *   - the mjx.step / mjx.forward physics (engine.py:655, 668, 721) is
  *     **parity unpinned**: it is a restatement of the published algorithm under
- *     assumptions A1-A4, cross-checked only against an independent float64
- *     derivation (tests/test_oracle_physics.py).  tools/dump_reference_fixture.py
- *     regenerates a true fixture on any machine that has jax + mujoco.
+ *     assumptions A1-A4, cross-checked only against the independent dense
+ *     numpy restatement of mjx.step on the compiled Point model
+ *     (tests/test_art_cpu.py::test_numpy_mjx_step_equals_closed_form_point_oracle).
+ *     tests/tools/dump_reference_fixture.py regenerates a true fixture on any
+ *     machine that has jax + mujoco.
  *
  * Arithmetic: fp32 throughout, compiled -ffp-contract=off, elementary functions
  * from guardx_b200/csrc/gx_math.h (shared with the kernels so that integer
