@@ -56,9 +56,10 @@ ALG_BYTES_STEP = 348      # single-step API contract
 ALG_BYTES_ROLLOUT = 192   # multi-step kernel, I/O only
 L2_BYTES = 126e6
 FLUSH_BYTES = 512 << 20       # written before every timed region: evicts the L2
-REGION_SECONDS = 0.025        # a timed region lasts at least this long, whatever --steps is
+REGION_SECONDS = float(os.environ.get("GX_BENCH_REGION_S", "0.025"))   # a timed region lasts at least this long, whatever --steps is
 MAX_REGION_STEPS = 1 << 16    # graph nodes per region (bounds capture time when --steps is huge)
-REGIONS = 7                   # regions measured; the median is reported
+BURN_IN = 2000                # random-action steps every batch takes before anything is timed (num_steps = 1000)
+REGIONS = int(os.environ.get("GX_BENCH_REGIONS", "7"))   # regions measured; the median is reported
 TASK = "Goal_Point_8Hazards"
 
 
@@ -134,7 +135,7 @@ def host_threads():
 
 def workload_config(n, world, how):
     return {"workload": f"{TASK}, {n} envs per GPU, random-action rollout (a ~ U(-1,1), pre-generated), "
-                        "step + reset_done every step",
+                        f"step + reset_done every step, stationary (each batch burnt in for {BURN_IN} steps)",
             "envs_per_gpu": n, "total_envs": n * world, "how": how,
             "parallelism": f"dp{world} (independent env shards, no data-path collective)"}
 
@@ -198,6 +199,13 @@ class Batch:
         self.env = Engine({'env_num': n, 'num_steps': 1000, '_seed': seed}, env_id_offset=offset,
                           pool_size=pool_size)
         self.env.reset()
+        # burn-in: BURN_IN random-action steps (fused rollout kernel, no outputs) so that the timed steps see the
+        # STATIONARY workload -- episodes in every phase, a few envs finishing (and being re-placed) in every
+        # launch.  A freshly reset batch has no done env for its first ~130 steps, and a 4096-env launch is as
+        # slow as its slowest warp: timing fresh batches under-reports the step time by ~8 %.
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rc = self.env._lib.gx_rollout(self.env._h, BURN_IN, None, None, None, None, None, sp)
+        assert rc == 0, self.env._lib.gx_last_error()
         g = torch.Generator(device='cuda').manual_seed(1234 + offset)
         self.act = torch.rand(n_act, n, 2, device='cuda', generator=g) * 2 - 1
         od = self.env.obs_flat_size
@@ -336,6 +344,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-legged", action="store_true", help="skip the ant / 65536-env measurement")
     ap.add_argument("--no-ppo", action="store_true", help="skip the PPO-Lagrangian section")
+    ap.add_argument("--value-only", action="store_true", help="diagnostic: print value / timing after the graph-replayed regions and stop")
     args = ap.parse_args()
 
     # stdout carries the ONE JSON line and nothing else: native libraries (NCCL prints its version banner with
@@ -406,6 +415,14 @@ def main():
     stats = torch.stack([b.env.stats() for b in batches]).sum(0)
     gxd.allreduce_stats(stats)   # NCCL all-reduce of the 8-double episode statistics vector
     value = world * n * S / dt
+    if args.value_only:
+        if rank == 0:
+            _emit({"value": value, "ms_per_step": 1e3 * dt / S, "steps": K, "windows_per_region": M,
+                   "region_ms": [1e3 * x for x in region_s], "clocks": sampler.stop()})
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     # ---- the same steps launched one by one from Python (no graph) ----------
     Ss = max(K, 2000)
     dt_stream = max_over_ranks(torch, dist, [time_steps(torch, lib, batches, Ss, stream, barrier)])[0]
