@@ -28,14 +28,19 @@ One JSON line on stdout (rank 0).  Keys beyond the driver's contract:
 Timing (the same whatever --steps K is): a WINDOW is exactly K fused step launches; a timed
 REGION is M back-to-back windows, M chosen so that a region lasts >= 20 ms; REGIONS (7) regions
 are measured and the MEDIAN is reported (min / max beside it), so ms_per_step x steps = one
-window.  Every region is a chain of CUDA graphs; all regions, their L2 flushes and their
-CUDA events are enqueued while the GPU is still busy with an untimed replay, so neither
-graph-launch latency nor the host is inside a timed region.
+window.  Every region is a chain of CUDA graphs; all regions and their CUDA events are
+enqueued while the GPU is still busy with SETTLE_SECONDS of untimed replays, so neither
+graph-launch latency nor the host is inside a timed region, and the GPU is in its sustained
+state (on this pool a B200 steps ~6 % faster during the first ~0.25 s of a burst of
+memory-heavy work than afterwards, at a constant SM clock: tools/diag_regions.py).
 
-L2 policy: every region starts after a 512 MB write (L2 flush, outside the events) and every
-timed step touches a batch whose state, actions and output buffers have not been touched for
-R-1 steps, where R batches x ~1.5 MB exceed twice the 126 MB L2 (config.l2 says so); the
-L2-resident number is reported beside it.
+L2 policy: every timed step touches a batch whose state, actions, layout pool and output
+buffers have not been touched for R-1 steps, where R batches x ~1.5 MB (+ 1.3 MB of layout
+pool each) exceed twice the 126 MB L2 (config.l2 says so); the L2-resident number is reported
+beside it.  (A replay starts at batch 0 again while the previous one ended at batch
+(S-1) mod R, so at most R/2 of the S launches of a region can see lines of the previous
+replay: < 2 %.  GX_BENCH_FLUSH=1 adds a 512 MB write before every region instead; the big
+writes themselves push the GPU into its slower sustained state, so they are off by default.)
 """
 from __future__ import annotations
 
@@ -59,6 +64,8 @@ FLUSH_BYTES = 512 << 20       # written before every timed region: evicts the L2
 REGION_SECONDS = float(os.environ.get("GX_BENCH_REGION_S", "0.025"))   # a timed region lasts at least this long, whatever --steps is
 MAX_REGION_STEPS = 1 << 16    # graph nodes per region (bounds capture time when --steps is huge)
 BURN_IN = 2000                # random-action steps every batch takes before anything is timed (num_steps = 1000)
+SETTLE_SECONDS = 0.3          # untimed replays before the timed regions (sustained GPU state)
+FLUSH = bool(int(os.environ.get("GX_BENCH_FLUSH", "0")))   # 512 MB write before every region (see the docstring)
 REGIONS = int(os.environ.get("GX_BENCH_REGIONS", "7"))   # regions measured; the median is reported
 TASK = "Goal_Point_8Hazards"
 
@@ -135,7 +142,7 @@ def host_threads():
 
 def workload_config(n, world, how):
     return {"workload": f"{TASK}, {n} envs per GPU, random-action rollout (a ~ U(-1,1), pre-generated), "
-                        f"step + reset_done every step, stationary (each batch burnt in for {BURN_IN} steps)",
+                        f"step + reset_done every step, stationary (random episode phases + {BURN_IN} burn-in steps per batch)",
             "envs_per_gpu": n, "total_envs": n * world, "how": how,
             "parallelism": f"dp{world} (independent env shards, no data-path collective)"}
 
@@ -199,10 +206,16 @@ class Batch:
         self.env = Engine({'env_num': n, 'num_steps': 1000, '_seed': seed}, env_id_offset=offset,
                           pool_size=pool_size)
         self.env.reset()
-        # burn-in: BURN_IN random-action steps (fused rollout kernel, no outputs) so that the timed steps see the
-        # STATIONARY workload -- episodes in every phase, a few envs finishing (and being re-placed) in every
-        # launch.  A freshly reset batch has no done env for its first ~130 steps, and a 4096-env launch is as
-        # slow as its slowest warp: timing fresh batches under-reports the step time by ~8 %.
+        # STATIONARY workload: a freshly reset batch has every env at step 0 of its episode, and with random
+        # actions most episodes end by the num_steps timeout -- all in the same launch.  A 4096-env launch is
+        # as slow as its slowest warp, so what a launch costs depends on whether ANY env finishes in it.  The
+        # timed steps therefore start from mixed episode phases: each env's step counter is set to a random
+        # phase (through the public state injection), then BURN_IN random-action steps (fused rollout kernel,
+        # no outputs) let positions and phases decorrelate.  ~4 envs of 4096 finish in every launch.
+        g = torch.Generator(device='cuda').manual_seed(4321 + offset + 7919 * seed)
+        st = self.env.get_state()
+        st[:, 10] = torch.randint(0, 1000, (n,), device='cuda', generator=g).float()   # Engine._steps (gx_get_state row)
+        self.env.set_state(st)
         sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         rc = self.env._lib.gx_rollout(self.env._h, BURN_IN, None, None, None, None, None, sp)
         assert rc == 0, self.env._lib.gx_last_error()
@@ -257,6 +270,7 @@ class Regions:
     flush (512 MB write, evicts the 126 MB L2), event, graphs, event, flush, ... -- so that
     neither the host nor the graph-launch latency is inside a region."""
 
+
     def __init__(self, torch, issue, S, flush_buf, chunk=2048):
         self.torch, self.S, self.flush_buf = torch, S, flush_buf
         self.graphs = []
@@ -276,13 +290,14 @@ class Regions:
         for g in self.graphs:
             g.replay()
 
-    def measure(self, stream, regions, barrier=None, flush=True):
+    def measure(self, stream, regions, barrier=None, flush=FLUSH, settle=1):
         torch = self.torch
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(regions)]
         if barrier:
             barrier()
         torch.cuda.synchronize()
-        self.replay()                      # untimed: the GPU is busy while everything below is enqueued
+        for _ in range(max(1, settle)):    # untimed: the GPU is busy (and settled) while everything below is enqueued
+            self.replay()
         for r, (e0, e1) in enumerate(evs):
             if flush and self.flush_buf is not None:
                 self.flush_buf.fill_(float(r))
@@ -384,14 +399,14 @@ def main():
 
     # ---- batches: R independent n-env batches, working set > 2 x L2 -----------
     od = 43
-    per_batch = n * (116 + 4 * (od + 3)) + 8 * n * 8   # state + outputs + 8 action slices
+    per_batch = n * (116 + 4 * (od + 3)) + 8 * n * 8   # state + outputs + 8 action slices (the 1.3 MB layout pool is extra)
     R = int(L2_BYTES * 2.0 / per_batch) + 1
     R = max(2, min(R, 512))
     pool_size = 16384
     batches = [Batch(Engine, torch, n, rank * n, seed=k, n_act=8, pool_size=pool_size) for k in range(R)]
     for b in batches:
         b.env.stats_reset()   # in-kernel episode statistics on (what ppo_train.py:370-376 does on the host)
-    working_set = R * per_batch
+    working_set = R * (per_batch + pool_size * 80)
     flush_buf = torch.empty(FLUSH_BYTES // 4, device='cuda')
 
     sampler = ClockSampler(local_rank)
@@ -404,7 +419,8 @@ def main():
     issue = lambda sp, t0, steps: issue_steps(lib, batches, steps, sp, t0=t0)
     for attempt in range(4):
         reg = Regions(torch, issue, M * K, flush_buf)
-        region_s = max_over_ranks(torch, dist, reg.measure(stream, REGIONS, barrier))
+        settle = int(SETTLE_SECONDS / (M * K * est * 0.7)) + 1
+        region_s = max_over_ranks(torch, dist, reg.measure(stream, REGIONS, barrier, settle=settle))
         dt = median(region_s)                                         # one region = M windows = S steps
         del reg
         if dt >= 0.8 * REGION_SECONDS or M >= m_cap:
@@ -428,7 +444,7 @@ def main():
     dt_stream = max_over_ranks(torch, dist, [time_steps(torch, lib, batches, Ss, stream, barrier)])[0]
     # ---- same graph chain over one batch only (L2-resident state) ----------
     hot = Regions(torch, lambda sp, t0, steps: issue_steps(lib, batches[:1], steps, sp, t0=t0), S, None)
-    dt_hot = median(max_over_ranks(torch, dist, hot.measure(stream, 5, barrier, flush=False)))
+    dt_hot = median(max_over_ranks(torch, dist, hot.measure(stream, 5, barrier, flush=False, settle=4)))
     del hot
 
     # ---- e2e: host buffers through Engine.step_host -----------------------
@@ -569,7 +585,7 @@ def main():
             e_ = time_steps(torch, lib, bl, 4 * Rb, stream) / (4 * Rb)
             kk = max(2 * Rb, min(4096, int(REGION_SECONDS / e_) + 1))
             gs = Regions(torch, lambda sp_, t0, steps: issue_steps(lib, bl, steps, sp_, t0=t0), kk, flush_buf)
-            ds = gs.measure(stream, 5)
+            ds = gs.measure(stream, 5, settle=6)
             d = median(ds)
             del gs
             gbs = big * ALG_BYTES_STEP * kk / d / 1e9
@@ -599,10 +615,11 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(n, world, "CUDA: fused step + auto-reset (gx_step_autoreset), one kernel "
                                                      "launch per step, replayed as CUDA graphs, in-kernel episode statistics"),
-                           l2=f"cold: 512 MB flush before every region; {R} independent {n}-env batches stepped "
-                              f"round-robin, working set {working_set / 1e6:.0f} MB > 2 x 126 MB L2",
+                           l2=f"cold: {R} independent {n}-env batches (own state, actions, outputs, layout pool) stepped "
+                              f"round-robin, working set {working_set / 1e6:.0f} MB > 2 x 126 MB L2"
+                              + ("; 512 MB flush before every region" if FLUSH else ""),
                            timing=f"window = {K} steps; region = {M} windows = {S} launches back to back; "
-                                  f"{REGIONS} regions, median reported; events enqueued behind an untimed replay"),
+                                  f"{REGIONS} regions, median reported; events enqueued behind {SETTLE_SECONDS} s of untimed replays"),
             "timing": {"windows_per_region": M, "launches_per_region": S, "regions": REGIONS,
                        "region_ms_median": 1e3 * dt, "region_ms_min": 1e3 * min(region_s), "region_ms_max": 1e3 * max(region_s),
                        "window_ms": 1e3 * dt / M},

@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const 
     float gx_, gy_;
     gx_load_static<NH_CT>(s, i, gx_, gy_, hz_regs);
     const float2 a = action[i];
+    float4 ep_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (STATS) ep_acc = gx_stats_load(s, i);
     float qa[3];
     int32_t bins[AUX ? 1 + GX_MAX_HAZARDS : 1];
     GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a.x, a.y, row,
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const 
       ax[0] = o.flags; ax[1] = o.violations;
       for (int k = 0; k < 1 + p.nh; ++k) ax[2 + k] = bins[k];
     }
-    if (STATS) gx_stats_step(s, i, o.reward, o.cost, o.done);
+    if (STATS) gx_stats_commit(s, i, ep_acc, o.reward, o.cost, o.done);
   }
   const int rows = min(32, p.n - wbase);
   gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
@@ -481,7 +483,7 @@ __global__ void gx_rollout_kernel(const __grid_constant__ gx_params p, const GxS
 // ---- 16-lanes-per-env variants (small batches; gx_lanes.cuh) ------------------
 template <bool STATS, bool AUTORESET>
 __global__ void __launch_bounds__(128) gx_step_lanes_kernel(
-    const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool,
+    const __grid_constant__ gx_params p, const __grid_constant__ GxState s, const float* __restrict__ pool,
     const float2* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
     float* __restrict__ done, float* __restrict__ cost, float* __restrict__ qacc, double* __restrict__ stats) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,12 +499,18 @@ __global__ void __launch_bounds__(128) gx_step_lanes_kernel(
   float gx_ = g.x, gy_ = g.y, ox, oy;
   gx_load_object(s, i, sub, gx_, gy_, ox, oy);
   const float2 a = action[i];
+  float4 ep_acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (STATS && sub == 9) ep_acc = gx_stats_load(s, i);   // needed at the very end: load it now
   float qa[3];
-  GxLaneStep r = gx_step_lanes(p, sub, gmask, d, gx_, gy_, ox, oy, a.x, a.y, qacc ? qa : nullptr);
-  if (AUTORESET && r.out.done > 0.0f) {
-    const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
-    gx_reset_done_lanes(p, s, i, sub, gmask, live, lay, d, gx_, gy_, ox, oy, r.obs);
-    r.c0 = 0.0f; r.c1 = 0.0f; r.c2 = 0.0f;
+  GxLaneStep r;
+  if (AUTORESET) {
+    // the layout this env is re-placed with if the step ends its episode (keyed by the env's age after the step):
+    // drawn and loaded now, so that it is in registers when the step knows
+    const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age + 1, GX_STREAM_PICK);
+    const GxSpecLayout sp = gx_spec_layout(lay, sub);
+    r = gx_step_autoreset_lanes(p, s, i, sub, gmask, live, lay, sp, d, gx_, gy_, ox, oy, a.x, a.y, qacc ? qa : nullptr);
+  } else {
+    r = gx_step_lanes(p, sub, 0xffffffffu, gmask, d, gx_, gy_, ox, oy, a.x, a.y, qacc ? qa : nullptr);
   }
   if (live) {
     gx_store_row_lanes(obs + (size_t)i * 43, sub, r.obs, r.c0, r.c1, r.c2, d);
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(128) gx_step_lanes_kernel(
     if (sub == 4) done[i] = r.out.done;
     if (sub == 5) cost[i] = r.out.cost;
     if (qacc && sub >= 6 && sub <= 8) qacc[3 * (size_t)i + (sub - 6)] = qa[sub - 6];
-    if (STATS && sub == 9) gx_stats_step(s, i, r.out.reward, r.out.cost, r.out.done);
+    if (STATS && sub == 9) gx_stats_commit(s, i, ep_acc, r.out.reward, r.out.cost, r.out.done);
   }
 }
 
@@ -538,7 +546,7 @@ __global__ void __launch_bounds__(128) gx_rollout_lanes_kernel(
     const uint64_t tg = d.age;
     gx_u32x4 u = gx_philox4x32_10((uint32_t)gid, (uint32_t)tg, (uint32_t)(tg >> 32), GX_STREAM_ACTION, p.seed_lo, p.seed_hi);
     const float a0 = gx_uniform(u.v[0], -1.0f, 1.0f), a1 = gx_uniform(u.v[1], -1.0f, 1.0f);
-    GxLaneStep r = gx_step_lanes(p, sub, gmask, d, gx_, gy_, ox, oy, a0, a1, nullptr);
+    GxLaneStep r = gx_step_lanes(p, sub, 0xffffffffu, gmask, d, gx_, gy_, ox, oy, a0, a1, nullptr);
     if (STATS && live && sub == 9) gx_stats_step(s, i, r.out.reward, r.out.cost, r.out.done);
     if (r.out.done > 0.0f) {
       const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
@@ -1312,6 +1320,27 @@ GX_API int gx_debug_math(int fn, const float* a, const float* b, float* out, flo
   if (n == 0) return GX_OK;
   gx_debug_math_kernel<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(fn, a, b, out, out2, n);
   GX_LAUNCH_CHECK("gx_debug_math_kernel");
+  return GX_OK;
+}
+
+// SM clock as the kernels see it: one thread spins for `spin_cycles` SM cycles and reports
+// cycles / globaltimer-nanoseconds (MHz).  NVML samples at a few Hz; this probe can sit
+// between two graph launches on the stream (bench.py uses it to report the clock the timed
+// steps actually ran at).
+__global__ void gx_debug_sm_clock_kernel(long long spin_cycles, float* out_mhz) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const long long c0 = clock64();
+  long long c1 = c0;
+  while (c1 - c0 < spin_cycles) c1 = clock64();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  *out_mhz = t1 > t0 ? (float)((double)(c1 - c0) * 1000.0 / (double)(t1 - t0)) : 0.0f;
+}
+
+GX_API int gx_debug_sm_clock(float* out_mhz, int32_t spin_cycles, void* stream) {
+  if (!out_mhz || spin_cycles <= 0) return gx_fail(GX_EINVAL, "gx_debug_sm_clock: bad argument");
+  gx_debug_sm_clock_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long)spin_cycles, out_mhz);
+  GX_LAUNCH_CHECK("gx_debug_sm_clock_kernel");
   return GX_OK;
 }
 

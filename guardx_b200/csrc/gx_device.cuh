@@ -450,18 +450,25 @@ __device__ __forceinline__ void gx_art_hazard(const GxState& s, const float* lay
 // Per-env accumulators only -- no atomics and no grid-wide reduction in the step
 // (4096 same-address atomics per launch cost more than the step itself).  The
 // sums over envs are taken, deterministically, when the statistics are read.
-__device__ __forceinline__ void gx_stats_step(const GxState& s, int i, float reward, float cost, float done) {
-  float4 e = s.ep[i];
+// Split in two so that latency-bound kernels can issue the accumulator load at their top (it is
+// the only load a step would otherwise issue at its very end, a full DRAM round trip on the
+// critical path of every launch).  The sums over finished episodes are updated with
+// fire-and-forget vector reductions (red.global.add.v4.f32): each env's slot has a single writer
+// per launch, so the result is the same single fp32 addition, and nothing waits for it.
+__device__ __forceinline__ float4 gx_stats_load(const GxState& s, int i) { return s.ep[i]; }
+
+__device__ __forceinline__ void gx_stats_commit(const GxState& s, int i, float4 e, float reward, float cost, float done) {
   e.x += reward; e.y += cost; e.z += 1.0f; e.w += cost;
   if (done > 0.0f) {
-    float4 f0 = s.fin[i], f1 = s.fin[(size_t)s.cap + i];
-    f0.x += 1.0f; f0.y += e.x; f0.z += e.y; f0.w += e.z;
-    f1.x += e.x * e.x; f1.y += e.y * e.y;
-    s.fin[i] = f0;
-    s.fin[(size_t)s.cap + i] = f1;
+    atomicAdd(&s.fin[i], make_float4(1.0f, e.x, e.y, e.z));
+    atomicAdd(&s.fin[(size_t)s.cap + i], make_float4(e.x * e.x, e.y * e.y, 0.0f, 0.0f));
     e.x = 0.f; e.y = 0.f; e.z = 0.f;
   }
   s.ep[i] = e;
+}
+
+__device__ __forceinline__ void gx_stats_step(const GxState& s, int i, float reward, float cost, float done) {
+  gx_stats_commit(s, i, gx_stats_load(s, i), reward, cost, done);
 }
 
 #endif  // GX_DEVICE_CUH_

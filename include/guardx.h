@@ -306,6 +306,9 @@ int gx_compact_done(const float* done, int32_t n, int32_t* idx, int32_t* count, 
  *      a, b, out, out2: device arrays of n floats (b/out2 may be NULL). ------ */
 int gx_debug_math(int fn, const float* a, const float* b, float* out, float* out2, int n,
                   void* stream);
+/* diagnostics: the SM clock (MHz) a kernel sees on `stream`'s device, measured over
+ * `spin_cycles` cycles of one spinning thread against %globaltimer; *out_mhz is a DEVICE float */
+int gx_debug_sm_clock(float* out_mhz, int32_t spin_cycles, void* stream);
 
 #ifdef __cplusplus
 }
