@@ -108,14 +108,23 @@ def parse(config: dict) -> dict:
     return merged
 
 
+# touch sensors each robot file defines; the JAX Engine never reads `sensors_obs`, but callers see it in
+# `env.config` and it is part of what a pickled env carries (safe_rl_env_config.py:123, 179, 207, 266)
+_BASE_SENSORS = ['accelerometer', 'velocimeter', 'gyro', 'magnetometer']
+_ANKLE_TOUCH = [f'touch_ankle_{i}{s}' for s in 'ab' for i in (1, 2, 3, 4)]
+_TASK_SENSORS = {'Swimmer': _BASE_SENSORS + [f'touch_point{i}' for i in (1, 2, 3, 4)],
+                 'Ant': _BASE_SENSORS + _ANKLE_TOUCH, 'Doggo': _BASE_SENSORS + _ANKLE_TOUCH,
+                 'Walker': _BASE_SENSORS + ['touch_right_foot', 'touch_left_foot']}
+
+
 def configuration(task: str) -> dict:
-    """The runnable subset of safe_rl_env_config.configuration_list."""
-    # safe_rl_env_config.py:59-82 (Point), :111-136 (Swimmer), :195-221 (Ant), :254-280 (Walker):
-    # the four entries differ only in robot_base
+    """The runnable subset of safe_rl_env_config.configuration_list: equal, key by key, to the reference's
+    dicts (tests/golden/task_configs.json, tests/test_oracle_golden.py)."""
+    # safe_rl_env_config.py:59-82 (Point), :111-136 (Swimmer), :167-193 (Doggo), :195-221 (Ant), :254-280 (Walker)
     name = task[:-len("_noconti")] if task.endswith("_noconti") else task
     parts = name.split("_")
     if len(parts) == 3 and parts[0] == "Goal" and parts[2] == "8Hazards" and parts[1] in _TASK_ROBOT:
-        return {
+        cfg = {
             'robot_base': _TASK_ROBOT[parts[1]],
             'task': 'goal',
             'goal_size': 0.5,
@@ -127,6 +136,9 @@ def configuration(task: str) -> dict:
             'hazards_num': 8,
             'hazards_size': 0.3,
         }
+        if parts[1] in _TASK_SENSORS:
+            cfg['sensors_obs'] = list(_TASK_SENSORS[parts[1]])
+        return cfg
     raise NotImplementedError(
         f"task {task!r}: built are Goal_{{Point,Swimmer,Ant,Walker,Doggo}}_8Hazards "
         "(the Push/Chase/Defense/Ghost entries are rejected by the reference Engine itself, engine.py:326-328)")

@@ -15,7 +15,7 @@ import ctypes as C
 
 import numpy as np
 
-from guardx_b200 import config as gxconfig
+from . import oracle_config as gxconfig     # the oracle's own defaults / lowering / model compile
 from . import mjx_numpy as mx
 from . import oracle as _o
 
@@ -28,9 +28,8 @@ class ArtOracleEngine:
     def __init__(self, config: dict, dtype=np.float32):
         self.L = _o.lib()
         self.config = gxconfig.parse(config)
-        self.model = gxconfig.compiled_model(self.config)
-        assert self.model is not None, 'ArtOracleEngine is for the articulated robots; the Point has oracle.OracleEngine'
-        self.gx_config = gxconfig.lower(self.config, 0, 0, self.model)
+        self.model = gxconfig.world_model(self.config)
+        self.gx_config = gxconfig.lower(self.config, 0, 0)
         self.mm = mx.MjxModel(self.model, dtype)
         self.dtype = dtype
         m = self.model

@@ -31,7 +31,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from guardx_b200 import mjcf
+from . import mj_compile as mjc     # the oracle's own model compiler: nothing here imports the product
 
 mjMINVAL = 1e-15
 mjMINIMP, mjMAXIMP = 0.0001, 0.9999
@@ -58,7 +58,7 @@ def quat2mat(q):
 class MjxModel:
     """mjx.put_model: the compiled constants cast to the working dtype."""
 
-    def __init__(self, m: mjcf.Model, dtype=np.float32, capsules=None):
+    def __init__(self, m: 'mjc.OModel', dtype=np.float32, capsules=None):
         self.m = m
         self.dtype = dtype
         f = lambda a: np.asarray(a, dtype)
@@ -86,16 +86,16 @@ class MjxModel:
         # capsule contacts are restated for free-joint robots (Doggo); for the planar robots the
         # capsule-plane pairs of the swimmer sit exactly at dist == margin and are treated as never
         # active (assumption A2), as is the Point's box-plane pair
-        with_capsules = bool((m.jnt_type == mjcf.JNT_FREE).any()) if capsules is None else capsules
+        with_capsules = bool((m.jnt_type == mjc.FREE).any()) if capsules is None else capsules
         for g1, g2 in m.contact_pairs:
             t1, t2 = int(m.geom_type[g1]), int(m.geom_type[g2])
-            if t2 == mjcf.GEOM_PLANE:
+            if t2 == mjc.PLANE:
                 g1, g2, t1, t2 = g2, g1, t2, t1
-            if t1 == mjcf.GEOM_PLANE and t2 == mjcf.GEOM_SPHERE:
+            if t1 == mjc.PLANE and t2 == mjc.SPHERE:
                 self.sphere_plane.append((g1, g2))
-            elif with_capsules and t1 == mjcf.GEOM_PLANE and t2 == mjcf.GEOM_CAPSULE:
+            elif with_capsules and t1 == mjc.PLANE and t2 == mjc.CAPSULE:
                 self.capsule_plane.append((g1, g2))
-            elif with_capsules and t1 == mjcf.GEOM_CAPSULE and t2 == mjcf.GEOM_CAPSULE:
+            elif with_capsules and t1 == mjc.CAPSULE and t2 == mjc.CAPSULE:
                 self.capsule_capsule.append((g1, g2))
             else:
                 self.ignored_pairs.append((g1, g2))
@@ -117,7 +117,7 @@ def kinematics(mm: MjxModel, qpos):
         quat = quat_mul(xquat[:, p], np.broadcast_to(mm.body_quat[b], (N, 4)))
         for k in range(m.body_jntnum[b]):
             j = m.body_jntadr[b] + k
-            if m.jnt_type[j] == mjcf.JNT_FREE:     # the pose is the qpos (position + normalised quaternion)
+            if m.jnt_type[j] == mjc.FREE:     # the pose is the qpos (position + normalised quaternion)
                 a = m.jnt_qposadr[j]
                 pos = qpos[:, a:a + 3].copy()
                 quat = qpos[:, a + 3:a + 7] / np.linalg.norm(qpos[:, a + 3:a + 7], axis=1, keepdims=True)
@@ -128,7 +128,7 @@ def kinematics(mm: MjxModel, qpos):
             xanchor[:, j] = pos + np.einsum('nij,j->ni', R, mm.jnt_pos[j])
             xaxis[:, j] = np.einsum('nij,j->ni', R, mm.jnt_axis[j])
             dq = qpos[:, m.jnt_qposadr[j]] - mm.qpos0[m.jnt_qposadr[j]]
-            if m.jnt_type[j] == mjcf.JNT_SLIDE:
+            if m.jnt_type[j] == mjc.SLIDE:
                 pos = pos + xaxis[:, j] * dq[:, None]
             else:
                 half = dq * dt(0.5)
@@ -166,14 +166,14 @@ def com_pos(mm: MjxModel, d):
     for j in range(m.njnt):
         i = m.jnt_dofadr[j]
         b = m.jnt_bodyid[j]
-        if m.jnt_type[j] == mjcf.JNT_FREE:
+        if m.jnt_type[j] == mjc.FREE:
             # three translations along the world axes, three rotations about the body axes
             for a in range(3):
                 cdof[:, i + a, 3 + a] = 1
                 ax = d['xmat'][:, b, :, a]
                 cdof[:, i + 3 + a, :3] = ax
                 cdof[:, i + 3 + a, 3:] = _cross(ax, root_com[:, b] - d['xpos'][:, b])
-        elif m.jnt_type[j] == mjcf.JNT_SLIDE:
+        elif m.jnt_type[j] == mjc.SLIDE:
             cdof[:, i, 3:] = d['xaxis'][:, j]
         else:
             cdof[:, i, :3] = d['xaxis'][:, j]
@@ -230,7 +230,7 @@ def com_vel(mm: MjxModel, d, qvel):
     for b in range(1, m.nbody):
         v = cvel[:, m.body_parentid[b]].copy()
         k0 = 0
-        if m.body_jntnum[b] and m.jnt_type[m.body_jntadr[b]] == mjcf.JNT_FREE:
+        if m.body_jntnum[b] and m.jnt_type[m.body_jntadr[b]] == mjc.FREE:
             # mj_comVel: the translations have cdof_dot = 0; the three rotations all use the velocity
             # after the translations (not sequentially updated)
             i0 = m.body_dofadr[b]
@@ -254,7 +254,7 @@ def passive(mm: MjxModel, qpos, qvel):
     m = mm.m
     f = -mm.dof_damping[None, :] * qvel
     for j in range(m.njnt):
-        if m.jnt_stiffness[j] != 0 and m.jnt_type[j] in (mjcf.JNT_SLIDE, mjcf.JNT_HINGE):
+        if m.jnt_stiffness[j] != 0 and m.jnt_type[j] in (mjc.SLIDE, mjc.HINGE):
             f[:, m.jnt_dofadr[j]] -= mm.jnt_stiffness[j] * (qpos[:, m.jnt_qposadr[j]] - mm.qpos_spring[m.jnt_qposadr[j]])
     return f
 
@@ -373,7 +373,7 @@ def make_constraint(mm: MjxModel, d, qpos, qvel):
     def geom_pose(g):
         bd = m.geom_bodyid[g]
         pos = d['xpos'][:, bd] + np.einsum('nij,j->ni', d['xmat'][:, bd], mm.geom_pos[g])
-        mat = np.einsum('nij,jk->nik', d['xmat'][:, bd], mjcf.quat2mat(m.geom_quat[g]).astype(dt))
+        mat = np.einsum('nij,jk->nik', d['xmat'][:, bd], mjc._rot(m.geom_quat[g]).astype(dt))
         return pos, mat
 
     def make_frame(a):
@@ -652,7 +652,7 @@ def integrate_pos(mm: MjxModel, qpos, qvel):
     out = qpos.copy()
     for j in range(m.njnt):
         a, i = m.jnt_qposadr[j], m.jnt_dofadr[j]
-        if m.jnt_type[j] == mjcf.JNT_FREE:
+        if m.jnt_type[j] == mjc.FREE:
             out[:, a:a + 3] = qpos[:, a:a + 3] + mm.timestep * qvel[:, i:i + 3]
             w = qvel[:, i + 3:i + 6]
             wn = np.linalg.norm(w, axis=1)

@@ -11,7 +11,8 @@ import subprocess
 
 import numpy as np
 
-from guardx_b200 import _abi, config as gxconfig
+from guardx_b200 import _abi      # ctypes mirror of include/guardx.h only (the struct IS the boundary)
+from . import oracle_config as gxconfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgxoracle.so")

@@ -8,13 +8,13 @@ from guardx_b200 import _abi
 from guardx_b200.engine import Engine
 
 lib = _abi.load_library()
-n = 4096
+n = int(os.environ.get('N', '4096'))
 R = int(os.environ.get("R", "170"))
 if os.environ.get("FRESH"):
     bench.BURN_IN = 1
     _ri = torch.randint
     torch.randint = lambda lo, hi, *a, **k: _ri(0, 1, *a, **k)    # every env at phase 0: no env finishes for ~100 steps
-batches = [bench.Batch(Engine, torch, n, 0, seed=k, n_act=8, pool_size=16384) for k in range(R)]
+batches = [bench.Batch(Engine, torch, n, 0, seed=k, n_act=8, pool_size=16384 if n <= 16384 else 0) for k in range(R)]
 for b in batches:
     b.env.stats_reset()
 flush_buf = torch.empty(bench.FLUSH_BYTES // 4, device='cuda')
