@@ -235,6 +235,26 @@ class ArtOracleEngine:
             parts.append(self.qvel[:, nvr:])
         return np.concatenate(parts, 1).astype(np.float32)
 
+    def set_state(self, rows):
+        """inverse of get_state(): load env states read from the CUDA env (gx_get_state rows), so that the oracle can
+        take ONE step from wherever a large CUDA batch has got to (tests at BASELINE.json configs[3] size)."""
+        rows = np.asarray(rows, np.float32)
+        assert rows.shape[0] == self.n
+        nr, nvr = self.nq_robot, self.nv_robot
+        o = 0
+        self.qpos = np.zeros((self.n, self.model.nq), self.dtype); self.qvel = np.zeros((self.n, self.model.nv), self.dtype)
+        self.warm = np.zeros((self.n, self.model.nv), self.dtype)
+        self.qpos[:, :nr] = rows[:, o:o + nr]; o += nr
+        self.qvel[:, :nvr] = rows[:, o:o + nvr]; o += nvr
+        self.warm[:, :nvr] = rows[:, o:o + nvr]; o += nvr
+        self.prev_dist = rows[:, o].copy(); self.done = rows[:, o + 1].copy(); self.steps = rows[:, o + 2].copy(); o += 3
+        self.qpos[:, self.qadr['goal_x']] = rows[:, o]; self.qpos[:, self.qadr['goal_y']] = rows[:, o + 1]; o += 2
+        for h in range(self.nh):
+            self.qpos[:, self.qadr[f'hazard{h}_x']] = rows[:, o]; self.qpos[:, self.qadr[f'hazard{h}_y']] = rows[:, o + 1]; o += 2
+        if self.free_root:
+            self.qvel[:, nvr:] = rows[:, o:o + self.model.nv - nvr]; o += self.model.nv - nvr
+        assert o == rows.shape[1], (o, rows.shape)
+
     def round_state_to_fp32(self):
         """Make the float64 state exactly what get_state() hands to the CUDA env (one-step parity
         from bit-identical inputs)."""

@@ -245,3 +245,40 @@ def test_doggo_step_replays_from_a_cuda_graph(mods):
         o, r, d, i = b_env.step_autoreset(act)
         assert torch.equal(o, obs) and torch.equal(r, rdc[0]) and torch.equal(d, rdc[1]) and torch.equal(i['cost'], rdc[2])
     assert torch.isfinite(obs).all()
+
+
+def test_doggo_config4_size_one_step_vs_oracle(mods):
+    """65 536 Doggo envs per GPU use the per-block chunks of the GLOBAL scratch (gx_tree.cuh) in a grid of 2048 blocks;
+    the small tests above run one or two blocks.  Roll the big batch 40 steps on its own, hand 512 random envs to the
+    float64 oracle, one step from bit-identical states with the same actions; tolerances of the small test."""
+    Engine, Oracle, pool = mods
+    n, k = 65536, 512
+    g = Engine({'env_num': n, 'robot_base': 'xmls/doggo.xml', 'num_steps': 1000, '_seed': 4})
+    g.reset()
+    for _ in range(5):
+        out = g.rollout(8)
+        del out
+    st = cpu(g.get_state())
+    rng = np.random.default_rng(22)
+    finite = np.isfinite(st).all(1)
+    assert finite.mean() > 0.999
+    ids = rng.choice(np.flatnonzero(finite), k, replace=False)
+    o = Oracle({'env_num': k, 'robot_base': 'xmls/doggo.xml', 'num_steps': 1000, '_seed': 4}, dtype=np.float64)
+    o.reset(pool[:k])
+    o.set_state(st[ids])
+    a = rng.uniform(-1.2, 1.2, (n, NU)).astype(np.float32)
+    og, rg, dg, ig = g.step(torch.from_numpy(a).cuda(), want_aux=True)
+    oo, ro, do, io = o.step(a[ids])
+    kq = NU + 34 + NQ
+    close(cpu(og)[ids][:, :kq], oo[:, :kq], 5e-5, 5e-5, 'doggo 65536-env grid: obs (ctrl..qpos)')
+    close(cpu(og)[ids][:, kq:], oo[:, kq:], 2e-3, 5e-4, 'qvel')
+    close(cpu(rg)[ids], ro, 5e-5, 0, 'reward')
+    close(cpu(ig['cost'])[ids], io['cost'], 5e-5, 0, 'cost')
+    qs = 1 + np.abs(io['qacc']).max(1, keepdims=True)
+    close(cpu(ig['obs']['qacc'])[ids] / qs, io['qacc'] / qs, 5e-4, 0, 'qacc relative to the env max')
+    clear = (np.abs(io['dist'] - 0.5) > 1e-4) & (np.abs(np.abs(io['d_dist']) - 1) > 1e-4)
+    assert (cpu(dg)[ids] == do)[clear].all()
+    aux = cpu(ig['aux'])[ids]
+    bins_o = np.concatenate([io['goal_bin'], io['hazard_bins']], 1)
+    assert (aux[:, 2:11] != bins_o).sum() <= 2
+    assert int((o.last_data['efc_D'] > 0).sum(1).max()) >= 12      # the robots have landed: capsule contacts active
