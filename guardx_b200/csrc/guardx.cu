@@ -298,6 +298,93 @@ __device__ __forceinline__ void gx_reset_done_env(const gx_params& p, const GxSt
   gx_reset_row<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, row);
 }
 
+// ---- Engine.step + Engine.reset_done with ONE observation pass (thread per env) ----------------
+// Same idea as gx_step_autoreset_lanes (gx_lanes.cuh): whether the env finishes is known before the
+// lidar (goal distance, jump, timeout; and the NaN/Inf guard reduces to ctrl / qpos / qvel when pose
+// and objects are finite and of sane magnitude), so a finishing env is re-placed FIRST and the single
+// observation pass produces its reset observation; reward, cost, violations, flags are the step's.
+// A finishing thread pays a Philox draw, five 128-bit pool loads and eight square roots instead of a
+// second full observation pass, which is what its 31 warp-mates would otherwise wait for.
+// Exotic states -- reachable through gx_set_state / caller layouts only -- take the reference order
+// (step observation, then re-place, then reset observation), out of line.
+// `fused_ok` (uniform): observe_vel / observe_acc off and a lidar that cannot overflow.
+// (Tried: hazards left in the state arrays and a NON-unrolled hazard loop, to shrink the ~3 k-instruction
+// hot path after ncu showed stall_no_instruction 2.0 per issue at 2^20 envs: no gain there, and 13.3 -> 19.9 us
+// per step at 65 536 envs, where the in-loop loads are exposed -- dropped.)
+template <int NH_CT>
+__device__ __noinline__ GxStepOut gx_step_then_reset_env(const gx_params& p, const GxState& s, const float* pool, int i, GxDyn& d,
+                                                         float& gx_, float& gy_, float4* hz_regs, float a0, float a1, float* row,
+                                                         float* qacc) {
+  GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a0, a1, row, qacc, nullptr);
+  if (o.done > 0.0f) {
+    const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
+    gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
+  }
+  return o;
+}
+
+template <int NH_CT>
+__device__ __forceinline__ GxStepOut gx_step_env_autoreset(const gx_params& p, const GxState& s, const float* pool, int i,
+                                                           GxDyn& d, float& gx_, float& gy_, float4* hz_regs, float a0,
+                                                           float a1, float* row, float* qacc, bool fused_ok) {
+  bool sane = fused_ok & (gx_abs(d.qx) < GX_SANE_BOUND) & (gx_abs(d.qy) < GX_SANE_BOUND) & !gx_notfinite(d.qth) &
+              (gx_abs(gx_) < GX_SANE_BOUND) & (gx_abs(gy_) < GX_SANE_BOUND);
+#pragma unroll
+  for (int k = 0; k < (NH_CT + 1) / 2; ++k)
+    sane &= (gx_abs(hz_regs[k].x) < GX_SANE_BOUND) & (gx_abs(hz_regs[k].y) < GX_SANE_BOUND) &
+            (gx_abs(hz_regs[k].z) < GX_SANE_BOUND) & (gx_abs(hz_regs[k].w) < GX_SANE_BOUND);
+  if (!sane) return gx_step_then_reset_env<NH_CT>(p, s, pool, i, d, gx_, gy_, hz_regs, a0, a1, row, qacc);
+  float c0 = d.hc * a0, c1 = d.hs * a0, c2 = a1;
+  const float last_dist = d.prev_dist, last_done = d.done;
+  float px, py, r00, r10;
+  for (int k = 0; k < p.substeps; ++k) gx_mjx_step_point(p, d, c0, c1, c2, px, py, r00, r10, qacc);
+  float dist;
+  {
+    float dx = gx_ - px, dy = gy_ - py;
+    dist = gx_sqrt(dx * dx + dy * dy);
+  }
+  const int bad = gx_notfinite(c0) | gx_notfinite(c1) | gx_notfinite(c2) | gx_notfinite(d.qx) | gx_notfinite(d.qy) |
+                  gx_notfinite(d.qth) | gx_notfinite(d.vx) | gx_notfinite(d.vy) | gx_notfinite(d.vw);
+  const float last = last_done > 0.0f ? dist : last_dist;
+  const float d_dist = last - dist;
+  GxStepOut out;
+  out.reward = d_dist * p.reward_distance;
+  out.done = dist < p.goal_size ? 1.0f : 0.0f;
+  out.flags = out.done > 0.0f ? GX_AUX_GOAL : 0;
+  if (gx_abs(d_dist) > 1.0f) { out.done = 1.0f; out.reward = 0.0f; out.flags |= GX_AUX_JUMP; }
+  if (bad) { out.reward = 0.0f; out.done = 1.0f; out.flags |= GX_AUX_GUARD; }
+  if (d.steps > p.num_steps) { out.done = 1.0f; out.flags |= GX_AUX_TIMEOUT; }
+  d.steps = out.done > 0.0f ? 0.0f : d.steps + 1.0f;
+  d.done = out.done;
+  d.prev_dist = dist;
+  d.hc = r00;
+  d.hs = r10;
+  d.age += 1;
+  float cost_step = 0.0f;
+  int viol_step = 0;
+  if (out.done > 0.0f) {
+    // the step's cost at the step pose (engine.py:804-811), then the re-placement
+#pragma unroll
+    for (int h = 0; h < NH_CT; ++h) {
+      const float4 v = hz_regs[h >> 1];
+      const float hx = (h & 1) ? v.z : v.x, hy = (h & 1) ? v.w : v.y;
+      float dx = hx - px, dy = hy - py;
+      float dh = gx_sqrt(dx * dx + dy * dy);
+      float term = p.hazards_size - gx_min(dh, p.hazards_size);
+      if (term > 0.0f) ++viol_step;
+      cost_step = cost_step + term;
+    }
+    const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
+    gx_place<NH_CT>(p, s, i, lay, gx_, gy_, hz_regs, d);
+    px = d.qx; py = d.qy; r00 = 1.0f; r10 = 0.0f;   // gx_kinematics(0) returns exactly (1, 0)
+    c0 = 0.0f; c1 = 0.0f; c2 = 0.0f;
+  }
+  GxObsOut o = gx_obs_row<NH_CT>(p, s, i, gx_, gy_, hz_regs, d, c0, c1, c2, px, py, r00, r10, row, nullptr);
+  out.cost = out.done > 0.0f ? cost_step : o.cost;
+  out.violations = out.done > 0.0f ? viol_step : o.violations;
+  return out;
+}
+
 // ---- episode statistics (ppo_train.py:370-376, 405-411 on the host) --------
 // Per-env accumulators only -- no atomics and no grid-wide reduction in the step
 // (4096 same-address atomics per launch cost more than the step itself).  The
@@ -340,12 +427,12 @@ __global__ void __launch_bounds__(1024) gx_stats_reduce_kernel(const GxState s, 
 // the step's, the observation row of a done env is its reset observation (what
 // step() followed by reset_done() returns).
 template <int NH_CT, bool AUX, bool STATS, bool AUTORESET>
-__global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const __grid_constant__ gx_params p, const GxState s,
+__global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const __grid_constant__ gx_params p, const __grid_constant__ GxState s,
                                const float* __restrict__ pool,
                                const float2* __restrict__ action, float* __restrict__ obs,
                                float* __restrict__ reward, float* __restrict__ done,
                                float* __restrict__ cost, float* __restrict__ qacc,
-                               int32_t* __restrict__ aux, double* __restrict__ stats) {
+                               int32_t* __restrict__ aux, double* __restrict__ stats, int bulk) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int wbase = i - lane;
@@ -355,6 +442,7 @@ __global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const 
   if (i < p.n) {
     GxDyn d;
     gx_load_dyn(s, i, d);
+    constexpr bool FUSED = AUTORESET && NH_CT != 0 && !AUX;
     float4 hz_regs[NH_CT ? (NH_CT + 1) / 2 : 1];
     float gx_, gy_;
     gx_load_static<NH_CT>(s, i, gx_, gy_, hz_regs);
@@ -363,11 +451,16 @@ __global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const 
     if (STATS) ep_acc = gx_stats_load(s, i);
     float qa[3];
     int32_t bins[AUX ? 1 + GX_MAX_HAZARDS : 1];
-    GxStepOut o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a.x, a.y, row,
-                                     qacc ? qa : nullptr, AUX ? bins : nullptr);
-    if (AUTORESET && o.done > 0.0f) {
-      const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
-      gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
+    GxStepOut o;
+    if constexpr (FUSED) {
+      const bool fused_ok = (p.off_vel < 0) & (p.off_acc < 0) & (p.use_exp ? p.neg_exp_gain <= 0.0f : p.lidar_max_dist > 0.0f);
+      o = gx_step_env_autoreset<NH_CT>(p, s, pool, i, d, gx_, gy_, hz_regs, a.x, a.y, row, qacc ? qa : nullptr, fused_ok);
+    } else {
+      o = gx_step_env<NH_CT>(p, s, i, d, gx_, gy_, hz_regs, a.x, a.y, row, qacc ? qa : nullptr, AUX ? bins : nullptr);
+      if (AUTORESET && o.done > 0.0f) {
+        const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
+        gx_reset_done_env<NH_CT>(p, s, i, lay, d, gx_, gy_, hz_regs, row);
+      }
     }
     gx_store_dyn(s, i, d);
     reward[i] = o.reward;
@@ -382,7 +475,7 @@ __global__ void __launch_bounds__(128, GX_STEP_MIN_BLOCKS) gx_step_kernel(const 
     if (STATS) gx_stats_commit(s, i, ep_acc, o.reward, o.cost, o.done);
   }
   const int rows = min(32, p.n - wbase);
-  gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane);
+  gx_store_tile_any(tile, obs + (size_t)wbase * p.obs_dim, rows, p.obs_dim, lane, bulk != 0);
 }
 
 template <int NH_CT>
@@ -951,9 +1044,9 @@ GX_API int gx_reset_with_layout(gx_env* e, const float* layout, float* obs, void
 template <int NH_CT>
 static void launch_step(gx_env* e, int grid, int block, size_t sh, cudaStream_t st, const float* action,
                         float* obs, float* reward, float* done, float* cost, float* qacc, int32_t* aux,
-                        bool autoreset) {
+                        bool autoreset, int bulk) {
   const float2* a2 = reinterpret_cast<const float2*>(action);
-#define GX_ST(AX, ST, AR) gx_step_kernel<NH_CT, AX, ST, AR><<<grid, block, sh, st>>>(e->p, e->s, e->pool, a2, obs, reward, done, cost, qacc, aux, e->stats)
+#define GX_ST(AX, ST, AR) gx_step_kernel<NH_CT, AX, ST, AR><<<grid, block, sh, st>>>(e->p, e->s, e->pool, a2, obs, reward, done, cost, qacc, aux, e->stats, bulk)
 #define GX_ST2(AX, ST) do { if (autoreset) GX_ST(AX, ST, true); else GX_ST(AX, ST, false); } while (0)
   if (aux) { if (e->stats_on) GX_ST2(true, true); else GX_ST2(true, false); }
   else { if (e->stats_on) GX_ST2(false, true); else GX_ST2(false, false); }
@@ -986,8 +1079,11 @@ static int gx_step_impl(gx_env* e, const float* action, float* obs, float* rewar
   }
   const int block = pick_block(e), grid = div_up(e->p.n, block);
   const size_t sh = tile_bytes(e, block);
-  if (fast_path(e)) launch_step<8>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset);
-  else launch_step<0>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset);
+  // observation tiles leave as asynchronous bulk copies, except towards mapped HOST memory (tile_stores: the
+  // zero-copy route of gx_step_host keeps the plain coalesced 128-bit stores)
+  const int bulk = tile_stores ? 0 : 1;
+  if (fast_path(e)) launch_step<8>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset, bulk);
+  else launch_step<0>(e, grid, block, sh, st, action, obs, reward, done, cost, qacc, aux, autoreset, bulk);
   GX_LAUNCH_CHECK("gx_step_kernel");
   return GX_OK;
 }

@@ -238,7 +238,6 @@ __device__ __forceinline__ GxLaneStep gx_step_lanes(const gx_params& p, int sub,
 // through gx_set_state) the env takes the reference order in gx_step_then_reset_lanes (out of line).
 // Results are bit-identical either way (tests/test_parity_gpu.py).
 // ---------------------------------------------------------------------------
-#define GX_SANE_BOUND 1.0e15f   // squares of ego components stay below FLT_MAX with a wide margin
 
 struct GxSpecLayout {   // speculative re-placement, loaded at the top of the kernel
   float2 goal, robot, obj;
@@ -272,7 +271,7 @@ __device__ __forceinline__ GxLaneStep gx_step_autoreset_lanes(const gx_params& p
   const bool obj_ok = (gx_abs(ox) < GX_SANE_BOUND) & (gx_abs(oy) < GX_SANE_BOUND);
   const bool objs_ok = (__ballot_sync(0xffffffffu, obj_ok) & gmask) == gmask;
   const bool sane = objs_ok & (gx_abs(d.qx) < GX_SANE_BOUND) & (gx_abs(d.qy) < GX_SANE_BOUND) & !gx_notfinite(d.qth) &
-                    (gx_abs(gx_) < GX_SANE_BOUND) & (gx_abs(gy_) < GX_SANE_BOUND);
+                    (gx_abs(gx_) < GX_SANE_BOUND) & (gx_abs(gy_) < GX_SANE_BOUND) & (p.neg_exp_gain <= 0.0f);
   if (!sane) {
     GxDyn dd = d;
     float g0 = gx_, g1 = gy_, o0 = ox, o1 = oy;
