@@ -14,6 +14,7 @@
 #include "../../include/guardx.h"
 #include "gx_device.cuh"
 #include "gx_lanes.cuh"
+#include "gx_policy.cuh"
 #include "gx_art.cuh"
 #include "gx_art_launch.h"
 #include "gx_tree_launch.h"
@@ -1389,6 +1390,45 @@ GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h
   GX_CUDA(cudaStreamWaitEvent(user, e->ev_copied[(chunk - 1) & 1], 0));
   GX_CUDA(cudaStreamSynchronize(e->rs_copy));
   return GX_OK;
+}
+
+// ---- policy half of a PPO rollout step (gx_policy.cuh) ---------------------------------
+template <int K1>
+static int gx_policy_launch(gx_env* e, cudaStream_t st, const float* W, const float* obs, uint64_t noise_seed, int A, float* act,
+                            float* val, float* cval, float* logp, float* mu_out) {
+  const size_t sh = gx_policy_smem_floats(K1) * sizeof(float);
+  static bool attr_set = false;      // per instantiation
+  if (!attr_set) {
+    GX_CUDA(cudaFuncSetAttribute(gx_policy_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    attr_set = true;
+  }
+  const int grid = div_up(e->p.n, GX_POL_ENVS);
+  gx_policy_kernel<K1><<<grid, GX_POL_THREADS, sh, st>>>(W, obs, e->p.n, e->p.obs_dim, A, e->s.d2, e->p.env_id_offset,
+                                                         e->p.seed_lo ^ (uint32_t)noise_seed, e->p.seed_hi ^ (uint32_t)(noise_seed >> 32),
+                                                         act, val, cval, logp, mu_out);
+  GX_LAUNCH_CHECK("gx_policy_kernel");
+  return GX_OK;
+}
+
+GX_API int64_t gx_policy_weight_floats(const gx_env* e) {
+  return e ? (int64_t)gx_policy_weight_count(e->p.obs_dim, gx_act_dim(e)) : (int64_t)GX_EINVAL;
+}
+
+GX_API int gx_policy_step(gx_env* e, const float* weights, const float* obs, uint64_t noise_seed, float* act, float* val,
+                          float* cval, float* logp, float* mu_out, void* stream) {
+  if (!e || !weights || !obs || !act || !val || !cval || !logp) return gx_fail(GX_EINVAL, "gx_policy_step: NULL argument");
+  if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_policy_step: call gx_reset first");
+  const int A = gx_act_dim(e);
+  if (A > GX_POL_MAX_ACT) return gx_fail(GX_EINVAL, "gx_policy_step: act_dim %d > %d", A, GX_POL_MAX_ACT);
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch ((e->p.obs_dim + 3) & ~3) {   // Point 43, Swimmer 46, Ant 64, Walker 70, Doggo 85 (+ 2 / 4 with observe_vel / observe_acc)
+#define GX_POL_CASE(K) case K: return gx_policy_launch<K>(e, st, weights, obs, noise_seed, A, act, val, cval, logp, mu_out)
+    GX_POL_CASE(44); GX_POL_CASE(48); GX_POL_CASE(52); GX_POL_CASE(64); GX_POL_CASE(68); GX_POL_CASE(72); GX_POL_CASE(76);
+    GX_POL_CASE(88); GX_POL_CASE(92);
+#undef GX_POL_CASE
+    default: return gx_fail(GX_EINVAL, "gx_policy_step: no kernel instantiated for obs_dim %d", e->p.obs_dim);
+  }
 }
 
 // ---- diagnostics -------------------------------------------------------------

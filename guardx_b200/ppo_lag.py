@@ -87,7 +87,8 @@ class PPOLagConfig:
     lmd_init: float = 0.0
     hidden_sizes: tuple = (64, 64)
     seed: int = 0
-    use_graph: bool = True         # capture policy + env step + buffer writes as ONE CUDA graph, replayed T times
+    use_fused: bool = True         # rollout step = gx_policy_step + gx_step_autoreset (two launches), the epoch one CUDA graph
+    use_graph: bool = True         # (when not fused) capture the torch policy + env step + buffer writes as one CUDA graph
     log: list = field(default_factory=list)
 
 
@@ -201,30 +202,123 @@ class GraphedRolloutStep:
             self.graph.replay()
 
 
+def pack_policy(ac: ActorCritic, obs_dim: int, act_dim: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """The actor-critic's parameters in the layout gx_policy_step reads (csrc/gx_policy.cuh):
+    W1 [K1][192] | B1 [192] | W2 [3][64][64] | B2 [192] | W3 [A+2][64] | B3 [A+2] | log_std [A], nets ordered
+    mu_net, v, vc; K1 = obs_dim rounded up to 4 (padding rows are zero).  Written in place into ``out`` when given,
+    so that a captured CUDA graph keeps reading the same buffer after every update."""
+    nets = (ac.mu_net, ac.v, ac.vc)
+    lin = [[m for m in net if isinstance(m, nn.Linear)] for net in nets]
+    assert all(len(l) == 3 and l[0].out_features == 64 and l[1].out_features == 64 for l in lin), \
+        'gx_policy_step is built for hidden_sizes == (64, 64) (the reference default, ppo_train.py:461)'
+    k1 = (obs_dim + 3) // 4 * 4
+    with torch.no_grad():
+        w1 = torch.zeros(k1, 192, device=ac.log_std.device)
+        w1[:obs_dim] = torch.cat([l[0].weight.t() for l in lin], 1)          # [obs_dim, 3*64]
+        parts = [w1.reshape(-1), torch.cat([l[0].bias for l in lin]),
+                 torch.stack([l[1].weight.t() for l in lin]).reshape(-1),       # [net][k][u]
+                 torch.cat([l[1].bias for l in lin]),
+                 torch.cat([l[2].weight for l in lin]).reshape(-1),             # rows: A actor heads, v, vc
+                 torch.cat([l[2].bias for l in lin]), ac.log_std]
+        flat = torch.cat([x.float().reshape(-1) for x in parts])
+        if out is None:
+            return flat.contiguous()
+        out.copy_(flat)
+        return out
+
+
+class FusedRollout:
+    """One epoch's rollout as 2 T kernel launches in ONE CUDA graph: per control step the policy kernel
+    (gx_policy_step: three MLPs + Gaussian sample + log-prob, reading the observation row the env wrote and writing
+    act / val / cval / logp straight into the rollout buffer) and the env kernel (gx_step_autoreset, reading that
+    action, writing reward / done / cost into the buffer and the next observation into the buffer's next row).
+    No copy kernels, no torch ops, no host work between the T steps.  ``buf['obs']`` has T + 1 rows."""
+
+    how = ("gx_policy_step (3 fp32 MLPs + Philox Gaussian sample + log-prob, one launch) + gx_step_autoreset per step, "
+           "outputs written in place into the rollout buffer; 2T launches replayed as one CUDA graph")
+
+    def __init__(self, env, ac, T, noise_seed=0):
+        import ctypes as C
+        N, dev = env.env_num, env.device
+        od, ad = env.observation_space.shape[0], env.action_space.shape[0]
+        f = lambda *s: torch.empty(*s, device=dev)
+        self.env, self.ac, self.T, self.od, self.ad = env, ac, T, od, ad
+        self.buf = dict(obs=f(T + 1, N, od), act=f(T, N, ad), rew=f(T, N), cost=f(T, N), done=f(T, N), val=f(T, N),
+                        cval=f(T, N), logp=f(T, N))
+        L, h = env._lib, env._h
+        assert int(L.gx_policy_weight_floats(h)) > 0
+        self.weights = torch.empty(int(L.gx_policy_weight_floats(h)), device=dev)
+        self.refresh_weights()
+        b = self.buf
+        p = lambda x: C.c_void_p(x.data_ptr())
+
+        def issue(sp):
+            for t in range(T):
+                rc = L.gx_policy_step(h, p(self.weights), p(b['obs'][t]), C.c_uint64(noise_seed), p(b['act'][t]), p(b['val'][t]),
+                                      p(b['cval'][t]), p(b['logp'][t]), None, sp)
+                assert rc == 0, L.gx_last_error()
+                rc = L.gx_step_autoreset(h, p(b['act'][t]), p(b['obs'][t + 1]), p(b['rew'][t]), p(b['done'][t]), p(b['cost'][t]), sp)
+                assert rc == 0, L.gx_last_error()
+
+        self.reset_into_buffer()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            sp = C.c_void_p(side.cuda_stream)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                issue(sp)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+
+    def refresh_weights(self):
+        pack_policy(self.ac, self.od, self.ad, out=self.weights)
+
+    def reset_into_buffer(self):
+        """env.reset() (ppo_train.py:401) with the observation written into row 0 of the rollout buffer"""
+        import ctypes as C
+        from . import _abi
+        env = self.env
+        _abi.check(env._lib, env._lib.gx_reset(env._h, C.c_void_p(self.buf['obs'][0].data_ptr()), env._stream()), "gx_reset")
+        env._obs = self.buf['obs'][0]
+
+    def run(self):
+        self.graph.replay()
+
+
 class RolloutTimer:
     """Times ONE epoch's rollout (T steps: policy forward + sample, env step + auto-reset, the
-    eight buffer writes) with CUDA events on the current stream; used by bench.py."""
+    buffer writes) with CUDA events on the current stream; used by bench.py."""
 
-    how = "policy forward + Gaussian sample + gx_step_autoreset + 8 buffer writes per step, one CUDA graph replayed T times"
-
-    def __init__(self, env, ac, T):
+    def __init__(self, env, ac, T, fused=True):
         N, dev = env.env_num, env.device
-        f = lambda *s: torch.empty(*s, device=dev)
-        self.T, self.env = T, env
-        self.buf = dict(obs=f(T, N, env.observation_space.shape[0]), act=f(T, N, env.action_space.shape[0]), rew=f(T, N),
-                        cost=f(T, N), done=f(T, N), val=f(T, N), cval=f(T, N), logp=f(T, N))
+        self.T, self.env, self.fused = T, env, fused
         env.reset()
         env.stats_reset()
-        self.step = GraphedRolloutStep(env, ac, self.buf)
-        self.step.run(env.reset(), T)      # warm-up
+        if fused:
+            self.roll = FusedRollout(env, ac, T)
+            self.how = FusedRollout.how
+        else:
+            f = lambda *s: torch.empty(*s, device=dev)
+            self.buf = dict(obs=f(T, N, env.observation_space.shape[0]), act=f(T, N, env.action_space.shape[0]), rew=f(T, N),
+                            cost=f(T, N), done=f(T, N), val=f(T, N), cval=f(T, N), logp=f(T, N))
+            self.step = GraphedRolloutStep(env, ac, self.buf)
+            self.how = "torch policy forward + sample + gx_step_autoreset + 8 buffer writes per step (~30 kernels), one CUDA graph replayed T times"
+        self.run()      # warm-up
         torch.cuda.synchronize(dev)
 
     def run(self) -> float:
-        o = self.env.reset()
+        if self.fused:
+            self.roll.reset_into_buffer()
+        else:
+            o = self.env.reset()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(self.env.device)
         e0.record()
-        self.step.run(o, self.T)
+        if self.fused:
+            self.roll.run()
+        else:
+            self.step.run(o, self.T)
         e1.record()
         torch.cuda.synchronize(self.env.device)
         return e0.elapsed_time(e1) * 1e-3
@@ -246,21 +340,34 @@ def ppo_lag(env, cfg: PPOLagConfig | None = None, ac: ActorCritic | None = None)
     vc_opt = torch.optim.Adam(ac.vc.parameters(), lr=cfg.vf_lr)
     N, T = env.env_num, cfg.max_ep_len
     f = lambda *s: torch.empty(*s, device=dev)
-    buf = dict(obs=f(T, N, obs_dim), act=f(T, N, act_dim), rew=f(T, N), cost=f(T, N), done=f(T, N), val=f(T, N),
-               cval=f(T, N), logp=f(T, N))
     lmd = cfg.lmd_init
-    graphed = None
-    if cfg.use_graph:
+    graphed = fused = None
+    use_fused = cfg.use_fused and tuple(cfg.hidden_sizes) == (64, 64)
+    if not use_fused:
+        buf = dict(obs=f(T, N, obs_dim), act=f(T, N, act_dim), rew=f(T, N), cost=f(T, N), done=f(T, N), val=f(T, N),
+                   cval=f(T, N), logp=f(T, N))
+    if use_fused:
         env.reset()
         env.stats_reset()     # statistics on BEFORE capture: the captured launch is the accumulating variant
+        fused = FusedRollout(env, ac, T, noise_seed=cfg.seed + 10000 * gxd.rank())
+        buf = dict(fused.buf, obs=fused.buf['obs'][:T])
+    elif cfg.use_graph:
+        env.reset()
+        env.stats_reset()
         graphed = GraphedRolloutStep(env, ac, buf)
     t_start = time.time()
     for epoch in range(cfg.epochs):
-        o = env.reset()                                   # ppo_train.py:401 resets at every epoch end
-        env.stats_reset()
+        if fused is not None:
+            fused.refresh_weights()                       # the parameters Adam just updated, in the kernel's layout
+            fused.reset_into_buffer()                     # ppo_train.py:401 resets at every epoch end
+            env.stats_reset()
+            fused.run()
+        else:
+            o = env.reset()
+            env.stats_reset()
         if graphed is not None:
             graphed.run(o, T)
-        for t in range(0 if graphed is None else T, T):
+        for t in range(0 if (graphed is None and fused is None) else T, T):
             a, v, vc, logp = ac.step(o)
             buf['obs'][t], buf['act'][t], buf['val'][t], buf['cval'][t], buf['logp'][t] = o, a, v, vc, logp
             o, r, d, info = env.step_autoreset(a)         # step + reset_done in one launch, nothing leaves the device

@@ -299,6 +299,21 @@ int gx_gae(const float* reward, const float* value, const float* done, const flo
  *      host-side np.where(done == 1) of ppo_train.py:403-411 / scpo/scpo.py:722.  No env handle. */
 int gx_compact_done(const float* done, int32_t n, int32_t* idx, int32_t* count, void* stream);
 
+/* ---- the policy half of a PPO / PPO-Lagrangian rollout step in one launch ------------------
+ * Replaces `ac.step(o)` + the rollout-buffer stores of safe_rl_libX/ppo/ppo_train.py:364-379 (actor-critic of
+ * ppo_core.py:116-160: three fp32 tanh MLPs obs -> 64 -> 64 -> {act_dim | 1 | 1}, state-independent log-std,
+ * Gaussian sample + log-probability; the third net is the cost critic of TRPO-Lag).
+ *   weights   device, gx_policy_weight_floats(e) floats, packed as csrc/gx_policy.cuh documents
+ *   obs       device [env_num, obs_dim] (what the env kernels wrote)
+ *   act       device [env_num, act_dim]  sampled action   (feed it to gx_step / gx_step_autoreset)
+ *   val, cval, logp   device [env_num]
+ *   mu_out    device [env_num, act_dim] or NULL: the actor mean (tests)
+ * The exploration noise is a pure function of (noise_seed, config seed, global env id, the env's step count): the call
+ * can be captured in a CUDA graph and replayed.  Call before the env step of the same control step. */
+int64_t gx_policy_weight_floats(const gx_env* e);
+int gx_policy_step(gx_env* e, const float* weights, const float* obs, uint64_t noise_seed, float* act, float* val,
+                   float* cval, float* logp, float* mu_out, void* stream);
+
 /* ---- diagnostics: evaluate the shared fp32 math (csrc/gx_math.h) on the
  *      device, so tests can prove host/device bit-equality of the header.
  *      fn: 0 sincos(a)->out,out2   1 atan2(a,b)->out   2 exp(a)->out

@@ -114,7 +114,7 @@ def test_graphed_rollout_agrees_with_eager_rollout():
     logs = []
     for use_graph in (False, True):
         env = make("Goal_Point_8Hazards", env_num=300, seed=3, max_ep_len=25)
-        cfg = ppo_lag.PPOLagConfig(epochs=2, max_ep_len=25, train_pi_iters=3, train_v_iters=3, use_graph=use_graph, seed=5)
+        cfg = ppo_lag.PPOLagConfig(epochs=2, max_ep_len=25, train_pi_iters=3, train_v_iters=3, use_graph=use_graph, use_fused=False, seed=5)
         _, log = ppo_lag.ppo_lag(env, cfg)
         logs.append(log)
     for a, b in zip(*logs):
@@ -122,3 +122,131 @@ def test_graphed_rollout_agrees_with_eager_rollout():
         assert np.isfinite([b['MeanStepReward'], b['MeanStepCost']]).all()
         # the graph warm-up consumes extra policy samples, so trajectories differ; the statistics must be sane and close
         assert abs(a['MeanStepCost'] - b['MeanStepCost']) < 0.05
+
+
+def test_pack_policy_layout():
+    """pack_policy writes the layout csrc/gx_policy.cuh documents (checked on the CPU with a numpy forward pass)."""
+    torch.manual_seed(1)
+    od, ad = 43, 2
+    ac = ppo_lag.ActorCritic(od, ad)
+    with torch.no_grad():
+        ac.log_std.copy_(torch.tensor([-0.3, -0.7]))
+    w = ppo_lag.pack_policy(ac, od, ad).numpy()
+    k1 = 44
+    o = 0
+    W1 = w[o:o + k1 * 192].reshape(k1, 192); o += k1 * 192
+    B1 = w[o:o + 192]; o += 192
+    W2 = w[o:o + 3 * 64 * 64].reshape(3, 64, 64); o += 3 * 64 * 64
+    B2 = w[o:o + 192]; o += 192
+    W3 = w[o:o + (ad + 2) * 64].reshape(ad + 2, 64); o += (ad + 2) * 64
+    B3 = w[o:o + ad + 2]; o += ad + 2
+    LS = w[o:o + ad]; o += ad
+    assert o == w.size and (W1[od:] == 0).all()
+    x = torch.randn(5, od)
+    xp = np.concatenate([x.numpy(), np.zeros((5, 1), np.float32)], 1)
+    h1 = np.tanh(xp @ W1 + B1)
+    h2 = np.tanh(np.concatenate([h1[:, n * 64:(n + 1) * 64] @ W2[n] for n in range(3)], 1) + B2)
+    mu = h2[:, :64] @ W3[:ad].T + B3[:ad]
+    v = h2[:, 64:128] @ W3[ad] + B3[ad]
+    vc = h2[:, 128:] @ W3[ad + 1] + B3[ad + 1]
+    with torch.no_grad():
+        np.testing.assert_allclose(mu, ac.mu_net(x).numpy(), atol=2e-6)
+        np.testing.assert_allclose(v, ac.v(x).squeeze(-1).numpy(), atol=2e-6)
+        np.testing.assert_allclose(vc, ac.vc(x).squeeze(-1).numpy(), atol=2e-6)
+    np.testing.assert_array_equal(LS, ac.log_std.detach().numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task,n", [("Goal_Point_8Hazards", 1000), ("Goal_Ant_8Hazards", 100), ("Goal_Doggo_8Hazards", 70)])
+def test_policy_kernel_matches_the_torch_actor_critic(task, n):
+    """gx_policy_step vs ActorCritic: mean / value / cost value within 1e-5 of the torch forward pass (fp32, different
+    summation order), logp == Normal.log_prob of the stored action, noise ~ N(0, 1), replay-safe counters."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    from guardx_b200 import make
+    env = make(task, env_num=n, seed=2, max_ep_len=50)
+    od, ad = env.observation_space.shape[0], env.action_space.shape[0]
+    torch.manual_seed(3)
+    ac = ppo_lag.ActorCritic(od, ad).cuda()
+    with torch.no_grad():
+        for p_ in ac.parameters():
+            p_.mul_(3.0)                                   # saturate some tanh units
+        ac.log_std.copy_(torch.linspace(-1.0, 0.2, ad))
+    w = ppo_lag.pack_policy(ac, od, ad)
+    assert w.numel() == env._lib.gx_policy_weight_floats(env._h)
+    obs = env.reset()
+    f = lambda *s: torch.empty(*s, device='cuda')
+    act, val, cval, logp, mu = f(n, ad), f(n), f(n), f(n), f(n, ad)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    zs = []
+    for t in range(6):
+        rc = env._lib.gx_policy_step(env._h, p(w), p(obs), C.c_uint64(77), p(act), p(val), p(cval), p(logp), p(mu), env._stream())
+        assert rc == 0, env._lib.gx_last_error()
+        with torch.no_grad():
+            mu_t, v_t, vc_t = ac.mu_net(obs), ac.v(obs).squeeze(-1), ac.vc(obs).squeeze(-1)
+            std = torch.exp(ac.log_std)
+            lp_t = torch.distributions.Normal(mu, std).log_prob(act).sum(-1)
+        assert float((mu - mu_t).abs().max()) <= 1e-5 * (1 + float(mu_t.abs().max()))
+        assert float((val - v_t).abs().max()) <= 1e-5 * (1 + float(v_t.abs().max()))
+        assert float((cval - vc_t).abs().max()) <= 1e-5 * (1 + float(vc_t.abs().max()))
+        assert float((logp - lp_t).abs().max()) <= 2e-5 * (1 + float(lp_t.abs().max()))
+        zs.append(((act - mu) / std).flatten().cpu())
+        act2 = act.clone()
+        rc = env._lib.gx_policy_step(env._h, p(w), p(obs), C.c_uint64(77), p(act), p(val), p(cval), p(logp), None, env._stream())
+        assert torch.equal(act, act2)                      # same counters -> same draw (deterministic, graph-replayable)
+        obs, r, d, info = env.step_autoreset(act)          # the env's step count advances -> fresh noise next time
+    z = torch.cat(zs)
+    assert torch.isfinite(z).all()
+    assert abs(float(z.mean())) < 5.0 / z.numel() ** 0.5 and abs(float(z.var()) - 1.0) < 8.0 / z.numel() ** 0.5
+    assert float(z.abs().max()) > 2.5                      # tails are there
+    # successive steps of one env and neighbouring envs are uncorrelated
+    zz = torch.stack([x.view(n, ad)[:, 0] for x in zs])
+    assert abs(float((zz[:-1] * zz[1:]).mean())) < 5.0 / (zz[:-1].numel()) ** 0.5
+    assert abs(float((zz[:, :-1] * zz[:, 1:]).mean())) < 5.0 / (zz[:, 1:].numel()) ** 0.5
+
+
+@pytest.mark.gpu
+def test_fused_rollout_fills_the_buffer_like_the_step_by_step_loop():
+    """FusedRollout (2T launches in one graph, outputs written in place) against the same calls issued one by one with
+    separate tensors: bit-identical buffers (same kernels, same counters)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    from guardx_b200 import make
+    n, T = 500, 30
+    bufs = []
+    for fused in (True, False):
+        env = make("Goal_Point_8Hazards", env_num=n, seed=4, max_ep_len=12)      # timeouts inside the window
+        torch.manual_seed(9)
+        ac = ppo_lag.ActorCritic(43, 2).cuda()
+        if fused:
+            env.reset(); env.stats_reset()
+            fr = ppo_lag.FusedRollout(env, ac, T, noise_seed=5)
+            env.set_counters(0, 0)       # (capture ran no kernels; the reset above consumed pool epoch 0)
+            fr.reset_into_buffer(); env.stats_reset()
+            fr.run()
+            torch.cuda.synchronize()
+            bufs.append({k: v.clone() for k, v in fr.buf.items()})
+            st_f = env.stats().clone()
+        else:
+            env.reset(); env.stats_reset()
+            env.set_counters(0, 0)
+            w = ppo_lag.pack_policy(ac, 43, 2)
+            o = env.reset(); env.stats_reset()
+            f = lambda *s: torch.empty(*s, device='cuda')
+            b = dict(obs=f(T + 1, n, 43), act=f(T, n, 2), rew=f(T, n), cost=f(T, n), done=f(T, n), val=f(T, n), cval=f(T, n), logp=f(T, n))
+            p = lambda t: C.c_void_p(t.data_ptr())
+            for t in range(T):
+                b['obs'][t] = o
+                a, v, vc, lp = f(n, 2), f(n), f(n), f(n)
+                assert env._lib.gx_policy_step(env._h, p(w), p(o), C.c_uint64(5), p(a), p(v), p(vc), p(lp), None, env._stream()) == 0
+                o, r, d, info = env.step_autoreset(a)
+                b['act'][t], b['val'][t], b['cval'][t], b['logp'][t], b['rew'][t], b['done'][t], b['cost'][t] = a, v, vc, lp, r, d, info['cost']
+            b['obs'][T] = o
+            bufs.append(b)
+            st_e = env.stats()
+    for k in bufs[0]:
+        assert torch.equal(bufs[0][k].view(torch.int32), bufs[1][k].view(torch.int32)), k
+    assert float(bufs[0]['done'].sum()) >= n            # episodes really ended (and envs were re-placed) inside the graph
+    assert torch.equal(st_f, st_e)
