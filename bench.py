@@ -475,7 +475,7 @@ def main():
     hp_r, hp_d, hp_c = (torch.empty(Tp, n).pin_memory() for _ in range(3))
     reps_p = 8
 
-    Rp = min(R, 8)   # PCIe, not L2, bounds this path; 8 batches keep every call on a different env state
+    Rp = 2           # PCIe, not L2, bounds this path; two batches alternate
 
     def e2e_pipe(k):
         acc = 0.0
@@ -484,7 +484,8 @@ def main():
             acc += float(hp_r[-1, -1])   # the rollout's result is read on the host
         return acc
 
-    e2e_pipe(2 * Rp)   # warm-up: every batch has its chunk ring, streams and events before the timed region
+    e2e_pipe(5 * Rp)   # warm-up: chunk rings / streams exist, and gx_rollout_host has timed both of its routes (DMA ring,
+                       # zero-copy) on every handle -- with all ranks running -- and settled on the faster one
     if barrier:
         barrier()
     torch.cuda.synchronize()
@@ -492,6 +493,10 @@ def main():
     e2e_pipe(reps_p)
     dt_pipe = max_over_ranks(torch, dist, [time.perf_counter() - t0])[0]
     e2e_value = world * n * Tp * reps_p / dt_pipe
+    _rates = (C.c_double * 2)()
+    e2e_route = lib.gx_rollout_host_route(batches[0].h, _rates)
+    e2e_route = {"route": {0: "dma ring", 1: "zero-copy tile stores"}.get(e2e_route, "undecided"),
+                 "probe_dma": _rates[0], "probe_zero_copy": _rates[1]}
     del hp_obs
 
     # ---- fused rollout kernel ----------------------------------------------
@@ -627,7 +632,7 @@ def main():
             "value_stream_launch": world * n * Ss / dt_stream,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 2 * 4,
-                    "d2h_bytes_per_step": n * (od + 3) * 4, "steps": Tp * reps_p,
+                    "d2h_bytes_per_step": n * (od + 3) * 4, "steps": Tp * reps_p, "rank0_route": e2e_route,
                     "per_step_sync": {"value": e2e_sync_value, "steps": Ke,
                                       "path": "Engine.step_host: one blocking call per step (policy in the loop)"},
                     "path": "Engine.rollout_host -> gx_rollout_host: every step's action from pinned host memory, every "

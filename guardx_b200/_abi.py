@@ -133,6 +133,7 @@ PROTOTYPES = {
     "gx_gae": (_I, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_double, C.c_double, _P, _P, _P]),
     "gx_debug_math": (_I, [_I, _P, _P, _P, _P, _I, _P]),
     "gx_debug_sm_clock": (_I, [_P, _I, _P]),
+    "gx_rollout_host_route": (_I, [_P, _P]),
     "gx_policy_weight_floats": (C.c_int64, [_P]),
     "gx_policy_step": (_I, [_P, _P, _P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
 }

@@ -3,6 +3,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
 //        -Xcompiler -ffp-contract=off,-fPIC -shared guardx.cu -o ../libguardx.so
 // -fmad=false / -ffp-contract=off are REQUIRED (bit-parity contract, gx_math.h).
+#include <chrono>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -100,6 +101,11 @@ struct gx_env {
   int ring_steps;
   cudaStream_t rs_compute, rs_copy;
   cudaEvent_t ev_in, ev_computed[2], ev_copied[2];
+  // route of gx_rollout_host: 0 = DMA ring (copy engine), 1 = zero-copy (the kernels' tile stores go to the mapped
+  // host buffers).  Which one is faster depends on what else shares the host side (alone on the box the copy engine
+  // wins; with 8 ranks the DMA route collapsed to 1/4 in round 1), so the first calls time both and the faster stays.
+  int rh_calls, rh_route;
+  double rh_rate[2];
 };
 
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
@@ -1323,6 +1329,29 @@ GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h
   const size_t n = (size_t)e->p.n, od = (size_t)e->p.obs_dim;
   const size_t ad = (size_t)gx_act_dim(e);
   const size_t per_step = (od + 3 + ad) * n;  // obs | reward | done | cost | action
+  // ---- route ---------------------------------------------------------------------------------------------------
+  const void *zo = nullptr, *zr = nullptr, *zd = nullptr, *zc = nullptr;
+  const bool can_zc = !e->art_host && !e->tree_host && gx_host_mapped(h_obs, &zo) && gx_host_mapped(h_reward, &zr) &&
+                      gx_host_mapped(h_done, &zd) && gx_host_mapped(h_cost, &zc);
+  int route = 0;
+  if (can_zc) {
+    const char* force = getenv("GX_ROLLOUT_HOST_ROUTE");   // "dma" | "zc" | unset = measure
+    if (force && force[0] == 'z') route = 1;
+    else if (force && force[0] == 'd') route = 0;
+    else if (e->rh_calls < 4) route = e->rh_calls & 1;      // probe: dma, zc, dma, zc
+    else route = e->rh_route;
+  }
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto finish = [&](int rc_) {
+    if (rc_ == GX_OK && can_zc) {
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+      const double rate = (double)n * T / (dt > 1e-9 ? dt : 1e-9);
+      if (e->rh_calls >= 2 && e->rh_calls < 4) e->rh_rate[route] = rate;   // the second probe of each route (first ones allocate)
+      if (e->rh_calls == 3) e->rh_route = e->rh_rate[1] > e->rh_rate[0] ? 1 : 0;
+      e->rh_calls++;
+    }
+    return rc_;
+  };
   if (!e->ring_steps) {
     // ~8 MB of output per chunk keeps the copy engine near its large-transfer rate
     int S = (int)((8u << 20) / (sizeof(float) * (od + 3) * n));
@@ -1357,6 +1386,28 @@ GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h
     if (rc == GX_OK && err != cudaSuccess) rc = gx_fail(GX_ECUDA, "gx_rollout_host: %s failed: %s", what, cudaGetErrorString(err));
     return rc == GX_OK;
   };
+  if (route == 1) {
+    // zero-copy: the actions of a chunk go up by DMA (8 B per env-step), the step kernels write observation tiles,
+    // reward, done and cost straight into the caller's mapped host buffers (coalesced 128-bit stores over PCIe);
+    // no device-to-host copy, no second stream
+    float* d_obs = (float*)zo; float* d_rew = (float*)zr; float* d_done = (float*)zd; float* d_cost = (float*)zc;
+    if (cu(cudaEventRecord(e->ev_in, user), "cudaEventRecord")) cu(cudaStreamWaitEvent(e->rs_compute, e->ev_in, 0), "cudaStreamWaitEvent");
+    int chunk = 0;
+    for (int t0 = 0; t0 < T && rc == GX_OK; t0 += S, ++chunk) {
+      const int kk = chunk & 1, s_now = (T - t0 < S) ? (T - t0) : S;
+      float* d_act = e->ring[kk];          // the ring buffers only stage actions on this route
+      // (the H2D copy into ring[kk] may overwrite actions that chunk - 2 has consumed: same stream, in order)
+      if (!cu(cudaMemcpyAsync(d_act, h_action + ad * n * t0, sizeof(float) * ad * n * s_now, cudaMemcpyHostToDevice, e->rs_compute), "H2D copy")) break;
+      for (int t = 0; t < s_now && rc == GX_OK; ++t)
+        rc = gx_step_impl(e, d_act + ad * n * t, d_obs + od * n * (t0 + t), d_rew + n * (t0 + t), d_done + n * (t0 + t), d_cost + n * (t0 + t),
+                          nullptr, nullptr, e->rs_compute, true, "gx_rollout_host", true);
+    }
+    if (rc == GX_OK) cu(cudaEventRecord(e->ev_computed[0], e->rs_compute), "cudaEventRecord");
+    if (rc == GX_OK) cu(cudaStreamWaitEvent(user, e->ev_computed[0], 0), "cudaStreamWaitEvent");
+    cudaError_t serr = cudaStreamSynchronize(e->rs_compute);
+    if (rc == GX_OK && serr != cudaSuccess) rc = gx_fail(GX_ECUDA, "gx_rollout_host: %s", cudaGetErrorString(serr));
+    return finish(rc);
+  }
   int chunk = 0;
   if (cu(cudaEventRecord(e->ev_in, user), "cudaEventRecord")) cu(cudaStreamWaitEvent(e->rs_compute, e->ev_in, 0), "cudaStreamWaitEvent");
   for (int t0 = 0; t0 < T && rc == GX_OK; t0 += S, ++chunk) {
@@ -1389,7 +1440,13 @@ GX_API int gx_rollout_host(gx_env* e, int32_t T, const float* h_action, float* h
   // the caller's stream (and the host) see the finished rollout
   GX_CUDA(cudaStreamWaitEvent(user, e->ev_copied[(chunk - 1) & 1], 0));
   GX_CUDA(cudaStreamSynchronize(e->rs_copy));
-  return GX_OK;
+  return finish(GX_OK);
+}
+
+GX_API int gx_rollout_host_route(const gx_env* e, double* rates2) {
+  if (!e) return GX_EINVAL;
+  if (rates2) { rates2[0] = e->rh_rate[0]; rates2[1] = e->rh_rate[1]; }
+  return e->rh_calls < 4 ? -1 : e->rh_route;
 }
 
 // ---- policy half of a PPO rollout step (gx_policy.cuh) ---------------------------------

@@ -279,6 +279,10 @@ int gx_step_host(gx_env* env, const float* h_action, float* h_obs, float* h_rewa
  *      gx_step_host. ------------------------------------------------------- */
 int gx_rollout_host(gx_env* env, int32_t T, const float* h_action, float* h_obs, float* h_reward,
                     float* h_done, float* h_cost, void* stream);
+/* Which route gx_rollout_host settled on: 0 = DMA ring (copy engine), 1 = zero-copy (kernels store straight into the
+ * mapped host buffers), -1 = still measuring (the first four calls time both).  rates2 (host, may be NULL) receives
+ * the env-steps/s measured for the two routes.  GX_ROLLOUT_HOST_ROUTE=dma|zc in the environment forces one. */
+int gx_rollout_host_route(const gx_env* e, double* rates2);
 
 /* ---- rollout-side op: GAE-lambda advantages and rewards-to-go
  *      over a time-major rollout, replacing PPOBufferX.finish_path

@@ -429,17 +429,26 @@ def test_rollout_host_matches_step_host(mods, n, T):
     a.reset(); b.reset()
     od = a.obs_flat_size
     h_out = torch.empty(n * (od + 3)).pin_memory()
-    for rep in range(2):
+    for rep in range(6):      # calls 0..3 alternate the DMA ring and the zero-copy route (probing), 4.. use the faster one
         h_act = torch.empty(T, n, 2).uniform_(-1, 1).pin_memory()
         h_obs = torch.empty(T, n, od).pin_memory()
         h_r, h_d, h_c = (torch.empty(T, n).pin_memory() for _ in range(3))
         a.rollout_host(h_act, h_obs, h_r, h_d, h_c)
+        assert a._lib.gx_rollout_host_route(a._h, None) == (-1 if rep < 3 else a._lib.gx_rollout_host_route(a._h, None))
         for t in range(T):
             b.step_host(h_act[t], h_out, auto_reset_done=True)
             assert torch.equal(h_out[:n * od].view(n, od), h_obs[t]), (rep, t)
             assert torch.equal(h_out[n * od:n * od + n], h_r[t])
             assert torch.equal(h_out[n * od + n:n * od + 2 * n], h_d[t])
             assert torch.equal(h_out[n * od + 2 * n:], h_c[t])
+    assert a._lib.gx_rollout_host_route(a._h, None) in (0, 1)
+    # pageable outputs cannot be mapped: the DMA ring is the only route, results unchanged
+    h_act = torch.empty(T, n, 2).uniform_(-1, 1).pin_memory()
+    p_obs, p_r, p_d, p_c = torch.empty(T, n, od), torch.empty(T, n), torch.empty(T, n), torch.empty(T, n)
+    a.rollout_host(h_act, p_obs, p_r, p_d, p_c)
+    for t in range(T):
+        b.step_host(h_act[t], h_out, auto_reset_done=True)
+        assert torch.equal(h_out[:n * od].view(n, od), p_obs[t]) and torch.equal(h_out[n * od + 2 * n:], p_c[t])
 
 
 def test_episode_statistics_match_oracle(mods):

@@ -1,0 +1,23 @@
+#!/bin/bash
+# Round-2 profile capture (run under gpurun): one ncu --set full capture per dominant kernel at HEAD, each after the same
+# command has exited 0 without ncu, plus the launch list of the bench command.  Reports land in gpurun_out/;
+# tools/ncu_summary.py turns them into profiles/r2_*.txt (with the SASS opcode histogram of the captured kernel).
+set -u
+O=gpurun_out
+P="ncu --set full --clock-control none --import-source on"
+run() { # name, kernel regex, skip, count, command...
+  local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
+  "$@" > $O/r2_${name}_plain.log 2>&1 && $P -k regex:$rx -s $skip -c $cnt -o $O/r2_prof_${name} "$@" > $O/r2_${name}_ncu.log 2>&1
+  echo "$name rc=$?"
+}
+run lanes_4096 gx_step_lanes_kernel 20 2 python tools/prof_target.py 4096 30
+run step_65536 gx_step_kernel 6 2 python tools/prof_target.py 65536 12
+run step_1m gx_step_kernel 3 2 python tools/prof_target.py 1048576 6
+run art_ant_65536 gx_art_kernel 35 1 python tools/prof_target.py 65536 3 0 xmls/ant.xml
+run tree_doggo_4096 gx_tree_kernel 35 1 python tools/prof_target.py 4096 3 0 xmls/doggo.xml
+run policy_4096 gx_policy_kernel 25 2 python tools/prof_policy.py 4096 20
+# launch list of the bench command (cold-cache, serialised: shares, not absolutes)
+python bench.py --steps 20 --warmup 5 --no-sweep --no-legged --no-ppo > $O/r2_bench_plain.json 2> $O/r2_bench_plain.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r2_launches.csv \
+    python bench.py --steps 20 --warmup 5 --no-sweep --no-legged --no-ppo > $O/r2_launches_ncu.log 2>&1
+echo "launches rc=$?"

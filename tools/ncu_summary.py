@@ -27,6 +27,8 @@ def run(args):
 def main():
     rep = sys.argv[1]
     nlines = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+    head_ = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
+    print(f'# {rep}  (ncu --set full --clock-control none --import-source on; repository HEAD when summarised: {head_})')
     rows = list(csv.reader(io.StringIO(run([rep, '--page', 'raw', '--csv']))))
     head, units, data = rows[0], rows[1], rows[2:]
     col = {k: i for i, k in enumerate(head)}
@@ -44,8 +46,35 @@ def main():
                 pass
     ts, ti = sum(o[0] for o in out) or 1, sum(o[1] for o in out) or 1
     print(f'\n# hottest source lines (first captured launch): % of stall samples, % of executed warp-instructions, line, source')
-    for o in sorted(out, reverse=True)[:nlines]:
+    seen = set()
+    for o in sorted(out, reverse=True):
+        if (o[2], o[3]) in seen:
+            continue
+        seen.add((o[2], o[3]))
         print('%5.1f%% %5.1f%%  %4d  %s' % (100 * o[0] / ts, 100 * o[1] / ti, o[2], o[3]))
+        if len(seen) >= nlines:
+            break
+    # SASS opcode histogram of the captured kernel, weighted by executed warp-instructions (first captured launch)
+    sass = list(csv.reader(io.StringIO(run([rep, '--page', 'source', '--csv', '--print-source', 'sass']))))
+    hist, static, first = {}, {}, True
+    for r in sass:
+        if len(r) > 6 and r[0].startswith('0x'):
+            toks = r[1].split()
+            op = next((t for t in toks if not t.startswith('@')), '?').split('.')[0]
+            try:
+                ex = int(r[5])
+            except ValueError:
+                ex = 0
+            hist[op] = hist.get(op, 0) + ex
+            static[op] = static.get(op, 0) + 1
+        elif r and r[0] == 'Kernel Name':
+            if not first:
+                break
+            first = False
+    tot = sum(hist.values()) or 1
+    print(f'\n# SASS opcodes of the captured kernel: executed warp-instructions (% of {tot}), static count  [{sum(static.values())} instructions in the binary]')
+    for op, ex in sorted(hist.items(), key=lambda kv: -kv[1])[:22]:
+        print('%-10s %6.2f%%  %5d' % (op, 100.0 * ex / tot, static[op]))
 
 
 if __name__ == '__main__':
