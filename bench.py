@@ -570,6 +570,10 @@ def main():
                            "envs_per_gpu": n_leg, "steps": Td, "value": world * n_leg * Td / dt_dog, "unit": "env-steps/s",
                            "us_per_step": 1e6 * dt_dog / Td, "bound": "dependent-issue latency (DESIGN.md 5b), not HBM",
                            "finite": fin}
+    # ---- BASELINE configs[2]: Button task, Car robot, vases / pillars / gremlins / hazards, 16384 envs on 1 GPU ----
+    task3 = None
+    if not args.no_legged and rank == 0:
+        task3 = task3_section(torch, stream)
     # ---- BASELINE configs[4]: PPO-Lagrangian rollout + update, env on the CUDA kernels ----
     ppo = None
     if not args.no_ppo:
@@ -654,6 +658,8 @@ def main():
         }
         if ppo is not None:
             line["ppo_lag"] = ppo
+        if task3 is not None:
+            line["config3"] = task3
         if legged is not None:
             line["legged"] = legged
         if sweep is not None:
@@ -664,6 +670,59 @@ def main():
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def task3_section(torch, stream):
+    """BASELINE.json configs[2]: 'Button/Push Car robot with vases, pillars and gremlins, 16384 envs, 1 B200' on the
+    config-3 extension (include/guardx_task.h; NO reference implementation exists).  Fused step +
+    auto-reset, random actions resident in HBM, cold L2 (rotating batches), same region protocol as the headline."""
+    from guardx_b200 import task_engine
+    n = 16384
+    lib = task_engine.load_library()
+    out = {}
+    for name in ("Button_Car", "Push_Car"):
+        envs = [task_engine.make_task(name, env_num=n, seed=k, max_ep_len=1000) for k in range(2)]
+        od = envs[0].obs_flat_size
+        per = n * 4 * (envs[0].state_dim + od + 3 + 2 * 4)
+        Rb = int(L2_BYTES * 2.0 / per) + 1
+        envs += [task_engine.make_task(name, env_num=n, seed=k, max_ep_len=1000) for k in range(2, Rb)]
+        bufs = []
+        g = torch.Generator(device='cuda').manual_seed(99)
+        for e in envs:
+            e.reset()
+            st = e.get_state()
+            st[:, 11] = torch.randint(0, 1000, (n,), device='cuda', generator=g).float()      # random episode phases
+            e.set_state(st)
+            act = torch.rand(4, n, 2, device='cuda', generator=g) * 2 - 1
+            bufs.append((e, act, torch.empty(n, od, device='cuda'), torch.empty(3, n, device='cuda')))
+        pr = lambda t_: C.c_void_p(t_.data_ptr())
+
+        def issue(sp, t0, steps):
+            for t in range(t0, t0 + steps):
+                e, act, obs, rdc = bufs[t % Rb]
+                rc = lib.gxt_step(e._h, pr(act[(t // Rb) % 4]), pr(obs), pr(rdc[0]), pr(rdc[1]), pr(rdc[2]), None, 1, sp)
+                assert rc == 0, lib.gx_last_error()
+
+        sp = C.c_void_p(stream.cuda_stream)
+        issue(sp, 0, 40 * Rb)                      # warm-up / burn-in
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream); issue(sp, 0, 4 * Rb); ev1.record(stream); torch.cuda.synchronize()
+        est = ev0.elapsed_time(ev1) * 1e-3 / (4 * Rb)
+        S = max(2 * Rb, min(4096, int(REGION_SECONDS / est) + 1))
+        reg = Regions(torch, issue, S, None)
+        ds = reg.measure(stream, 5, settle=max(1, int(SETTLE_SECONDS / (S * est)) + 1))
+        d = median(ds)
+        del reg
+        alg = 4 * (2 * 14 + 2 * (envs[0].state_dim - 16) // 1 // 2 + od + 3 + 2)   # dynamic state r+w, objects r, obs + r/d/c w, action r
+        out[name] = {"envs": n, "obs_dim": od, "objects": int(envs[0].layout_dim - 2 - 4) // 2, "steps_per_region": S,
+                     "us_per_step": 1e6 * d / S, "value": n * S / d, "unit": "env-steps/s", "alg_bytes_per_env_step": alg,
+                     "achieved_gbs": n * S * alg / d / 1e9, "finite": bool(torch.isfinite(bufs[0][2]).all().item())}
+        del bufs, envs
+        torch.cuda.empty_cache()
+    out["workload"] = ("Button / Push task, Car robot, 4 hazards + 4 vases + 2 pillars + 4 gremlins (+ 4 buttons | box + goal), 16384 envs, "
+                       "fused step + auto-reset, cold L2 (BASELINE.json configs[2]); no reference implementation exists: parity unpinned")
+    return out
 
 
 def ppo_section(torch, dist, rank, world, local_rank):

@@ -42,6 +42,15 @@ static int gx_fail(int code, const char* fmt, ...) {
   return code;
 }
 
+// same, for the other translation units of the library (gx_task.cu)
+int gx_set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
 #define GX_CUDA(call)                                                                   \
   do {                                                                                  \
     cudaError_t e_ = (call);                                                            \

@@ -28,6 +28,28 @@ def test_header_symbols_all_exported_and_bound():
     assert sorted(_abi.PROTOTYPES) == declared
 
 
+def test_task_extension_symbols_exported_and_bound():
+    """include/guardx_task.h (config-3 extension): every declared symbol is exported and has a ctypes prototype; the
+    config struct has the same layout on both sides; the default config is sane."""
+    from guardx_b200 import task_engine
+    lib = task_engine.load_library()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "guardx_task.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(gxt_[a-z0-9_]+)\s*\(", src)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in guardx_task.h but not exported"
+    assert sorted(task_engine.PROTOTYPES) == declared
+    assert lib.gxt_config_size() == C.sizeof(task_engine.GxtConfig)
+    c = task_engine.lower(task_engine.parse({'env_num': 16384}))
+    assert list(c.count) == [0, 0, 4, 4, 4, 2, 4, 1] and c.task == 1 and c.robot == 1 and c.lidar_num_bins == 16
+    with pytest.raises(AssertionError, match="Bad key"):
+        task_engine.parse({'ghosts_num': 8})
+    import torch
+    if not torch.cuda.is_available():
+        h = C.c_void_p()
+        assert lib.gxt_create(C.byref(c), 0, C.byref(h)) == _abi.GX_ECUDA and not h.value     # no CPU fallback
+
+
 def test_config_layout_and_defaults_agree():
     lib = _abi.load_library()
     assert lib.gx_config_size() == C.sizeof(_abi.GxConfig)
