@@ -5,7 +5,7 @@ import io
 import subprocess
 import sys
 
-KEYS = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
+KEYS = ['gpu__time_duration.sum', 'sm__cycles_active.avg', 'smsp__cycles_active.avg', 'sm__cycles_elapsed.max', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread',
         'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor',
         'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct',
