@@ -13,8 +13,8 @@ run() { # name, kernel regex, skip, count, command...
 run lanes_4096 gx_step_lanes_kernel 20 2 python tools/prof_target.py 4096 30
 run step_65536 gx_step_kernel 6 2 python tools/prof_target.py 65536 12
 run step_1m gx_step_kernel 3 2 python tools/prof_target.py 1048576 6
-run art_ant_65536 gx_art_kernel 35 1 python tools/prof_target.py 65536 3 0 xmls/ant.xml
-run tree_doggo_4096 gx_tree_kernel 35 1 python tools/prof_target.py 4096 3 0 xmls/doggo.xml
+run art_ant_65536 gx_art_kernel 31 1 python tools/prof_target.py 65536 3 0 xmls/ant.xml
+run tree_doggo_4096 gx_tree_kernel 31 1 python tools/prof_target.py 4096 3 0 xmls/doggo.xml
 run policy_4096 gx_policy_kernel 25 2 python tools/prof_policy.py 4096 20
 # launch list of the bench command (cold-cache, serialised: shares, not absolutes)
 python bench.py --steps 20 --warmup 5 --no-sweep --no-legged --no-ppo > $O/r2_bench_plain.json 2> $O/r2_bench_plain.err && \
