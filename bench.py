@@ -64,7 +64,7 @@ FLUSH_BYTES = 512 << 20       # written before every timed region: evicts the L2
 REGION_SECONDS = float(os.environ.get("GX_BENCH_REGION_S", "0.025"))   # a timed region lasts at least this long, whatever --steps is
 MAX_REGION_STEPS = 1 << 16    # graph nodes per region (bounds capture time when --steps is huge)
 BURN_IN = 2000                # random-action steps every batch takes before anything is timed (num_steps = 1000)
-SETTLE_SECONDS = 0.3          # untimed replays before the timed regions (sustained GPU state)
+SETTLE_SECONDS = float(os.environ.get("GX_BENCH_SETTLE_S", "0.3"))   # untimed replays before the timed regions (sustained GPU state)
 FLUSH = bool(int(os.environ.get("GX_BENCH_FLUSH", "0")))   # 512 MB write before every region (see the docstring)
 REGIONS = int(os.environ.get("GX_BENCH_REGIONS", "7"))   # regions measured; the median is reported
 TASK = "Goal_Point_8Hazards"
