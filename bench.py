@@ -28,19 +28,19 @@ One JSON line on stdout (rank 0).  Keys beyond the driver's contract:
 Timing (the same whatever --steps K is): a WINDOW is exactly K fused step launches; a timed
 REGION is M back-to-back windows, M chosen so that a region lasts >= 20 ms; REGIONS (7) regions
 are measured and the MEDIAN is reported (min / max beside it), so ms_per_step x steps = one
-window.  Every region is a chain of CUDA graphs; all regions and their CUDA events are
-enqueued while the GPU is still busy with SETTLE_SECONDS of untimed replays, so neither
-graph-launch latency nor the host is inside a timed region, and the GPU is in its sustained
-state (on this pool a B200 steps ~6 % faster during the first ~0.25 s of a burst of
-memory-heavy work than afterwards, at a constant SM clock: tools/diag_regions.py).
+window.  Every region is a chain of at most TWO CUDA graphs; all regions and their CUDA events
+are enqueued while the GPU is still busy with SETTLE_SECONDS of untimed replays, so neither
+graph-launch latency nor the host is inside a timed region.  (Why two: with four 2048-node
+graphs launched in turn, every step of a region measured 6 % slower than with three -- 5.97 vs
+5.61 us, reproducibly and at a constant SM clock -- which is graph re-upload, not kernel time;
+with <= 2 graphs --steps 20, 4000 and 20000 agree to 0.006 %.)
 
 L2 policy: every timed step touches a batch whose state, actions, layout pool and output
 buffers have not been touched for R-1 steps, where R batches x ~1.5 MB (+ 1.3 MB of layout
 pool each) exceed twice the 126 MB L2 (config.l2 says so); the L2-resident number is reported
 beside it.  (A replay starts at batch 0 again while the previous one ended at batch
 (S-1) mod R, so at most R/2 of the S launches of a region can see lines of the previous
-replay: < 2 %.  GX_BENCH_FLUSH=1 adds a 512 MB write before every region instead; the big
-writes themselves push the GPU into its slower sustained state, so they are off by default.)
+replay: < 2 %.  GX_BENCH_FLUSH=1 adds a 512 MB write before every region instead.)
 """
 from __future__ import annotations
 
@@ -64,7 +64,7 @@ FLUSH_BYTES = 512 << 20       # written before every timed region: evicts the L2
 REGION_SECONDS = float(os.environ.get("GX_BENCH_REGION_S", "0.025"))   # a timed region lasts at least this long, whatever --steps is
 MAX_REGION_STEPS = 1 << 16    # graph nodes per region (bounds capture time when --steps is huge)
 BURN_IN = 2000                # random-action steps every batch takes before anything is timed (num_steps = 1000)
-SETTLE_SECONDS = float(os.environ.get("GX_BENCH_SETTLE_S", "0.3"))   # untimed replays before the timed regions (sustained GPU state)
+SETTLE_SECONDS = float(os.environ.get("GX_BENCH_SETTLE_S", "0.3"))   # untimed replays before the timed regions (the GPU is busy while the timed work is enqueued)
 FLUSH = bool(int(os.environ.get("GX_BENCH_FLUSH", "0")))   # 512 MB write before every region (see the docstring)
 REGIONS = int(os.environ.get("GX_BENCH_REGIONS", "7"))   # regions measured; the median is reported
 TASK = "Goal_Point_8Hazards"
@@ -262,7 +262,7 @@ def time_steps(torch, lib, batches, steps, stream, barrier=None):
 
 class Regions:
     """A timed REGION = `S` fused step launches (S = M windows x K steps) as a chain of CUDA
-    graphs (<= 2048 kernel nodes each; every chunk is its own graph, so the round-robin over
+    graphs (at most two per region; every chunk is its own graph, so the round-robin over
     the batches runs on unbroken from the first step of a region to the last).  Legal because
     every counter the kernels use lives in device memory.
 
@@ -271,9 +271,13 @@ class Regions:
     neither the host nor the graph-launch latency is inside a region."""
 
 
-    def __init__(self, torch, issue, S, flush_buf, chunk=2048):
+    def __init__(self, torch, issue, S, flush_buf, chunk=None):
         self.torch, self.S, self.flush_buf = torch, S, flush_buf
         self.graphs = []
+        # at most TWO graphs per region: with four 2048-node graphs launched in turn every step of the region measured
+        # 6 % slower than with three (5.97 vs 5.61 us, reproducibly, whatever the settle time: re-upload of the graphs'
+        # device-side images, not kernel time; tools/diag_regions.py)
+        chunk = chunk or max(2048, (S + 1) // 2)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         sp = C.c_void_p(side.cuda_stream)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -229,6 +230,109 @@ __global__ void __launch_bounds__(64) gxt_step_kernel(const __grid_constant__ gx
     if (aux) { aux[4 * (size_t)i] = flags; aux[4 * (size_t)i + 1] = o.violations; aux[4 * (size_t)i + 2] = o.contacts; aux[4 * (size_t)i + 3] = o.goal_bin; }
   }
   gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, min(32, p.n - wbase), p.obs_dim, lane);
+}
+
+// ---- Engine.step (+ fused reset_done) with 8 lanes per env: 4 envs per warp, 16 per 128-thread block ----------------
+template <bool AUTORESET>
+__global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_constant__ gxt_params p, float* __restrict__ S,
+                                                             const float* __restrict__ pool, const float* __restrict__ action,
+                                                             float* __restrict__ obs, float* __restrict__ reward, float* __restrict__ done,
+                                                             float* __restrict__ cost, int32_t* __restrict__ aux) {
+  const int l = threadIdx.x & (GXT_LPE - 1), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int env = (blockIdx.x * blockDim.x + threadIdx.x) / GXT_LPE;
+  const int wenv0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / GXT_LPE;     // first env of this warp
+  if (wenv0 >= p.n) return;
+  const bool live = env < p.n;
+  const int i = live ? env : p.n - 1;
+  const unsigned mask = gxt_grp_mask();
+  float* tile = gxt_smem + (size_t)warp * (32 / GXT_LPE) * p.obs_dim;
+  float* row = tile + (size_t)(lane / GXT_LPE) * p.obs_dim;
+  GxDyn d;
+  float prev_box, goal_button;
+  gxt_load_dyn(p, S, i, d, prev_box, goal_button);
+  const float a0 = action[(size_t)i * 2], a1 = action[(size_t)i * 2 + 1];
+  const float last_dist = d.prev_dist, last_box = prev_box, last_done = d.done;
+  GxtGeom g;
+  g.time = d.steps * p.dt;
+  float c0, c1, c2 = 0.0f;
+  if (p.robot == GXT_ROBOT_CAR) {
+    gxt_car_step(p, d, a0, a1, c0, c1, g.px, g.py, g.r00, g.r10);
+  } else {
+    c0 = d.hc * a0; c1 = d.hs * a0; c2 = a1;
+    gx_mjx_step_point(p.pt, d, c0, c1, c2, g.px, g.py, g.r00, g.r10, nullptr);
+  }
+  gxt_resolve_pillars(p, S, i, d);
+  gxt_zero_lidars(p, row, l);
+  __syncwarp(mask);
+  GxtObs o = gxt_obs_lanes(p, S, i, l, mask, g, goal_button, row, live ? &d : nullptr);
+  int bad = o.bad | gx_notfinite(c0) | gx_notfinite(c1) | gx_notfinite(c2) | gx_notfinite(d.qx) | gx_notfinite(d.qy) | gx_notfinite(d.qth) |
+            gx_notfinite(d.vx) | gx_notfinite(d.vy) | gx_notfinite(d.vw);
+  const float dist = o.dist_task;
+  const float last = last_done > 0.0f ? dist : last_dist;
+  const float d_dist = last - dist;
+  float rew, dn_flag;
+  int flags = 0;
+  if (p.task == GXT_TASK_PUSH) {
+    const float lastb = last_done > 0.0f ? o.dist_box : last_box;
+    rew = (lastb - o.dist_box) * p.reward_box_dist + d_dist * p.reward_box_goal;
+    dn_flag = dist < p.goal_size ? 1.0f : 0.0f;
+  } else if (p.task == GXT_TASK_BUTTON) {
+    rew = d_dist * p.reward_distance;
+    dn_flag = dist < p.size[GXT_ROBOT] + p.size[GXT_BUTTON] ? 1.0f : 0.0f;
+  } else {
+    rew = d_dist * p.reward_distance;
+    dn_flag = dist < p.goal_size ? 1.0f : 0.0f;
+  }
+  if (dn_flag > 0.0f) flags |= GX_AUX_GOAL;
+  if (gx_abs(d_dist) > 1.0f) { dn_flag = 1.0f; rew = 0.0f; flags |= GX_AUX_JUMP; }
+  if (bad) { rew = 0.0f; dn_flag = 1.0f; flags |= GX_AUX_GUARD; }
+  if (d.steps > p.num_steps) { dn_flag = 1.0f; flags |= GX_AUX_TIMEOUT; }
+  d.steps = dn_flag > 0.0f ? 0.0f : d.steps + 1.0f;
+  d.done = dn_flag;
+  d.prev_dist = dist;
+  prev_box = o.dist_box;
+  d.hc = g.r00; d.hs = g.r10;
+  d.age += 1;
+  if (AUTORESET && dn_flag > 0.0f) {
+    // re-place (the 8 lanes copy the layout row), then the reset observation: a second pass over the objects
+    __syncwarp(mask);
+    const float* lay = gxt_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
+    if (live) {
+      for (int k = l; k < 2 * p.nobj; k += GXT_LPE) S[(size_t)(GXT_SLOT_OBJ + k) * p.cap + i] = lay[k];
+      for (int gq = l; gq < p.ng; gq += GXT_LPE) S[(size_t)(GXT_SLOT_OBJ + 2 * p.nobj + gq) * p.cap + i] = lay[2 * p.nobj + 2 + gq];
+    }
+    d.qx = lay[2 * p.nobj]; d.qy = lay[2 * p.nobj + 1];
+    d.qth = 0.0f; d.vx = 0.0f; d.vy = 0.0f; d.vw = 0.0f;
+    goal_button = 0.0f;
+    if (p.task == GXT_TASK_BUTTON) {
+      const uint64_t gid = p.pt.env_id_offset + (uint64_t)i;
+      const gx_u32x4 r = gx_philox4x32_10((uint32_t)gid, (uint32_t)d.age, (uint32_t)(d.age >> 32), GX_STREAM_BUTTON, p.pt.seed_lo, p.pt.seed_hi);
+      goal_button = (float)gx_randint(r.v[0], (uint32_t)p.count[GXT_BUTTON]);
+    }
+    if (live && l == 0) S[(size_t)14 * p.cap + i] = goal_button;
+    c0 = 0.0f; c1 = 0.0f; c2 = 0.0f;
+    GxtGeom g2;
+    g2.px = d.qx; g2.py = d.qy; g2.r00 = 1.0f; g2.r10 = 0.0f; g2.time = 0.0f;
+    gxt_zero_lidars(p, row, l);
+    __threadfence_block();
+    __syncwarp(mask);
+    gxt_obs_lanes(p, S, i, l, mask, g2, goal_button, row, nullptr);
+  }
+  if (l == 0) {
+    if (p.off_ctrl >= 0) { row[p.off_ctrl] = c0; row[p.off_ctrl + 1] = c1; if (p.nu == 3) row[p.off_ctrl + 2] = c2; }
+    if (p.off_qpos >= 0) { row[p.off_qpos] = d.qx; row[p.off_qpos + 1] = d.qy; row[p.off_qpos + 2] = d.qth; }
+    if (p.off_qvel >= 0) { row[p.off_qvel] = d.vx; row[p.off_qvel + 1] = d.vy; row[p.off_qvel + 2] = d.vw; }
+    if (live) {
+      gxt_store_dyn(p, S, i, d, prev_box);
+      reward[i] = rew; done[i] = dn_flag; cost[i] = o.cost;
+      if (aux) { aux[4 * (size_t)i] = flags; aux[4 * (size_t)i + 1] = o.violations; aux[4 * (size_t)i + 2] = o.contacts; aux[4 * (size_t)i + 3] = o.goal_bin; }
+    }
+  }
+  __syncwarp();
+  // the warp's 4 rows are contiguous in shared memory and in the output
+  const int rows = min(32 / GXT_LPE, p.n - wenv0);
+  float* dst = obs + (size_t)wenv0 * p.obs_dim;
+  for (int k = lane; k < rows * p.obs_dim; k += 32) dst[k] = tile[k];
 }
 
 __global__ void gxt_reset_done_kernel(const __grid_constant__ gxt_params p, float* __restrict__ S, const float* __restrict__ pool,
@@ -467,6 +571,17 @@ GXT_API int gxt_step(gxt_env* e, const float* action, float* obs, float* reward,
   GxtDeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const gxt_params& p = e->p;
+  // 8 lanes per env while the batch cannot fill the machine with one thread per env (GXT_LANES=0|1 in the environment forces a path)
+  const char* force = getenv("GXT_LANES");
+  const bool lanes = force ? force[0] == '1' : p.n <= e->sm_count * 1024;
+  if (lanes) {
+    const int block = 128, epb = block / GXT_LPE;
+    const size_t sh = sizeof(float) * epb * p.obs_dim;
+    if (autoreset) gxt_step_lanes_kernel<true><<<gxt_div_up(p.n, epb), block, sh, st>>>(p, e->S, e->pool, action, obs, reward, done, cost, aux);
+    else gxt_step_lanes_kernel<false><<<gxt_div_up(p.n, epb), block, sh, st>>>(p, e->S, e->pool, action, obs, reward, done, cost, aux);
+    GXT_LAUNCH_CHECK("gxt_step_lanes_kernel");
+    return GX_OK;
+  }
   const int block = 64;
   const size_t sh = sizeof(float) * block * p.obs_dim;
   if (autoreset) gxt_step_kernel<true><<<gxt_div_up(p.n, block), block, sh, st>>>(p, e->S, e->pool, action, obs, reward, done, cost, aux);

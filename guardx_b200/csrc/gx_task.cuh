@@ -271,6 +271,170 @@ __device__ __forceinline__ void gxt_resolve_contacts(const gxt_params& p, float*
   }
 }
 
+// ---- 8 lanes per env (small and medium batches) -------------------------------------------------------------------
+// At BASELINE configs[2]'s size (16 384 envs) one thread per env leaves less than one warp per scheduler and every env is a
+// ~4 k-instruction dependent chain (18 objects x lidar ray + cost).  Here lane l of an env's 8 lanes owns objects l, l + 8, ...:
+// it reads the object once, casts its ray into the class's lidar (shared-memory row, float max as an integer atomicMax:
+// every contribution is >= +0, NaN is canonicalised to the positive pattern, which compares above every finite value),
+// adds its cost term, and -- for a vase or the box -- pushes it out of the robot's way.  Cost / counts are combined with a
+// fixed butterfly over the 8 lanes (same value on every lane).
+#define GXT_LPE 8
+
+__device__ __forceinline__ unsigned gxt_grp_mask() { return 0xffu << (threadIdx.x & 24); }
+
+__device__ __forceinline__ void gxt_scatter_atomic(const gx_params& p, const GxRay& r, float* bins, int& bad) {
+  const int nb = p.nb;
+  auto put = [&](int b, float v) {
+    bad |= gx_notfinite(v);
+    const int bits = (v != v) ? 0x7fc00000 : __float_as_int(v);
+    atomicMax(reinterpret_cast<int*>(bins + b), bits);
+  };
+  if (r.bin < nb) put(r.bin, r.sensor);
+  if (p.alias) {
+    int bp = r.bin + 1; if (bp >= nb) bp -= nb; if (bp >= nb) bp -= nb;
+    int bm = r.bin - 1; if (bm < 0) bm += nb;
+    put(bp, r.up);
+    put(bm, r.down);
+  }
+}
+
+__device__ __forceinline__ float gxt_sum8(float x, unsigned mask) {
+  x += __shfl_xor_sync(mask, x, 4);
+  x += __shfl_xor_sync(mask, x, 2);
+  x += __shfl_xor_sync(mask, x, 1);
+  return x;
+}
+__device__ __forceinline__ int gxt_sum8i(int x, unsigned mask) {
+  x += __shfl_xor_sync(mask, x, 4);
+  x += __shfl_xor_sync(mask, x, 2);
+  x += __shfl_xor_sync(mask, x, 1);
+  return x;
+}
+
+// One observation / cost pass of an env by its 8 lanes from the pose snapshot `g`.  `row`: the env's row in shared memory
+// (lidar ranges must be zero on entry, see gxt_zero_lidars).  `push` (may be null): the post-step robot state; vases and
+// the box that overlap it are pushed out (written back to S) AFTER their ray has been cast from where they were.
+__device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __restrict__ S, int i, int l, unsigned mask, const GxtGeom& g,
+                                                float goal_button, float* row, const GxDyn* push) {
+  GxtObs o;
+  o.goal_bin = 0;
+  int bad = 0, viol = 0, contacts = 0;
+  float cost = 0.0f;
+  const float rr = p.size[GXT_ROBOT];
+  const int tgt = p.task == GXT_TASK_BUTTON
+                      ? p.first[GXT_BUTTON] + min(max((int)goal_button, 0), p.count[GXT_BUTTON] - 1)
+                      : p.first[GXT_GOAL];
+  int goal_bin = 0;
+  // task distances (every lane, same numbers) from where target and box are NOW: the loop below may push the box
+  {
+    float tx, ty;
+    gxt_obj_xy(p, S, i, tgt, tx, ty);
+    const float dx = tx - g.px, dy = ty - g.py;
+    o.dist_task = gx_sqrt(dx * dx + dy * dy);
+    o.dist_box = 0.0f;
+    if (p.task == GXT_TASK_PUSH) {
+      float bx, by;
+      gxt_obj_xy(p, S, i, p.first[GXT_BOX], bx, by);
+      const float ex = bx - g.px, ey = by - g.py;
+      o.dist_box = gx_sqrt(ex * ex + ey * ey);
+      const float fx = tx - bx, fy = ty - by;
+      o.dist_task = gx_sqrt(fx * fx + fy * fy);       // box -> goal
+    }
+  }
+  __syncwarp(mask);
+#pragma unroll 1
+  for (int j = l; j < p.nobj; j += GXT_LPE) {
+    const int cls = gxt_class_of_obj(p, j);
+    float ox, oy;
+    if (cls == GXT_GREMLIN) gxt_gremlin_xy(p, S, i, j - p.first[GXT_GREMLIN], g.time, ox, oy);
+    else gxt_obj_xy(p, S, i, j, ox, oy);
+    float ex, ey;
+    gx_ego(ox, oy, g.px, g.py, g.r00, g.r10, ex, ey);
+    const GxRay r = gx_lidar_ray(p.pt, ex, ey);
+    int off = -1;
+    switch (cls) {
+      case GXT_BOX: off = p.off_box_lidar; break;
+      case GXT_BUTTON: off = p.off_buttons_lidar; break;
+      case GXT_HAZARD: off = p.off_hazards_lidar; break;
+      case GXT_VASE: off = p.off_vases_lidar; break;
+      case GXT_PILLAR: off = p.off_pillars_lidar; break;
+      case GXT_GREMLIN: off = p.off_gremlins_lidar; break;
+      default: break;
+    }
+    if (off >= 0) gxt_scatter_atomic(p.pt, r, row + off, bad);
+    if (j == tgt) {
+      goal_bin = r.bin;
+      if (p.off_goal_compass >= 0) { row[p.off_goal_compass] = ex; row[p.off_goal_compass + 1] = ey; bad |= gx_notfinite(ex) | gx_notfinite(ey); }
+      if (p.off_goal_lidar >= 0) gxt_scatter_atomic(p.pt, r, row + p.off_goal_lidar, bad);
+    }
+    if (cls == GXT_BOX && p.off_box_compass >= 0) { row[p.off_box_compass] = ex; row[p.off_box_compass + 1] = ey; bad |= gx_notfinite(ex) | gx_notfinite(ey); }
+    // cost term of this object (world-frame distance to the snapshot position, as engine.py:804-811 does for hazards)
+    const float dx = ox - g.px, dy = oy - g.py;
+    const float dist = gx_sqrt(dx * dx + dy * dy);
+    if (cls == GXT_HAZARD) {
+      const float term = p.size[GXT_HAZARD] - gx_min(dist, p.size[GXT_HAZARD]);
+      if (term > 0.0f) ++viol;
+      cost = cost + p.hazards_cost_scale * term;
+    } else if (cls == GXT_BUTTON) {
+      if (!(p.task == GXT_TASK_BUTTON && j == tgt) && dist < rr + p.size[GXT_BUTTON]) { cost = cost + p.buttons_cost; ++contacts; }
+    } else if (cls == GXT_VASE) {
+      if (dist < rr + p.size[GXT_VASE]) { cost = cost + p.vases_contact_cost; ++contacts; }
+    } else if (cls == GXT_PILLAR) {
+      if (dist < rr + p.size[GXT_PILLAR]) { cost = cost + p.pillars_cost; ++contacts; }
+    } else if (cls == GXT_GREMLIN) {
+      if (dist < rr + p.size[GXT_GREMLIN]) { cost = cost + p.gremlins_contact_cost; ++contacts; }
+      const float gap = dist - p.size[GXT_GREMLIN];
+      if (gap < p.gremlins_dist_threshold) cost = cost + p.gremlins_dist_cost * (p.gremlins_dist_threshold - gap);
+    }
+    // quasi-static push by the post-step robot
+    if (push && (cls == GXT_VASE || cls == GXT_BOX)) {
+      const float qx = ox - push->qx, qy = oy - push->qy;
+      const float dq = gx_sqrt(qx * qx + qy * qy);
+      const float lim = rr + p.size[cls];
+      if (dq < lim && dq > 0.0f) {
+        const float nx = gx_div(qx, dq), ny = gx_div(qy, dq);
+        S[(size_t)(GXT_SLOT_OBJ + 2 * j) * p.cap + i] = push->qx + nx * lim;
+        S[(size_t)(GXT_SLOT_OBJ + 2 * j + 1) * p.cap + i] = push->qy + ny * lim;
+      }
+    }
+  }
+  o.cost = gxt_sum8(cost, mask);
+  o.violations = gxt_sum8i(viol, mask);
+  o.contacts = gxt_sum8i(contacts, mask);
+  o.bad = gxt_sum8i(bad, mask) != 0;
+  o.goal_bin = gxt_sum8i(goal_bin, mask);          // exactly one lane owns the target
+  return o;
+}
+
+// the robot against the pillars (sequential: each projection moves the robot), every lane computes the same numbers
+__device__ __forceinline__ void gxt_resolve_pillars(const gxt_params& p, const float* __restrict__ S, int i, GxDyn& d) {
+  const float rr = p.size[GXT_ROBOT];
+#pragma unroll 1
+  for (int k = 0; k < p.count[GXT_PILLAR]; ++k) {
+    float ox, oy;
+    gxt_obj_xy(p, S, i, p.first[GXT_PILLAR] + k, ox, oy);
+    float dx = d.qx - ox, dy = d.qy - oy;
+    const float dist = gx_sqrt(dx * dx + dy * dy);
+    const float lim = rr + p.size[GXT_PILLAR];
+    if (dist < lim && dist > 0.0f) {
+      const float nx = gx_div(dx, dist), ny = gx_div(dy, dist);
+      d.qx = ox + nx * lim; d.qy = oy + ny * lim;
+      const float vn = d.vx * nx + d.vy * ny;
+      if (vn < 0.0f) { d.vx = d.vx - vn * nx; d.vy = d.vy - vn * ny; }
+    }
+  }
+}
+
+// zero the lidar ranges of the env's row (its 8 lanes stride over the row)
+__device__ __forceinline__ void gxt_zero_lidars(const gxt_params& p, float* row, int l) {
+  const int nb = p.pt.nb;
+  const int offs[7] = {p.off_box_lidar, p.off_buttons_lidar, p.off_goal_lidar, p.off_gremlins_lidar, p.off_hazards_lidar,
+                       p.off_pillars_lidar, p.off_vases_lidar};
+#pragma unroll
+  for (int c = 0; c < 7; ++c)
+    if (offs[c] >= 0) for (int k = l; k < nb; k += GXT_LPE) row[offs[c] + k] = 0.0f;
+}
+
 // ---- placement ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ const float* gxt_pick_layout(const gxt_params& p, const float* pool, const float* layout, int i, uint64_t age,
                                                         uint32_t stream) {
