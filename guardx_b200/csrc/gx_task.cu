@@ -247,6 +247,9 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
   const unsigned mask = gxt_grp_mask();
   float* tile = gxt_smem + (size_t)warp * (32 / GXT_LPE) * p.obs_dim;
   float* row = tile + (size_t)(lane / GXT_LPE) * p.obs_dim;
+  const int ob_stride = 2 * p.nobj + p.ng;
+  float* ob = gxt_smem + (size_t)(blockDim.x / GXT_LPE) * p.obs_dim + (size_t)(threadIdx.x / GXT_LPE) * ob_stride;
+  gxt_stage_objects(p, S, i, l, ob);
   GxDyn d;
   float prev_box, goal_button;
   gxt_load_dyn(p, S, i, d, prev_box, goal_button);
@@ -261,10 +264,10 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
     c0 = d.hc * a0; c1 = d.hs * a0; c2 = a1;
     gx_mjx_step_point(p.pt, d, c0, c1, c2, g.px, g.py, g.r00, g.r10, nullptr);
   }
-  gxt_resolve_pillars(p, S, i, d);
   gxt_zero_lidars(p, row, l);
   __syncwarp(mask);
-  GxtObs o = gxt_obs_lanes(p, S, i, l, mask, g, goal_button, row, live ? &d : nullptr);
+  gxt_resolve_pillars(p, ob, d);
+  GxtObs o = gxt_obs_lanes(p, S, ob, i, l, mask, g, goal_button, row, live ? &d : nullptr);
   int bad = o.bad | gx_notfinite(c0) | gx_notfinite(c1) | gx_notfinite(c2) | gx_notfinite(d.qx) | gx_notfinite(d.qy) | gx_notfinite(d.qth) |
             gx_notfinite(d.vx) | gx_notfinite(d.vy) | gx_notfinite(d.vw);
   const float dist = o.dist_task;
@@ -297,9 +300,15 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
     // re-place (the 8 lanes copy the layout row), then the reset observation: a second pass over the objects
     __syncwarp(mask);
     const float* lay = gxt_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
-    if (live) {
-      for (int k = l; k < 2 * p.nobj; k += GXT_LPE) S[(size_t)(GXT_SLOT_OBJ + k) * p.cap + i] = lay[k];
-      for (int gq = l; gq < p.ng; gq += GXT_LPE) S[(size_t)(GXT_SLOT_OBJ + 2 * p.nobj + gq) * p.cap + i] = lay[2 * p.nobj + 2 + gq];
+    for (int k = l; k < 2 * p.nobj; k += GXT_LPE) {
+      const float v = lay[k];
+      ob[k] = v;
+      if (live) S[(size_t)(GXT_SLOT_OBJ + k) * p.cap + i] = v;
+    }
+    for (int gq = l; gq < p.ng; gq += GXT_LPE) {
+      const float v = lay[2 * p.nobj + 2 + gq];
+      ob[2 * p.nobj + gq] = v;
+      if (live) S[(size_t)(GXT_SLOT_OBJ + 2 * p.nobj + gq) * p.cap + i] = v;
     }
     d.qx = lay[2 * p.nobj]; d.qy = lay[2 * p.nobj + 1];
     d.qth = 0.0f; d.vx = 0.0f; d.vy = 0.0f; d.vw = 0.0f;
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
     gxt_zero_lidars(p, row, l);
     __threadfence_block();
     __syncwarp(mask);
-    gxt_obs_lanes(p, S, i, l, mask, g2, goal_button, row, nullptr);
+    gxt_obs_lanes(p, S, ob, i, l, mask, g2, goal_button, row, nullptr);
   }
   if (l == 0) {
     if (p.off_ctrl >= 0) { row[p.off_ctrl] = c0; row[p.off_ctrl + 1] = c1; if (p.nu == 3) row[p.off_ctrl + 2] = c2; }
@@ -576,7 +585,7 @@ GXT_API int gxt_step(gxt_env* e, const float* action, float* obs, float* reward,
   const bool lanes = force ? force[0] == '1' : p.n <= e->sm_count * 1024;
   if (lanes) {
     const int block = 128, epb = block / GXT_LPE;
-    const size_t sh = sizeof(float) * epb * p.obs_dim;
+    const size_t sh = sizeof(float) * epb * (p.obs_dim + 2 * p.nobj + p.ng);     // observation rows + staged object coordinates
     if (autoreset) gxt_step_lanes_kernel<true><<<gxt_div_up(p.n, epb), block, sh, st>>>(p, e->S, e->pool, action, obs, reward, done, cost, aux);
     else gxt_step_lanes_kernel<false><<<gxt_div_up(p.n, epb), block, sh, st>>>(p, e->S, e->pool, action, obs, reward, done, cost, aux);
     GXT_LAUNCH_CHECK("gxt_step_lanes_kernel");

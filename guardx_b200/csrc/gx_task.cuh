@@ -314,8 +314,9 @@ __device__ __forceinline__ int gxt_sum8i(int x, unsigned mask) {
 // One observation / cost pass of an env by its 8 lanes from the pose snapshot `g`.  `row`: the env's row in shared memory
 // (lidar ranges must be zero on entry, see gxt_zero_lidars).  `push` (may be null): the post-step robot state; vases and
 // the box that overlap it are pushed out (written back to S) AFTER their ray has been cast from where they were.
-__device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __restrict__ S, int i, int l, unsigned mask, const GxtGeom& g,
-                                                float goal_button, float* row, const GxDyn* push) {
+// `ob`: the env's object coordinates staged in shared memory (xy per object, then the gremlin phases; gxt_stage_objects).
+__device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __restrict__ S, const float* ob, int i, int l, unsigned mask,
+                                                const GxtGeom& g, float goal_button, float* row, const GxDyn* push) {
   GxtObs o;
   o.goal_bin = 0;
   int bad = 0, viol = 0, contacts = 0;
@@ -327,14 +328,12 @@ __device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __re
   int goal_bin = 0;
   // task distances (every lane, same numbers) from where target and box are NOW: the loop below may push the box
   {
-    float tx, ty;
-    gxt_obj_xy(p, S, i, tgt, tx, ty);
+    const float tx = ob[2 * tgt], ty = ob[2 * tgt + 1];
     const float dx = tx - g.px, dy = ty - g.py;
     o.dist_task = gx_sqrt(dx * dx + dy * dy);
     o.dist_box = 0.0f;
     if (p.task == GXT_TASK_PUSH) {
-      float bx, by;
-      gxt_obj_xy(p, S, i, p.first[GXT_BOX], bx, by);
+      const float bx = ob[2 * p.first[GXT_BOX]], by = ob[2 * p.first[GXT_BOX] + 1];
       const float ex = bx - g.px, ey = by - g.py;
       o.dist_box = gx_sqrt(ex * ex + ey * ey);
       const float fx = tx - bx, fy = ty - by;
@@ -345,9 +344,13 @@ __device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __re
 #pragma unroll 1
   for (int j = l; j < p.nobj; j += GXT_LPE) {
     const int cls = gxt_class_of_obj(p, j);
-    float ox, oy;
-    if (cls == GXT_GREMLIN) gxt_gremlin_xy(p, S, i, j - p.first[GXT_GREMLIN], g.time, ox, oy);
-    else gxt_obj_xy(p, S, i, j, ox, oy);
+    float ox = ob[2 * j], oy = ob[2 * j + 1];
+    if (cls == GXT_GREMLIN) {      // circle of radius gremlins_travel about the centre, 1 rad / s
+      float sn, cs;
+      gx_sincos(ob[2 * p.nobj + (j - p.first[GXT_GREMLIN])] + g.time, &sn, &cs);
+      ox = ox + p.gremlins_travel * cs;
+      oy = oy + p.gremlins_travel * sn;
+    }
     float ex, ey;
     gx_ego(ox, oy, g.px, g.py, g.r00, g.r10, ex, ey);
     const GxRay r = gx_lidar_ray(p.pt, ex, ey);
@@ -407,12 +410,11 @@ __device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __re
 }
 
 // the robot against the pillars (sequential: each projection moves the robot), every lane computes the same numbers
-__device__ __forceinline__ void gxt_resolve_pillars(const gxt_params& p, const float* __restrict__ S, int i, GxDyn& d) {
+__device__ __forceinline__ void gxt_resolve_pillars(const gxt_params& p, const float* ob, GxDyn& d) {
   const float rr = p.size[GXT_ROBOT];
 #pragma unroll 1
   for (int k = 0; k < p.count[GXT_PILLAR]; ++k) {
-    float ox, oy;
-    gxt_obj_xy(p, S, i, p.first[GXT_PILLAR] + k, ox, oy);
+    const float ox = ob[2 * (p.first[GXT_PILLAR] + k)], oy = ob[2 * (p.first[GXT_PILLAR] + k) + 1];
     float dx = d.qx - ox, dy = d.qy - oy;
     const float dist = gx_sqrt(dx * dx + dy * dy);
     const float lim = rr + p.size[GXT_PILLAR];
@@ -423,6 +425,13 @@ __device__ __forceinline__ void gxt_resolve_pillars(const gxt_params& p, const f
       if (vn < 0.0f) { d.vx = d.vx - vn * nx; d.vy = d.vy - vn * ny; }
     }
   }
+}
+
+// stage the env's object coordinates and gremlin phases in shared memory: the 8 lanes issue their loads together, every
+// later access (lidar loop, pillars, target, box) is a shared-memory read instead of a dependent global load
+__device__ __forceinline__ void gxt_stage_objects(const gxt_params& p, const float* __restrict__ S, int i, int l, float* ob) {
+  const int cnt = 2 * p.nobj + p.ng;
+  for (int k = l; k < cnt; k += GXT_LPE) ob[k] = S[(size_t)(GXT_SLOT_OBJ + k) * p.cap + i];
 }
 
 // zero the lidar ranges of the env's row (its 8 lanes stride over the row)
