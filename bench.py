@@ -140,11 +140,15 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def workload_config(n, world, how):
+def workload_config(n, world):
+    """the `config` object: identical for the CUDA arm and the --impl reference arm (what differs -- how each arm runs the
+    workload, the measured L2 working set, the region sizes -- is in the top-level keys `how` and `timing`)"""
     return {"workload": f"{TASK}, {n} envs per GPU, random-action rollout (a ~ U(-1,1), pre-generated), "
-                        f"step + reset_done every step, stationary (random episode phases + {BURN_IN} burn-in steps per batch)",
-            "envs_per_gpu": n, "total_envs": n * world, "how": how,
-            "parallelism": f"dp{world} (independent env shards, no data-path collective)"}
+                        f"step + reset_done every step",
+            "envs_per_gpu": n, "total_envs": n * world,
+            "parallelism": f"dp{world} (independent env shards, no data-path collective)",
+            "l2": "CUDA arm: cold -- every timed launch touches a batch (state, actions, outputs, layout pool) not touched for "
+                  "R - 1 launches, R batches > 2 x 126 MB L2 (sizes in `timing`), episode phases stationary; CPU arm: host memory"}
 
 
 # ------------------------------------------------------------ reference arm
@@ -156,6 +160,11 @@ def oracle_steps_per_sec(n_envs, steps, warmup, threads):
     o.reset()
     L, h = o.L, o.h
     rng = np.random.default_rng(0)
+    # the same stationary workload as the CUDA arm: random episode phases, then a burn-in
+    st = o.get_state()
+    st[:, 10] = rng.integers(0, 1000, n_envs).astype(np.float32)
+    o.set_state(st)
+    o.rollout(500, want=())
     acts = rng.uniform(-1, 1, (64, n_envs, 2)).astype(np.float32)
     obs = np.empty((n_envs, o.obs_dim), np.float32)
     rdc = np.empty((3, n_envs), np.float32)
@@ -180,14 +189,20 @@ def reference_arm(args, rank, world):
         return
     threads = host_threads()
     n = ENVS_PER_GPU * world
-    rate, dt = oracle_steps_per_sec(n, args.steps, max(args.warmup, 3), threads)
-    sample = f"{args.steps} steps x {n} envs, gxo_step + gxo_reset_done, actions pre-generated in host memory"
+    # a window is args.steps steps; M windows back to back so that the timed region is ~2 s whatever --steps is
+    r0, d0 = oracle_steps_per_sec(n, max(args.steps, 50), max(args.warmup, 3), threads)
+    M = max(1, int(2.0 * r0 / (n * args.steps)))
+    rate, dt = oracle_steps_per_sec(n, args.steps * M, max(args.warmup, 3), threads)
+    dt /= M
+    sample = (f"{M} windows x {args.steps} steps x {n} envs ({dt * M:.2f} s), gxo_step + gxo_reset_done, stationary workload, "
+              "actions pre-generated in host memory")
     line = {
         "impl": "reference", "metric": "env-steps/sec", "value": rate, "unit": "env-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(ENVS_PER_GPU, world, "CPU oracle: gxo_step + gxo_reset_done per step, all host threads"),
+        "config": workload_config(ENVS_PER_GPU, world),
+        "how": "CPU oracle: gxo_step + gxo_reset_done per step, all host threads",
         "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                          "sample": sample,
                          "note": "CPU oracle (C restatement of the reference step, OpenMP); the reference itself "
@@ -626,14 +641,12 @@ def main():
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": K, "warmup": warmup, "ms_per_step": 1e3 * dt / S, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(n, world, "CUDA: fused step + auto-reset (gx_step_autoreset), one kernel "
-                                                     "launch per step, replayed as CUDA graphs, in-kernel episode statistics"),
-                           l2=f"cold: {R} independent {n}-env batches (own state, actions, outputs, layout pool) stepped "
-                              f"round-robin, working set {working_set / 1e6:.0f} MB > 2 x 126 MB L2"
-                              + ("; 512 MB flush before every region" if FLUSH else ""),
-                           timing=f"window = {K} steps; region = {M} windows = {S} launches back to back; "
-                                  f"{REGIONS} regions, median reported; events enqueued behind {SETTLE_SECONDS} s of untimed replays"),
-            "timing": {"windows_per_region": M, "launches_per_region": S, "regions": REGIONS,
+            "config": workload_config(n, world),
+            "how": "CUDA: fused step + auto-reset (gx_step_autoreset), one kernel launch per step, replayed as CUDA graphs, "
+                   f"in-kernel episode statistics; stationary workload (random episode phases + {BURN_IN} burn-in steps per batch)",
+            "timing": {"l2_batches": R, "l2_working_set_mb": working_set / 1e6, "l2_flush_between_regions": FLUSH,
+                       "window_steps": K, "settle_seconds": SETTLE_SECONDS,
+                       "windows_per_region": M, "launches_per_region": S, "regions": REGIONS,
                        "region_ms_median": 1e3 * dt, "region_ms_min": 1e3 * min(region_s), "region_ms_max": 1e3 * max(region_s),
                        "window_ms": 1e3 * dt / M},
             "value_l2_resident": world * n * S / dt_hot,

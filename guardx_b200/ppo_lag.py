@@ -388,9 +388,14 @@ def ppo_lag(env, cfg: PPOLagConfig | None = None, ac: ActorCritic | None = None)
         gxd.allreduce_stats(stats)
         summ = gxd.episode_summary(stats.tolist())
         # episodes cut by the epoch end count with what they accumulated (ppo_train.py:392-396 logs them too)
-        # (no finished episode anywhere: the mean accumulated cost per env, summed over ALL ranks so that
-        # every rank applies the same multiplier update)
-        ep_cost = summ['EpCost'] if summ['Episodes'] > 0 else float(gxd.global_mean(buf['cost'].sum(0).mean()))
+        # (no finished episode anywhere: the mean accumulated return / cost per env over ALL ranks, so that every rank
+        # applies the same multiplier update)
+        if summ['Episodes'] == 0:
+            # ppo_train.py:392-409 logs the paths the epoch end cuts off as episodes: per-env sums over the epoch
+            summ['EpRet'] = float(gxd.global_mean(buf['rew'].sum(0).mean()))
+            summ['EpCost'] = float(gxd.global_mean(buf['cost'].sum(0).mean()))
+            summ['EpLen'] = float(T)
+        ep_cost = summ['EpCost']
         info = ppo_update(ac, pi_opt, v_opt, vc_opt, data, cfg, lmd)
         lmd = max(0.0, lmd + cfg.lam_lr * (ep_cost - cfg.target_cost))     # trpolag.py:466-471
         row = dict(Epoch=epoch, Lambda=lmd, Time=time.time() - t_start, EpCostUsed=ep_cost,
