@@ -342,6 +342,34 @@ def test_nan_inf_actions_trip_the_guard(mods):
     bits_equal(cpu(g.get_state()), o.get_state(), "state")
 
 
+@pytest.mark.parametrize("n,lanes", [(96, True), (20000, False)])
+def test_exotic_states_through_the_fused_autoreset_paths(mods, n, lanes):
+    """The fused step + auto-reset kernels decide `done` before the lidar only for states whose pose and objects are finite and
+    below 1e15 (gx_lanes.cuh / guardx.cu: `sane`); anything else takes the reference order in an out-of-line function.  Inject
+    such states (NaN / Inf / astronomically large pose, goal and hazards, NaN velocities, huge step counters) and compare
+    step_autoreset with the oracle's step + reset_done, bit for bit, on both kernel families (16 lanes per env; thread per env)."""
+    g, o = make_pair(mods, {'env_num': n, '_seed': 6, 'num_steps': 30})
+    g.reset(); o.reset()
+    rng = np.random.default_rng(3)
+    for rep in range(3):
+        s = o.get_state()
+        k = np.arange(0, n, 7)
+        vals = np.array([np.nan, np.inf, -np.inf, 1e20, -3e16, 2e15, 1e14, -1e30], np.float32)
+        col = rng.choice([0, 1, 2, 3, 5, 11, 12, 13, 14, 20, 27], len(k))       # qx qy qth vx vw goal_x goal_y hazard coords
+        s[k, col] = vals[rng.integers(0, len(vals), len(k))]
+        s[k[::3], 10] = 40.0                                                     # and some step counters beyond num_steps
+        g.set_state(torch.from_numpy(s).cuda()); o.set_state(s)
+        for t in range(3):
+            a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+            og, rg, dg, ig = g.step_autoreset(torch.from_numpy(a).cuda())
+            oo, ro, do, io = o.step(a)
+            oo = o.reset_done()
+            bits_equal(cpu(og), oo, f"obs {rep}/{t}"); bits_equal(cpu(rg), ro, "reward"); bits_equal(cpu(dg), do, "done")
+            bits_equal(cpu(ig['cost']), io['cost'], "cost")
+        bits_equal(cpu(g.get_state()), o.get_state(), "state")
+        assert do.sum() >= 0
+
+
 def test_state_injection_roundtrip_and_one_step_parity(mods):
     n = 500
     g, o = make_pair(mods, {'env_num': n, '_seed': 4})
