@@ -211,6 +211,35 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
       for (int k = 0; k < K; ++k) { st.ql[j][k] = 0.0f; st.vl[j][k] = 0.0f; }
   };
 
+  // joint state -> HBM.  The state is stepped IN PLACE and stored as soon as it is final (after the step proper; after the
+  // re-placement for a throw-away step, whose warm start stays the stale one), so no second copy of it is live across
+  // the solver -- 15 registers less for the ant in every build.
+  auto store_state = [&](bool with_w) {
+    if (!live) return;
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const size_t d = (size_t)(m.root_qadr + r);
+        a.aq[d * cap + i] = st.qr[r];
+        a.aq[(nv + d) * cap + i] = st.vr[r];
+        if (with_w) a.aq[(2 * nv + d) * cap + i] = st.wr[r];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < LPL; ++j) {
+      const int leg = j * LANES + lane;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (k < m.leg[leg].nk) {
+          const size_t d = (size_t)(m.leg_qadr[leg] + k);
+          a.aq[d * cap + i] = st.ql[j][k];
+          a.aq[(nv + d) * cap + i] = st.vl[j][k];
+          if (with_w) a.aq[(2 * nv + d) * cap + i] = st.wl[j][k];
+        }
+      }
+    }
+  };
+
   if (MODE == GX_ART_RESET) {
     // Engine.reset (engine.py:454-467): mjx_reset starts from the pristine mjx_data
     // (qacc_warmstart 0), runs mjx.forward, observes; steps <- 0; done/key stay stale.
@@ -223,6 +252,7 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
 #pragma unroll
       for (int k = 0; k < K; ++k) st.wl[j][k] = 0.0f;
     gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, st, nullptr, nullptr, false, true, false, sn, qro, vro, qlo, vlo, nullptr);
+    store_state(true);
     GxArtObs o = gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row, nullptr);
     prev_dist = o.dist_goal;
     steps = 0.0f;
@@ -238,11 +268,9 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
     // prev_dist, steps and the done flag.
     const float* lay = gx_pick_layout(p, pool, layout, i, age, GX_STREAM_PICK);
     place(lay);
-    {
-      GxArtLane<LANES, NLEG, K, NB> tmp = st;   // scratch copy: the state itself stays un-stepped
-      for (int k = 0; k < p.substeps; ++k)
-        gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, tmp, nullptr, nullptr, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
-    }
+    store_state(false);   // the un-stepped pose is the state; the step below is for the observation only
+    for (int k = 0; k < p.substeps; ++k)
+      gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, st, nullptr, nullptr, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
     gx_art_obs_row<LANES, NLEG, K, NB>(p, s, m, i, lane, mask, lay, goal.x, goal.y, sn, cr, cl, qro, vro, qlo, vlo, row, nullptr);
   } else {
     // Engine.step (engine.py:469-495) + mjx_step (:659-700)
@@ -284,11 +312,11 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
 #pragma unroll
           for (int k = 0; k < K; ++k) cl[j][k] = 0.0f;
       }
-      GxArtLane<LANES, NLEG, K, NB> wk = st;   // pass 1 works on a scratch copy: the state stays un-stepped
+      if (pass == 1) store_state(false);   // re-placed, un-stepped pose; the warm start stays pass 0's (engine.py:719-731)
       for (int k = 0; k < p.substeps; ++k)
-        gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, wk, cr, cl, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
+        gx_art_step<LANES, NLEG, K, NB>(m, lane, mask, st, cr, cl, true, false, false, sn, qro, vro, qlo, vlo, nullptr);
       if (pass == 0) {
-        st = wk;
+        store_state(true);
         if (qacc_out && live) {   // info['obs']['qacc'] (engine.py:763-764): the solver's qacc of the last forward
           if (lane == 0)
 #pragma unroll
@@ -331,32 +359,10 @@ __global__ void __launch_bounds__(128, MINB) gx_art_kernel(const __grid_constant
   }
 
   // ---- write back
-  if (live) {
-    if (lane == 0) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const size_t d = (size_t)(m.root_qadr + r);
-        a.aq[d * cap + i] = st.qr[r];
-        a.aq[(nv + d) * cap + i] = st.vr[r];
-        a.aq[(2 * nv + d) * cap + i] = st.wr[r];
-      }
-      s.d2[i] = make_float4(prev_dist, was_done > 0.0f ? -steps : steps, __uint_as_float((uint32_t)age),
-                            __uint_as_float((uint32_t)(age >> 32)));
-      if (MODE == GX_ART_STEP) { reward[i] = o_reward; done[i] = o_done; cost[i] = o_cost; }
-    }
-#pragma unroll
-    for (int j = 0; j < LPL; ++j) {
-      const int leg = j * LANES + lane;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if (k < m.leg[leg].nk) {
-          const size_t d = (size_t)(m.leg_qadr[leg] + k);
-          a.aq[d * cap + i] = st.ql[j][k];
-          a.aq[(nv + d) * cap + i] = st.vl[j][k];
-          a.aq[(2 * nv + d) * cap + i] = st.wl[j][k];
-        }
-      }
-    }
+  if (live && lane == 0) {
+    s.d2[i] = make_float4(prev_dist, was_done > 0.0f ? -steps : steps, __uint_as_float((uint32_t)age),
+                          __uint_as_float((uint32_t)(age >> 32)));
+    if (MODE == GX_ART_STEP) { reward[i] = o_reward; done[i] = o_done; cost[i] = o_cost; }
   }
   if (MODE == GX_ART_RESET_DONE) {
     // only the done envs' rows are (over)written
