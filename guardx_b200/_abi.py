@@ -136,6 +136,8 @@ PROTOTYPES = {
     "gx_rollout_host_route": (_I, [_P, _P]),
     "gx_policy_weight_floats": (C.c_int64, [_P]),
     "gx_policy_step": (_I, [_P, _P, _P, C.c_uint64, _P, _P, _P, _P, _P, _P]),
+    "gx_policy_rollout_supported": (_I, [_P]),
+    "gx_policy_rollout": (_I, [_P, _P, C.c_int32, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

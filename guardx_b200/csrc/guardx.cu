@@ -1486,6 +1486,7 @@ GX_API int gx_policy_step(gx_env* e, const float* weights, const float* obs, uin
   if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_policy_step: call gx_reset first");
   const int A = gx_act_dim(e);
   if (A > GX_POL_MAX_ACT) return gx_fail(GX_EINVAL, "gx_policy_step: act_dim %d > %d", A, GX_POL_MAX_ACT);
+  if (reinterpret_cast<uintptr_t>(weights) & 15u) return gx_fail(GX_EINVAL, "gx_policy_step: weights must be 16-byte aligned (bulk-async copies)");
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   switch ((e->p.obs_dim + 3) & ~3) {   // Point 43, Swimmer 46, Ant 64, Walker 70, Doggo 85 (+ 2 / 4 with observe_vel / observe_acc)
@@ -1495,6 +1496,47 @@ GX_API int gx_policy_step(gx_env* e, const float* weights, const float* obs, uin
 #undef GX_POL_CASE
     default: return gx_fail(GX_EINVAL, "gx_policy_step: no kernel instantiated for obs_dim %d", e->p.obs_dim);
   }
+}
+
+// ---- a whole PPO rollout as one persistent launch (gx_policy.cuh: gx_policy_rollout_kernel) ----------------------------
+static bool lanes_shape(const gx_env* e) {
+  const gx_params& p = e->p;
+  return !e->art_host && !e->tree_host && p.nh == 8 && p.nb == 16 && p.obs_dim == 43 && p.alias && p.use_exp && p.ctrllimited &&
+         p.forcelimited && p.substeps == 1 && p.off_ctrl == 0 && p.off_compass == 3 && p.off_glidar == 5 && p.off_hlidar == 21 &&
+         p.off_qpos == 37 && p.off_qvel == 40;
+}
+
+GX_API int gx_policy_rollout_supported(const gx_env* e) { return e && lanes_shape(e) && gx_act_dim(e) == 2 ? 1 : 0; }
+
+GX_API int gx_policy_rollout(gx_env* e, const float* weights, int32_t T, uint64_t noise_seed, float* obs, float* act, float* reward,
+                             float* done, float* cost, float* val, float* cval, float* logp, void* stream) {
+  if (!e || !weights || !obs || !act || !reward || !done || !cost || !val || !cval || !logp)
+    return gx_fail(GX_EINVAL, "gx_policy_rollout: NULL argument");
+  if (!e->have_reset) return gx_fail(GX_ESTATE, "gx_policy_rollout: call gx_reset first");
+  if (T < 0) return gx_fail(GX_EINVAL, "gx_policy_rollout: T = %d", T);
+  if (!gx_policy_rollout_supported(e))
+    return gx_fail(GX_EINVAL, "gx_policy_rollout: built for the default Point shape (obs 43, act 2); use gx_policy_step + gx_step_autoreset");
+  if (reinterpret_cast<uintptr_t>(weights) & 15u) return gx_fail(GX_EINVAL, "gx_policy_rollout: weights must be 16-byte aligned (bulk-async copies)");
+  if (reinterpret_cast<uintptr_t>(act) & 7u) return gx_fail(GX_EINVAL, "gx_policy_rollout: act must be 8-byte aligned");
+  if (T == 0) return GX_OK;
+  DeviceGuard guard(e->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t sh = gx_policy_rollout_smem_floats() * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GX_CUDA(cudaFuncSetAttribute(gx_policy_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    GX_CUDA(cudaFuncSetAttribute(gx_policy_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    attr_set = true;
+  }
+  const int grid = div_up(e->p.n, GX_PR_ENVS);
+  float2* a2 = reinterpret_cast<float2*>(act);
+  const unsigned k0 = (uint32_t)noise_seed, k1 = (uint32_t)(noise_seed >> 32);
+  if (e->stats_on)
+    gx_policy_rollout_kernel<true><<<grid, GX_PR_THREADS, sh, st>>>(e->p, e->s, e->pool, weights, T, k0, k1, obs, a2, reward, done, cost, val, cval, logp);
+  else
+    gx_policy_rollout_kernel<false><<<grid, GX_PR_THREADS, sh, st>>>(e->p, e->s, e->pool, weights, T, k0, k1, obs, a2, reward, done, cost, val, cval, logp);
+  GX_LAUNCH_CHECK("gx_policy_rollout_kernel");
+  return GX_OK;
 }
 
 // ---- diagnostics -------------------------------------------------------------

@@ -264,8 +264,10 @@ __device__ __noinline__ void gx_step_then_reset_lanes(const gx_params& p, const 
 
 __device__ __forceinline__ GxLaneStep gx_step_autoreset_lanes(const gx_params& p, const GxState& s, int i, int sub, unsigned gmask,
                                                               bool live, const float* lay, const GxSpecLayout& sp, GxDyn& d,
-                                                              float gx_, float gy_, float ox, float oy, float a0, float a1,
+                                                              float& gx_, float& gy_, float& ox, float& oy, float a0, float a1,
                                                               float* qacc) {
+  // (goal and object by reference: a finishing env leaves with its NEW goal / object, which the multi-step callers keep in
+  // registers; the single-step kernel ignores them)
   GxLaneStep r;
   // exotic state: the whole env (16 lanes agree: pose is replicated, objects are checked by ballot) leaves the fast path
   const bool obj_ok = (gx_abs(ox) < GX_SANE_BOUND) & (gx_abs(oy) < GX_SANE_BOUND);
@@ -277,6 +279,7 @@ __device__ __forceinline__ GxLaneStep gx_step_autoreset_lanes(const gx_params& p
     float g0 = gx_, g1 = gy_, o0 = ox, o1 = oy;
     gx_step_then_reset_lanes(p, s, i, sub, gmask, live, lay, dd, g0, g1, o0, o1, a0, a1, qacc, r);
     d = dd;
+    gx_ = g0; gy_ = g1; ox = o0; oy = o1;
     return r;
   }
   r.c0 = d.hc * a0; r.c1 = d.hs * a0; r.c2 = a1;

@@ -1,30 +1,46 @@
-// gx_policy.cuh -- the policy half of a PPO / PPO-Lagrangian rollout step in ONE kernel.
+// gx_policy.cuh -- the policy half of a PPO / PPO-Lagrangian rollout step in ONE kernel (gx_policy_kernel), and a whole
+// rollout -- T x { policy, env step } -- in ONE persistent launch (gx_policy_rollout_kernel).
 //
 // The reference's rollout step (safe_rl_libX/ppo/ppo_train.py:364-379, ppo_core.py:116-160) is
 //   a, v, logp = ac.step(o)      three fp32 tanh MLPs obs -> 64 -> 64 -> {act_dim | 1 | 1} (actor mean, value critic,
 //                                cost critic: TRPO-Lag's vc), a state-independent log-std, a Gaussian sample and its
 //                                log-probability  -- ~30 small torch / cuBLAS kernels per step
 //   buf.store(o, a, r, v, logp)  five more copies
-// followed by env.step.  Here the whole `ac.step` + the buffer writes are one launch that reads the observation row
-// the env kernel wrote (directly in the rollout buffer) and writes act / val / cval / logp into the rollout buffer's
-// rows; the env kernel that follows reads `act` from there.  A rollout step is two launches.
+// followed by env.step.  gx_policy_kernel is the whole `ac.step` + the buffer writes as one launch that reads the
+// observation row the env kernel wrote (directly in the rollout buffer) and writes act / val / cval / logp into the
+// rollout buffer's rows; the env kernel that follows reads `act` from there.
 //
 // fp32 FFMA only (the reference policy is fp32; the largest contraction is a [32 x 64] x [64 x 64] tile per net: a
-// tensor-core path would need tf32 / bf16 operands, i.e. other numbers than the reference's).  Work split: one block
-// per 32 envs, 384 threads = 192 hidden units (3 nets x 64) x 2 halves of 16 envs.  A thread keeps ITS unit's weight
-// column in registers (obs_dim, then 64 values) and walks its 16 envs in two groups of 8 independent accumulators;
-// the activations of the 32 envs live in shared memory and are read as warp-wide broadcasts (all lanes of a warp
-// belong to the same net and read the same activation vector), so the inner loop is 1 LDS.128 + 2 FFMA2 (packed
-// fp32 pairs, fma.rn.f32x2) per env per four inputs.
+// tensor-core path would need tf32 / bf16 operands, i.e. other numbers than the reference's).
+//
+// What bounds a tiny fp32 MLP on an SM, measured (ncu, profiles/):
+//  * the shared-memory return path: the LSU delivers ONE warp-wide 4-byte operand per clock (128 B / clk / SM; an
+//    LDS.128 is 4 wavefronts, broadcast or not) while the four schedulers can retire four warp-wide FMAs.  The first
+//    version kept a unit's weight column in registers and read every activation once per FMA pair -- 4 B per FMA,
+//    18 k LSU cycles per 32-env block, which WAS its 9-10 us.  Hence register tiles: a thread owns an 8 unit x 4 env
+//    tile (32 accumulator pairs) and per four inputs loads 8 weight quads + 4 activation quads (12 LDS.128) for
+//    128 FMAs = 1.5 B per FMA;
+//    Six warps per 32 envs: warp = (net, half of the block's envs).  Measured alternatives: an 8 x 8 tile on three warps
+//    (1 B per FMA, 232 registers) is slower (one warp per scheduler cannot hide the LDS returns); splitting the reduction
+//    over warp PAIRS that exchange partial sums through shared memory (12 warps) is a wash (the exchange + second
+//    barrier cost what the shorter streams save).  At 12 LDS.128 per 64 FFMA2 the LSU is ~55 % and the FMA pipe ~50 %
+//    busy during the layers and the two do not overlap better without registers to prefetch into: FFMA2 issues once
+//    per 2.2 cycles per scheduler at this occupancy (tools/micro/ffma2.cu), i.e. at the scalar FMA rate;
+//  * and the activations: one tanh per 54 FMAs is as many instructions as the matrix products unless it is five
+//    instructions (gx_tanh_fast).
+// Lane mapping inside a warp tile: lane = 8 unit groups x 4 env groups; unit u = i * 8 + ug, env e = i * 4 + eg, so a
+// quarter-warp reads 128 contiguous bytes of weights and ONE broadcast activation quad: no bank conflicts.
+// The weights arrive as bulk-async copies (cp.async.bulk global -> shared, the non-tensor TMA path) on an mbarrier.
 //
 // Packed weights (device floats, written by guardx_b200/ppo_lag.py:pack_policy; K1 = obs_dim rounded up to 4):
-//   W1 [K1][192]   W1[k][net*64+u] = layer-0 weight of unit u of net `net` for input k (rows k >= obs_dim are 0)
-//   B1 [192]
-//   W2 [3][64][64] W2[net][k][u]
-//   B2 [192]
-//   W3 [A+2][64]   rows 0..A-1: actor mean head (net 0), row A: value head (net 1), row A+1: cost-value head (net 2)
+//   W1 [3][K1 / 4][64][4]  W1[net][k / 4][u][k & 3] = layer-0 weight of unit u of net `net` for input k (inputs k >= obs_dim
+//                          are 0): the layout the kernel keeps in shared memory, a thread's four weights are one LDS.128
+//   W2 [3][16][64][4]      W2[net][k / 4][u][k & 3]
+//   B1 [3][64]
+//   B2 [3][64]
+//   W3 [A+2][64]           rows 0..A-1: actor mean head (net 0), row A: value head (net 1), row A+1: cost-value head (net 2)
 //   B3 [A+2]
-//   LS [A]         log_std
+//   LS [A]                 log_std
 // nets: 0 = actor mean (mu_net), 1 = value critic (v), 2 = cost critic (vc).
 //
 // Exploration noise: a = mu + exp(log_std) * z, z ~ N(0,1) by Box-Muller on Philox4x32-10 keyed by
@@ -36,12 +52,16 @@
 #define GX_POLICY_CUH_
 
 #include "gx_device.cuh"
+#include "gx_lanes.cuh"
 
 #define GX_POL_HID 64
 #define GX_POL_UNITS 192   // 3 nets x 64
 #define GX_POL_ENVS 32     // envs per block
-#define GX_POL_THREADS 384
-#define GX_POL_GROUPS (GX_POL_ENVS * GX_POL_UNITS / GX_POL_THREADS / 8)   // groups of 8 envs per thread
+#define GX_POL_E 4         // envs per thread tile; a warp tile is 16 envs x 64 units
+#define GX_POL_EPW (4 * GX_POL_E)
+#define GX_POL_WARPS 6     // (net, half of the block's envs)
+#define GX_POL_THREADS (32 * GX_POL_WARPS)
+#define GX_POL_HS 72       // row stride of the hidden activations in shared memory (conflict-free tile stores)
 #define GX_POL_MAX_ACT 16
 #define GX_STREAM_POLICY 0x504f4c49u /* exploration noise */
 
@@ -51,9 +71,12 @@ __host__ __device__ inline size_t gx_policy_weight_count(int obs_dim, int act_di
          (size_t)(act_dim + 2) * GX_POL_HID + (act_dim + 2) + act_dim;
 }
 
+// shared memory: xs [32][K1] | h1 [3][32][HS] | h2 [3][32][HS] | w1s [3][K1/4][64][4] | w2s [3][16][64][4] |
+//                tail = B1 | B2 | W3 | B3 | LS (as packed) | mbarrier
+__host__ __device__ inline size_t gx_policy_tail_floats(int A) { return 2 * GX_POL_UNITS + (size_t)(A + 2) * (GX_POL_HID + 1) + A; }
 __host__ __device__ inline size_t gx_policy_smem_floats(int k1) {
-  return (size_t)GX_POL_ENVS * k1 + 2 * (size_t)GX_POL_ENVS * GX_POL_UNITS + 2 * (size_t)GX_POL_ENVS * (GX_POL_MAX_ACT + 2) +
-         3 * (size_t)GX_POL_HID * GX_POL_HID + GX_POL_UNITS + (size_t)(GX_POL_MAX_ACT + 2) * (GX_POL_HID + 1) + GX_POL_MAX_ACT + 8;
+  return (size_t)GX_POL_ENVS * k1 + 2 * 3 * (size_t)GX_POL_ENVS * GX_POL_HS + (size_t)k1 * GX_POL_UNITS + 3 * (size_t)GX_POL_HID * GX_POL_HID +
+         ((gx_policy_tail_floats(GX_POL_MAX_ACT) + 3) & ~(size_t)3) + 8;
 }
 
 // packed fp32 pair arithmetic (Blackwell FFMA2): d = a * b + c on both halves, round to nearest, one issue slot
@@ -73,41 +96,77 @@ __device__ __forceinline__ float gx_sum2(unsigned long long v) {
   return lo + hi;
 }
 
-// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU (ex2 + rcp): absolute error ~2e-7, which is what the 1e-5 bound on the heads
-// needs (libdevice's tanhf is ~55 instructions, 17 % of the kernel); exact limits at +-inf, NaN propagates
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the SFU, five instructions (FMUL, MUFU.EX2, FADD, MUFU.RCP, FFMA): absolute error
+// ~2e-7, which is what the 1e-5 bound on the heads needs.  The activations are as many instructions as the matrix
+// products here (one tanh per 54 FMAs): libdevice's tanhf is ~55 instructions, __expf + __fdividef with their range
+// handling 28 (45 % of this kernel's executed instructions, ncu).  Exact limits: exp2 -> inf gives rcp 0 -> 1,
+// exp2 -> 0 gives 1 - 2 = -1; NaN propagates.
 __device__ __forceinline__ float gx_tanh_fast(float x) {
-  const float t = __expf(2.0f * x);
-  return 1.0f - __fdividef(2.0f, t + 1.0f);
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 2.88539008177792681f));   // exp(2x) = 2^(2x log2 e)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t + 1.0f));
+  return __fmaf_rn(-2.0f, r, 1.0f);
 }
 
-// one layer for this thread's unit: 16 envs in two groups of 8 accumulator PAIRS (even-k and odd-k partial sums of one
-// env share a 64-bit register: the weights w[2m], w[2m+1] and the activations x[2m], x[2m+1] are adjacent already, so the
-// inner loop is 1 LDS.128 + 2 FFMA2 per env per four inputs); `in` rows have `stride` floats, the unit's inputs start at
-// `in + off`; K is a multiple of 4
+// One layer of one net for a warp's 16 env x 64 unit tile; this thread: 8 units x 4 envs.  Accumulator PAIRS: the
+// even-k and the odd-k partial sum of one (env, unit) share a 64-bit register -- the weights w[2m], w[2m+1] and the
+// activations x[2m], x[2m+1] are adjacent in shared memory already, so a quad of inputs is 2 FFMA2 per (env, unit) with
+// no packing work.  ws: this net's weights [K / 4][64][4]; bs: its biases [64]; `in` rows have `stride` floats; out rows
+// GX_POL_HS.  K is a multiple of 4.  The tile is produced and consumed by this warp alone: callers separate the layers
+// with __syncwarp.
 template <int K>
-__device__ __forceinline__ void gx_policy_layer(const float (&w)[K], float bias, const float* in, int stride, int off, int env0,
-                                                float* out, int j) {
-  unsigned long long w2[K / 2];
+__device__ __forceinline__ void gx_policy_layer(const float* ws, const float* bs, const float* in, int stride, float* out, int lane) {
+  constexpr int E = GX_POL_E;
+  const int eg = lane >> 3, ug = lane & 7;
+  unsigned long long acc[E][8];
 #pragma unroll
-  for (int m = 0; m < K / 2; ++m) w2[m] = gx_pack2(w[2 * m], w[2 * m + 1]);
-#pragma unroll 1
-  for (int grp = 0; grp < GX_POL_GROUPS; ++grp) {
-    unsigned long long acc[8];
+  for (int i = 0; i < 8; ++i) {
+    const float b = bs[i * 8 + ug];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = gx_pack2(bias, 0.0f);
-    const float* base = in + (size_t)(env0 + grp * 8) * stride + off;
-#pragma unroll
-    for (int k4 = 0; k4 < K / 4; ++k4) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const ulonglong2 x = *reinterpret_cast<const ulonglong2*>(base + e * stride + 4 * k4);
-        acc[e] = gx_fma2(w2[2 * k4], x.x, acc[e]);
-        acc[e] = gx_fma2(w2[2 * k4 + 1], x.y, acc[e]);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) out[(size_t)(env0 + grp * 8 + e) * GX_POL_UNITS + j] = gx_tanh_fast(gx_sum2(acc[e]));
+    for (int e = 0; e < E; ++e) acc[e][i] = gx_pack2(b, 0.0f);
   }
+  const float* wp = ws + ug * 4;
+  const float* xp = in + (size_t)eg * stride;
+#pragma unroll 2
+  for (int k4 = 0; k4 < K / 4; ++k4) {
+    ulonglong2 x[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = *reinterpret_cast<const ulonglong2*>(xp + (e * 4) * stride + 4 * k4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wp + (k4 * GX_POL_HID + i * 8) * 4);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e][i] = gx_fma2(w.x, x[e].x, acc[e][i]);
+#pragma unroll
+      for (int e = 0; e < E; ++e) acc[e][i] = gx_fma2(w.y, x[e].y, acc[e][i]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[(size_t)(e * 4 + eg) * GX_POL_HS + i * 8 + ug] = gx_tanh_fast(gx_sum2(acc[e][i]));
+}
+
+// mbarrier + bulk-async copy (global -> shared), the non-tensor TMA path
+__device__ __forceinline__ unsigned gx_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gx_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gx_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gx_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gx_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gx_bulk_g2s(float* smem_dst, const float* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gx_smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(gx_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void gx_mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(gx_smem_u32(bar)), "r"(parity)
+                 : "memory");
 }
 
 __device__ __forceinline__ void gx_cp_async4(float* smem_dst, const float* gsrc) {
@@ -130,123 +189,288 @@ __device__ __forceinline__ float gx_policy_noise(unsigned long long gid, unsigne
   return rad * ((a & 1) ? sn : cs);
 }
 
-// Phases, each ended by one barrier; everything a later phase needs from global memory is requested at the very top
-// (cp.async into shared memory, or into registers), so no phase but the first waits for L2 / HBM:
-//   0  cp.async: observation tile, W2, W3 | B3 | log_std;  registers: first-layer column, the (env, action) noise draws
-//   1  layer 1 -> h1        2  layer 2 (column from shared memory) -> h2        3  heads -> head
-//   4  sample, per-dimension log-prob terms, act / mu stores        5  per-env logp / val / cval stores
+// 64-long head dot product of output o for the hidden row hv (two interleaved accumulators)
+__device__ __forceinline__ float gx_policy_head(const float* W3, const float* B3, const float4* hv, int o) {
+  const float* wv = W3 + o * GX_POL_HID;
+  float acc0 = B3[o], acc1 = 0.0f;
+#pragma unroll
+  for (int k4 = 0; k4 < GX_POL_HID / 4; ++k4) {
+    const float4 x = hv[k4];
+    acc0 = __fmaf_rn(wv[4 * k4 + 0], x.x, acc0); acc1 = __fmaf_rn(wv[4 * k4 + 1], x.y, acc1);
+    acc0 = __fmaf_rn(wv[4 * k4 + 2], x.z, acc0); acc1 = __fmaf_rn(wv[4 * k4 + 3], x.w, acc1);
+  }
+  return acc0 + acc1;
+}
+
+// Phases:
+//   0  thread 0: two bulk copies (W1, W2 blocks) onto the mbarrier; all threads: cp.async of the observation tile and the
+//      small tail (biases, head rows, log_std); the lanes that will sample draw the exploration noise of the first action
+//      block while the loads fly; ONE block barrier (tile + tail visible), then the weights' mbarrier
+//   1  layer 1 -> h1        2  layer 2 -> h2   (per warp, __syncwarp between)
+//   3  lane = env (16 per warp): head dot products; the actor warps sample, write act / mu / logp; the critic warps write
+//      val / cval
 template <int K1>
 __global__ void __launch_bounds__(GX_POL_THREADS, 1)
 gx_policy_kernel(const float* __restrict__ W, const float* __restrict__ obs, int n, int obs_dim, int A, const float4* __restrict__ d2,
                  unsigned long long env_id_offset, unsigned k0, unsigned k1, float* __restrict__ act, float* __restrict__ val,
                  float* __restrict__ cval, float* __restrict__ logp, float* __restrict__ mu_out) {
   extern __shared__ __align__(16) float gx_pol_smem[];
-  float* xs = gx_pol_smem;                                   // [32][K1]   observations
-  float* h1 = xs + GX_POL_ENVS * K1;                         // [32][192]  first hidden layer, all three nets
-  float* h2 = h1 + GX_POL_ENVS * GX_POL_UNITS;               // [32][192]
-  float* head = h2 + GX_POL_ENVS * GX_POL_UNITS;             // [32][A+2]  mu | v | vc
-  float* lp = head + GX_POL_ENVS * (GX_POL_MAX_ACT + 2);     // [32][A]    per-dimension log-prob terms
-  float* w2s = lp + GX_POL_ENVS * (GX_POL_MAX_ACT + 2);      // [3][64][64] second-layer weights
-  float* w3s = w2s + 3 * GX_POL_HID * GX_POL_HID;            // B2 [192] | W3 [A+2][64] | B3 [A+2] | LS [A]
-  const int tid = threadIdx.x, j = tid % GX_POL_UNITS, half = tid / GX_POL_UNITS;
-  const int e_blk = blockIdx.x * GX_POL_ENVS;
+  float* xs = gx_pol_smem;                                   // [32][K1]      observations
+  float* h1 = xs + GX_POL_ENVS * K1;                         // [3][32][HS]   first hidden layer
+  float* h2 = h1 + 3 * GX_POL_ENVS * GX_POL_HS;              // [3][32][HS]
+  float* w1s = h2 + 3 * GX_POL_ENVS * GX_POL_HS;             // [3][K1 / 4][64][4]
+  float* w2s = w1s + K1 * GX_POL_UNITS;                      // [3][16][64][4]
+  float* tl = w2s + 3 * GX_POL_HID * GX_POL_HID;             // B1 [192] | B2 [192] | W3 [A+2][64] | B3 [A+2] | LS [A]
   const int OUT = A + 2;
+  const int tail = (int)gx_policy_tail_floats(A);
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(tl + ((gx_policy_tail_floats(GX_POL_MAX_ACT) + 3) & ~(size_t)3));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int net = warp >> 1, half = warp & 1;   // this warp: net `net`, envs [half * 16, half * 16 + 16) of the block
+  const int e_blk = blockIdx.x * GX_POL_ENVS;
   const float* W1 = W;
-  const float* B1 = W1 + (size_t)K1 * GX_POL_UNITS;
-  const float* W2 = B1 + GX_POL_UNITS;
-  const float* B2 = W2 + 3 * GX_POL_HID * GX_POL_HID;
-  const int tail = GX_POL_UNITS + OUT * GX_POL_HID + OUT + A;   // floats from B2 to the end of the pack
+  const float* W2 = W1 + (size_t)K1 * GX_POL_UNITS;
+  const float* TL = W2 + 3 * GX_POL_HID * GX_POL_HID;
   // ---- phase 0 --------------------------------------------------------------------------------------------------
+  if (tid == 0) {
+    gx_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    constexpr unsigned b1 = K1 * GX_POL_UNITS * sizeof(float), b2 = 3 * GX_POL_HID * GX_POL_HID * sizeof(float);
+    gx_mbar_expect_tx(bar, b1 + b2);
+    gx_bulk_g2s(w1s, W1, b1, bar);
+    gx_bulk_g2s(w2s, W2, b2, bar);
+  }
   for (int idx = tid; idx < GX_POL_ENVS * K1; idx += GX_POL_THREADS) {
     const int e = idx / K1, k = idx - e * K1, g = e_blk + e;
     if (g < n && k < obs_dim) gx_cp_async4(xs + idx, obs + (size_t)g * obs_dim + k);
     else xs[idx] = 0.0f;
   }
-  for (int c = tid; c < 3 * GX_POL_HID * GX_POL_HID / 4; c += GX_POL_THREADS) gx_cp_async16(w2s + 4 * c, W2 + 4 * c);
-  if ((((size_t)(B2 - W)) & 3) == 0) {
-    for (int c = tid; c < tail / 4; c += GX_POL_THREADS) gx_cp_async16(w3s + 4 * c, B2 + 4 * c);
-    for (int c = (tail & ~3) + tid; c < tail; c += GX_POL_THREADS) gx_cp_async4(w3s + c, B2 + c);
-  } else {
-    for (int c = tid; c < tail; c += GX_POL_THREADS) gx_cp_async4(w3s + c, B2 + c);
-  }
+  for (int c = tid; c < tail / 4; c += GX_POL_THREADS) gx_cp_async16(tl + 4 * c, TL + 4 * c);   // TL is 16-byte aligned: every block before it is a multiple of 4 floats
+  for (int c = (tail & ~3) + tid; c < tail; c += GX_POL_THREADS) gx_cp_async4(tl + c, TL + c);
   asm volatile("cp.async.commit_group;" ::: "memory");
-  float w1[K1];
+  // exploration noise of this lane's env, first block of four action dimensions: independent of the networks, so it is
+  // drawn while the loads fly (further blocks, act_dim > 4, are drawn in the sampling loop)
+  const bool mine = lane < GX_POL_EPW;                 // phase 3: lane = env of this warp's slice
+  const int le = half * GX_POL_EPW + (mine ? lane : 0);
+  const int g = e_blk + le;
+  unsigned age_lo = 0, age_hi = 0;
+  float z0[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (net == 0 && mine && g < n) {
+    const float4 c = d2[g];
+    age_lo = __float_as_uint(c.z); age_hi = __float_as_uint(c.w);
 #pragma unroll
-  for (int k = 0; k < K1; ++k) w1[k] = W1[(size_t)k * GX_POL_UNITS + j];
-  const float b1 = B1[j];
-  // exploration noise of this thread's (env, action) pairs: independent of the networks, so it is drawn while the loads fly
-  float z[2] = {0.0f, 0.0f};
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int idx = tid + q * GX_POL_THREADS;
-    if (idx < GX_POL_ENVS * A) {
-      const int e = idx / A, a = idx - e * A, g = e_blk + e;
-      if (g < n) {
-        const float4 c = d2[g];
-        z[q] = gx_policy_noise(env_id_offset + (unsigned long long)g, __float_as_uint(c.z), __float_as_uint(c.w), a, k0, k1);
-      }
-    }
+    for (int a = 0; a < 4; ++a)
+      if (a < A) z0[a] = gx_policy_noise(env_id_offset + (unsigned long long)g, age_lo, age_hi, a, k0, k1);
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // ---- phase 1, 2 -----------------------------------------------------------------------------------------------
-  gx_policy_layer<K1>(w1, b1, xs, K1, 0, half * 8 * GX_POL_GROUPS, h1, j);
-  const int net = j / GX_POL_HID, u = j - net * GX_POL_HID;
-  float w2[GX_POL_HID];
-#pragma unroll
-  for (int k = 0; k < GX_POL_HID; ++k) w2[k] = w2s[(net * GX_POL_HID + k) * GX_POL_HID + u];
-  const float b2 = w3s[j];
-  __syncthreads();
-  gx_policy_layer<GX_POL_HID>(w2, b2, h1, GX_POL_UNITS, net * GX_POL_HID, half * 8 * GX_POL_GROUPS, h2, j);
-  __syncthreads();
-  // ---- phase 3: heads, one 64-long dot product per (env, output) ---------------------------------------------------
-  const float* W3 = w3s + GX_POL_UNITS;
+  gx_mbar_wait(bar, 0);
+  // ---- phase 1, 2: this warp's net and envs ------------------------------------------------------------------------
+  float* h1n = h1 + ((size_t)net * GX_POL_ENVS + half * GX_POL_EPW) * GX_POL_HS;
+  float* h2n = h2 + ((size_t)net * GX_POL_ENVS + half * GX_POL_EPW) * GX_POL_HS;
+  gx_policy_layer<K1>(w1s + (size_t)net * K1 * GX_POL_HID, tl + net * GX_POL_HID, xs + (size_t)half * GX_POL_EPW * K1, K1, h1n, lane);
+  __syncwarp();
+  gx_policy_layer<GX_POL_HID>(w2s + (size_t)net * GX_POL_HID * GX_POL_HID, tl + GX_POL_UNITS + net * GX_POL_HID, h1n, GX_POL_HS, h2n, lane);
+  __syncwarp();
+  // ---- phase 3: lane = env; one 64-long dot product per output ---------------------------------------------------------
+  if (!mine) return;
+  const float* W3 = tl + 2 * GX_POL_UNITS;
   const float* B3 = W3 + OUT * GX_POL_HID;
   const float* LS = B3 + OUT;
-  for (int idx = tid; idx < GX_POL_ENVS * OUT; idx += GX_POL_THREADS) {
-    const int e = idx / OUT, o = idx - e * OUT;
-    const int hn = o < A ? 0 : o - A + 1;
-    const float4* hv = reinterpret_cast<const float4*>(h2 + (size_t)e * GX_POL_UNITS + hn * GX_POL_HID);
-    const float* wv = W3 + o * GX_POL_HID;
-    float acc0 = B3[o], acc1 = 0.0f;
-#pragma unroll
-    for (int k4 = 0; k4 < GX_POL_HID / 4; ++k4) {
-      const float4 x = hv[k4];
-      acc0 = __fmaf_rn(wv[4 * k4 + 0], x.x, acc0); acc1 = __fmaf_rn(wv[4 * k4 + 1], x.y, acc1);
-      acc0 = __fmaf_rn(wv[4 * k4 + 2], x.z, acc0); acc1 = __fmaf_rn(wv[4 * k4 + 3], x.w, acc1);
-    }
-    head[e * (GX_POL_MAX_ACT + 2) + o] = acc0 + acc1;
+  const float4* hv = reinterpret_cast<const float4*>(h2n + (size_t)lane * GX_POL_HS);
+  if (net != 0) {
+    const float v = gx_policy_head(W3, B3, hv, A + net - 1);
+    if (g < n) (net == 1 ? val : cval)[g] = v;
+    return;
   }
-  __syncthreads();
-  // ---- phase 4: Gaussian sample per (env, action dimension) -------------------------------------------------------
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const int idx = tid + q * GX_POL_THREADS;
-    if (idx < GX_POL_ENVS * A) {
-      const int e = idx / A, a = idx - e * A, g = e_blk + e;
-      if (g < n) {
-        const float mu = head[e * (GX_POL_MAX_ACT + 2) + a];
-        const float ls = LS[a], sd = expf(ls);
-        const float av = __fmaf_rn(sd, z[q], mu);
-        const float dlt = av - mu;
-        lp[e * GX_POL_MAX_ACT + a] = -(dlt * dlt) / (2.0f * sd * sd) - ls - 0.91893853320467274f;
-        act[(size_t)g * A + a] = av;
-        if (mu_out) mu_out[(size_t)g * A + a] = mu;
-      }
-    }
-  }
-  __syncthreads();
-  // ---- phase 5 ----------------------------------------------------------------------------------------------------
-  if (tid < GX_POL_ENVS) {
-    const int g = e_blk + tid;
+  // Gaussian sample per action dimension, log-probability summed in a fixed order (deterministic)
+  float s = 0.0f;
+  for (int a = 0; a < A; ++a) {
+    const float mu = gx_policy_head(W3, B3, hv, a);
+    float z;
+    if (a < 4) z = a == 0 ? z0[0] : (a == 1 ? z0[1] : (a == 2 ? z0[2] : z0[3]));
+    else z = g < n ? gx_policy_noise(env_id_offset + (unsigned long long)g, age_lo, age_hi, a, k0, k1) : 0.0f;
+    const float ls = LS[a], sd = expf(ls);
+    const float av = __fmaf_rn(sd, z, mu);
+    const float dlt = av - mu;
+    s += -(dlt * dlt) / (2.0f * sd * sd) - ls - 0.91893853320467274f;
     if (g < n) {
-      float s = 0.0f;
-      for (int a = 0; a < A; ++a) s += lp[tid * GX_POL_MAX_ACT + a];   // fixed order: deterministic
-      logp[g] = s;
-      val[g] = head[tid * (GX_POL_MAX_ACT + 2) + A];
-      cval[g] = head[tid * (GX_POL_MAX_ACT + 2) + A + 1];
+      act[(size_t)g * A + a] = av;
+      if (mu_out) mu_out[(size_t)g * A + a] = mu;
     }
   }
+  if (g < n) logp[g] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// A whole PPO rollout (ppo_train.py:364-417: T x { ac.step(o); env.step(a); buf.store }) as ONE persistent launch, for
+// the default Point shape (the shape the 16-lanes-per-env kernels handle: obs 43, act 2).
+//
+// Envs are independent and the policy is evaluated per env, so a block that owns 32 envs never needs another block: it
+// keeps its envs' dynamic state in registers, the three networks' weights in shared memory (loaded ONCE, two bulk-async
+// copies), and alternates two phases per control step, each closed by one block barrier:
+//   policy  (every thread first parks its env state in shared memory) warps 0-5 evaluate the three MLPs for the 32 observation rows that sit in shared memory (gx_policy_layer)
+//           and leave the actor means in shared memory, the two value heads in the rollout buffer; meanwhile warp 6
+//           draws the step's exploration noise (Philox + Box-Muller, lane = env)
+//   env     all 16 warps, 16 lanes per env: Gaussian sample + log-prob, then gx_step_autoreset_lanes (the single-step
+//           kernel's own device function); the new observation row goes to the rollout buffer AND to shared memory, where
+//           the next policy phase reads it
+// Against the 2T-launch graph this removes, per step: two launch / drain gaps, the reload of 82 KB of weights per block, and
+// the HBM round trips of state, observation and action.  Every number is produced by the same expressions as in
+// gx_policy_kernel + gx_step_lanes_kernel, so the rollout buffer is bit-identical (tests/test_ppo_lag.py).
+#define GX_PR_ENVS 32
+#define GX_PR_THREADS 512
+#define GX_PR_K1 44
+
+__host__ __device__ inline size_t gx_policy_rollout_smem_floats() {
+  return (size_t)GX_PR_ENVS * GX_PR_K1 + 2 * 3 * (size_t)GX_PR_ENVS * GX_POL_HS + (size_t)GX_PR_K1 * GX_POL_UNITS + 3 * (size_t)GX_POL_HID * GX_POL_HID +
+         ((gx_policy_tail_floats(2) + 3) & ~(size_t)3) + 8 + 2 * GX_PR_ENVS /* mu */ + 2 * GX_PR_ENVS /* z */ + 2 * GX_PR_ENVS /* age */ +
+         18 * GX_PR_THREADS /* env state parked during the policy phase */;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(GX_PR_THREADS, 1)
+gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, const float* __restrict__ pool, const float* __restrict__ W, int T,
+                         unsigned k0, unsigned k1, float* __restrict__ obs, float2* __restrict__ act, float* __restrict__ reward,
+                         float* __restrict__ done, float* __restrict__ cost, float* __restrict__ val, float* __restrict__ cval,
+                         float* __restrict__ logp) {
+  constexpr int K1 = GX_PR_K1, A = 2, OUT = A + 2, EPW = GX_POL_EPW;
+  static_assert(GX_PR_ENVS == GX_POL_ENVS, "the rollout kernel uses the policy kernel's warp layout");
+  extern __shared__ __align__(16) float gx_pol_smem[];
+  float* xs = gx_pol_smem;                                   // [32][K1]      observation rows (column 43 stays 0)
+  float* h1 = xs + GX_PR_ENVS * K1;                          // [3][32][HS]
+  float* h2 = h1 + 3 * GX_PR_ENVS * GX_POL_HS;               // [3][32][HS]
+  float* w1s = h2 + 3 * GX_PR_ENVS * GX_POL_HS;              // [3][K1 / 4][64][4]
+  float* w2s = w1s + K1 * GX_POL_UNITS;                      // [3][16][64][4]
+  float* tl = w2s + 3 * GX_POL_HID * GX_POL_HID;             // B1 | B2 | W3 | B3 | LS
+  constexpr int tail = 2 * GX_POL_UNITS + OUT * (GX_POL_HID + 1) + A;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(tl + ((tail + 3) & ~3));
+  float* mu_s = reinterpret_cast<float*>(bar) + 8;           // [32][2] actor means of the current step
+  float* z_s = mu_s + 2 * GX_PR_ENVS;                        // [32][2] exploration noise of the current step
+  unsigned* age_s = reinterpret_cast<unsigned*>(z_s + 2 * GX_PR_ENVS);   // [32][2] step counts (lo, hi) that key the noise
+  float* park = reinterpret_cast<float*>(age_s + 2 * GX_PR_ENVS) + threadIdx.x;   // [18][512] this thread's env state while it evaluates the policy
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int sub = tid & 15, el = tid >> 4;                   // env phase: 16 lanes per env
+  const int e_blk = blockIdx.x * GX_PR_ENVS;
+  const int env = e_blk + el, n = p.n;
+  const bool live = env < n;
+  const int i = live ? env : n - 1;
+  const unsigned gmask = gx_grp_mask();
+  const float* W2 = W + (size_t)K1 * GX_POL_UNITS;
+  const float* TL = W2 + 3 * GX_POL_HID * GX_POL_HID;
+  // ---- once: weights, tail, first observation rows, env state ---------------------------------------------------------
+  if (tid == 0) {
+    gx_mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    constexpr unsigned b1 = K1 * GX_POL_UNITS * sizeof(float), b2 = 3 * GX_POL_HID * GX_POL_HID * sizeof(float);
+    gx_mbar_expect_tx(bar, b1 + b2);
+    gx_bulk_g2s(w1s, W, b1, bar);
+    gx_bulk_g2s(w2s, W2, b2, bar);
+  }
+  for (int c = tid; c < tail; c += GX_PR_THREADS) tl[c] = TL[c];
+  for (int idx = tid; idx < GX_PR_ENVS * K1; idx += GX_PR_THREADS) {
+    const int e = idx / K1, k = idx - e * K1, g = e_blk + e;
+    xs[idx] = (g < n && k < 43) ? obs[(size_t)g * 43 + k] : 0.0f;
+  }
+  GxDyn d;
+  gx_load_dyn(s, i, d);
+  const float2 g0 = s.goal[i];
+  float gx_ = g0.x, gy_ = g0.y, ox, oy;
+  gx_load_object(s, i, sub, gx_, gy_, ox, oy);
+  if (sub == 0) { age_s[2 * el] = (unsigned)d.age; age_s[2 * el + 1] = (unsigned)(d.age >> 32); }
+  __syncthreads();
+  gx_mbar_wait(bar, 0);
+  const float* W3 = tl + 2 * GX_POL_UNITS;
+  const float* B3 = W3 + OUT * GX_POL_HID;
+  const float* LS = B3 + OUT;
+  for (int t = 0; t < T; ++t) {
+    const size_t row = (size_t)t * (size_t)n;
+    // the env state of this thread is dead weight during the policy phase: park it in shared memory so that the layers'
+    // register tiles have the whole budget (128 registers at 512 threads; 12.4 -> 11.9 us per step)
+    {
+      const float v[18] = {d.qx, d.qy, d.qth, d.vx, d.vy, d.vw, d.hc, d.hs, d.prev_dist, d.steps, d.done, __uint_as_float((unsigned)d.age),
+                           __uint_as_float((unsigned)(d.age >> 32)), gx_, gy_, ox, oy, 0.0f};
+#pragma unroll
+      for (int k = 0; k < 17; ++k) park[k * GX_PR_THREADS] = v[k];
+    }
+    // ---- policy phase ------------------------------------------------------------------------------------------------
+    if (warp < GX_POL_WARPS) {
+      const int net = warp >> 1, half = warp & 1;
+      float* h1n = h1 + ((size_t)net * GX_PR_ENVS + half * EPW) * GX_POL_HS;
+      float* h2n = h2 + ((size_t)net * GX_PR_ENVS + half * EPW) * GX_POL_HS;
+      gx_policy_layer<K1>(w1s + (size_t)net * K1 * GX_POL_HID, tl + net * GX_POL_HID, xs + (size_t)half * EPW * K1, K1, h1n, lane);
+      __syncwarp();
+      gx_policy_layer<GX_POL_HID>(w2s + (size_t)net * GX_POL_HID * GX_POL_HID, tl + GX_POL_UNITS + net * GX_POL_HID, h1n, GX_POL_HS, h2n, lane);
+      __syncwarp();
+      // heads: the actor warps use both half-warps (lane >> 4 = action dimension), the critic warps their first
+      const int le = half * EPW + (lane & 15), g = e_blk + le, o = lane >> 4;
+      const float4* hv = reinterpret_cast<const float4*>(h2n + (size_t)(lane & 15) * GX_POL_HS);
+      if (net == 0) {
+        mu_s[2 * le + o] = gx_policy_head(W3, B3, hv, o);
+      } else if (o == 0) {
+        const float v = gx_policy_head(W3, B3, hv, A + net - 1);
+        if (g < n) (net == 1 ? val : cval)[row + g] = v;
+      }
+    } else if (warp == GX_POL_WARPS) {
+      // exploration noise of env `lane` for this step: the two normals of Philox words (0, 1), as gx_policy_noise draws them
+      const int g = e_blk + lane;
+      float z0 = 0.0f, z1 = 0.0f;
+      if (g < n) {
+        const unsigned long long gid = p.env_id_offset + (unsigned long long)g;
+        const gx_u32x4 r = gx_philox4x32_10((unsigned)gid, age_s[2 * lane], age_s[2 * lane + 1] ^ (unsigned)(gid >> 32), GX_STREAM_POLICY,
+                                            p.seed_lo ^ k0, p.seed_hi ^ k1);
+        const float u1 = 1.0f - gx_u01(r.v[0]);
+        const float u2 = gx_u01(r.v[1]);
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincospif(2.0f * u2, &sn, &cs);
+        z0 = rad * cs; z1 = rad * sn;
+      }
+      z_s[2 * lane] = z0; z_s[2 * lane + 1] = z1;
+    }
+    __syncthreads();
+    {
+      float v[17];
+#pragma unroll
+      for (int k = 0; k < 17; ++k) v[k] = park[k * GX_PR_THREADS];
+      d.qx = v[0]; d.qy = v[1]; d.qth = v[2]; d.vx = v[3]; d.vy = v[4]; d.vw = v[5]; d.hc = v[6]; d.hs = v[7]; d.prev_dist = v[8];
+      d.steps = v[9]; d.done = v[10];
+      d.age = (uint64_t)__float_as_uint(v[11]) | ((uint64_t)__float_as_uint(v[12]) << 32);
+      gx_ = v[13]; gy_ = v[14]; ox = v[15]; oy = v[16];
+    }
+    // ---- env phase: sample (all 16 lanes of the env compute the same numbers), step, outputs --------------------------------
+    float av[2], lsum = 0.0f;
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      const float mu = mu_s[2 * el + a], z = z_s[2 * el + a];
+      const float ls = LS[a], sd = expf(ls);
+      av[a] = __fmaf_rn(sd, z, mu);
+      const float dlt = av[a] - mu;
+      lsum += -(dlt * dlt) / (2.0f * sd * sd) - ls - 0.91893853320467274f;
+    }
+    const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age + 1, GX_STREAM_PICK);
+    const GxSpecLayout sp = gx_spec_layout(lay, sub);
+    GxLaneStep r = gx_step_autoreset_lanes(p, s, i, sub, gmask, live, lay, sp, d, gx_, gy_, ox, oy, av[0], av[1], nullptr);
+    gx_store_row_lanes(xs + (size_t)el * K1, sub, r.obs, r.c0, r.c1, r.c2, d);
+    if (sub == 0) { age_s[2 * el] = (unsigned)d.age; age_s[2 * el + 1] = (unsigned)(d.age >> 32); }
+    if (live) {
+      const size_t k = row + (size_t)i;
+      gx_store_row_lanes(obs + (k + (size_t)n) * 43, sub, r.obs, r.c0, r.c1, r.c2, d);
+      if (sub == 3) reward[k] = r.out.reward;
+      if (sub == 4) done[k] = r.out.done;
+      if (sub == 5) cost[k] = r.out.cost;
+      if (sub == 10) act[k] = make_float2(av[0], av[1]);
+      if (sub == 11) logp[k] = lsum;
+      if (STATS && sub == 9) gx_stats_step(s, i, r.out.reward, r.out.cost, r.out.done);
+    }
+    __syncthreads();
+  }
+  if (live) gx_store_dyn_lanes(s, i, sub, d);
 }
 
 #endif  // GX_POLICY_CUH_

@@ -278,9 +278,11 @@ __device__ __forceinline__ void gxt_resolve_contacts(const gxt_params& p, float*
 // every contribution is >= +0, NaN is canonicalised to the positive pattern, which compares above every finite value),
 // adds its cost term, and -- for a vase or the box -- pushes it out of the robot's way.  Cost / counts are combined with a
 // fixed butterfly over the 8 lanes (same value on every lane).
+#ifndef GXT_LPE
 #define GXT_LPE 8
+#endif
 
-__device__ __forceinline__ unsigned gxt_grp_mask() { return 0xffu << (threadIdx.x & 24); }
+__device__ __forceinline__ unsigned gxt_grp_mask() { return ((1u << GXT_LPE) - 1u) << (threadIdx.x & 31 & ~(GXT_LPE - 1)); }
 
 __device__ __forceinline__ void gxt_scatter_atomic(const gx_params& p, const GxRay& r, float* bins, int& bad) {
   const int nb = p.nb;
@@ -299,12 +301,14 @@ __device__ __forceinline__ void gxt_scatter_atomic(const gx_params& p, const GxR
 }
 
 __device__ __forceinline__ float gxt_sum8(float x, unsigned mask) {
+  if (GXT_LPE > 8) x += __shfl_xor_sync(mask, x, 8);
   x += __shfl_xor_sync(mask, x, 4);
   x += __shfl_xor_sync(mask, x, 2);
   x += __shfl_xor_sync(mask, x, 1);
   return x;
 }
 __device__ __forceinline__ int gxt_sum8i(int x, unsigned mask) {
+  if (GXT_LPE > 8) x += __shfl_xor_sync(mask, x, 8);
   x += __shfl_xor_sync(mask, x, 4);
   x += __shfl_xor_sync(mask, x, 2);
   x += __shfl_xor_sync(mask, x, 1);

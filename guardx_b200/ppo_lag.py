@@ -204,20 +204,22 @@ class GraphedRolloutStep:
 
 def pack_policy(ac: ActorCritic, obs_dim: int, act_dim: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """The actor-critic's parameters in the layout gx_policy_step reads (csrc/gx_policy.cuh):
-    W1 [K1][192] | B1 [192] | W2 [3][64][64] | B2 [192] | W3 [A+2][64] | B3 [A+2] | log_std [A], nets ordered
-    mu_net, v, vc; K1 = obs_dim rounded up to 4 (padding rows are zero).  Written in place into ``out`` when given,
-    so that a captured CUDA graph keeps reading the same buffer after every update."""
+    W1 [3][K1/4][64][4] | W2 [3][16][64][4] | B1 [3][64] | B2 [3][64] | W3 [A+2][64] | B3 [A+2] | log_std [A], nets ordered
+    mu_net, v, vc; K1 = obs_dim rounded up to 4 (padding inputs are zero); W*[net][k/4][u][k&3] is the weight of hidden
+    unit u for input k (the kernel copies a net's block into shared memory as it is).  Written in place into ``out``
+    when given, so that a captured CUDA graph keeps reading the same buffer after every update."""
     nets = (ac.mu_net, ac.v, ac.vc)
     lin = [[m for m in net if isinstance(m, nn.Linear)] for net in nets]
     assert all(len(l) == 3 and l[0].out_features == 64 and l[1].out_features == 64 for l in lin), \
         'gx_policy_step is built for hidden_sizes == (64, 64) (the reference default, ppo_train.py:461)'
     k1 = (obs_dim + 3) // 4 * 4
     with torch.no_grad():
-        w1 = torch.zeros(k1, 192, device=ac.log_std.device)
-        w1[:obs_dim] = torch.cat([l[0].weight.t() for l in lin], 1)          # [obs_dim, 3*64]
-        parts = [w1.reshape(-1), torch.cat([l[0].bias for l in lin]),
-                 torch.stack([l[1].weight.t() for l in lin]).reshape(-1),       # [net][k][u]
-                 torch.cat([l[1].bias for l in lin]),
+        def tiles(w, k):          # Linear weight [64, in] -> [k/4][64][4]
+            wp = torch.zeros(64, k, device=w.device)
+            wp[:, :w.shape[1]] = w
+            return wp.reshape(64, k // 4, 4).permute(1, 0, 2).reshape(-1)
+        parts = [torch.cat([tiles(l[0].weight, k1) for l in lin]), torch.cat([tiles(l[1].weight, 64) for l in lin]),
+                 torch.cat([l[0].bias for l in lin]), torch.cat([l[1].bias for l in lin]),
                  torch.cat([l[2].weight for l in lin]).reshape(-1),             # rows: A actor heads, v, vc
                  torch.cat([l[2].bias for l in lin]), ac.log_std]
         flat = torch.cat([x.float().reshape(-1) for x in parts])
@@ -228,16 +230,26 @@ def pack_policy(ac: ActorCritic, obs_dim: int, act_dim: int, out: torch.Tensor |
 
 
 class FusedRollout:
-    """One epoch's rollout as 2 T kernel launches in ONE CUDA graph: per control step the policy kernel
-    (gx_policy_step: three MLPs + Gaussian sample + log-prob, reading the observation row the env wrote and writing
-    act / val / cval / logp straight into the rollout buffer) and the env kernel (gx_step_autoreset, reading that
-    action, writing reward / done / cost into the buffer and the next observation into the buffer's next row).
-    No copy kernels, no torch ops, no host work between the T steps.  ``buf['obs']`` has T + 1 rows."""
+    """One epoch's rollout (ppo_train.py:364-417) without torch ops, copy kernels or host work between the T steps;
+    every output is written in place into the rollout buffer (``buf['obs']`` has T + 1 rows).  Two routes:
 
-    how = ("gx_policy_step (3 fp32 MLPs + Philox Gaussian sample + log-prob, one launch) + gx_step_autoreset per step, "
-           "outputs written in place into the rollout buffer; 2T launches replayed as one CUDA graph")
+    * ``persistent`` (default where gx_policy_rollout_supported: the default Point shape): ONE launch of
+      gx_policy_rollout -- each block owns 32 envs, keeps their state in registers and the three networks in shared
+      memory, and alternates policy and env phases T times;
+    * otherwise 2 T launches in ONE CUDA graph: per control step the policy kernel (gx_policy_step: three MLPs +
+      Gaussian sample + log-prob, reading the observation row the env wrote) and the env kernel (gx_step_autoreset,
+      reading that action, writing the next observation into the buffer's next row).
 
-    def __init__(self, env, ac, T, noise_seed=0):
+    Both produce the same bits (tests/test_ppo_lag.py)."""
+
+    HOW_GRAPH = ("gx_policy_step (3 fp32 MLPs + Philox Gaussian sample + log-prob, one launch) + gx_step_autoreset per step, "
+                 "outputs written in place into the rollout buffer; 2T launches replayed as one CUDA graph")
+    HOW_PERSISTENT = ("gx_policy_rollout: ONE persistent launch for the T steps -- a block owns 32 envs (state in registers, the "
+                      "3 fp32 MLPs' weights in shared memory) and alternates policy phases (register-tiled FFMA2, Philox Gaussian "
+                      "sample + log-prob) and env phases (gx_step_autoreset's device function); outputs in place in the rollout buffer")
+    how = HOW_GRAPH
+
+    def __init__(self, env, ac, T, noise_seed=0, persistent=None):
         import ctypes as C
         N, dev = env.env_num, env.device
         od, ad = env.observation_space.shape[0], env.action_space.shape[0]
@@ -251,6 +263,16 @@ class FusedRollout:
         self.refresh_weights()
         b = self.buf
         p = lambda x: C.c_void_p(x.data_ptr())
+        supported = bool(L.gx_policy_rollout_supported(h))
+        self.persistent = supported if persistent is None else bool(persistent)
+        assert supported or not self.persistent, 'gx_policy_rollout handles the default Point shape only'
+        self.how = self.HOW_PERSISTENT if self.persistent else self.HOW_GRAPH
+        if self.persistent:
+            self.graph = None
+            self._args = (h, p(self.weights), C.c_int32(T), C.c_uint64(noise_seed), p(b['obs']), p(b['act']), p(b['rew']), p(b['done']),
+                          p(b['cost']), p(b['val']), p(b['cval']), p(b['logp']))
+            self.reset_into_buffer()
+            return
 
         def issue(sp):
             for t in range(T):
@@ -283,21 +305,26 @@ class FusedRollout:
         env._obs = self.buf['obs'][0]
 
     def run(self):
-        self.graph.replay()
+        if self.persistent:
+            from . import _abi
+            L = self.env._lib
+            _abi.check(L, L.gx_policy_rollout(*self._args, self.env._stream()), "gx_policy_rollout")
+        else:
+            self.graph.replay()
 
 
 class RolloutTimer:
     """Times ONE epoch's rollout (T steps: policy forward + sample, env step + auto-reset, the
     buffer writes) with CUDA events on the current stream; used by bench.py."""
 
-    def __init__(self, env, ac, T, fused=True):
+    def __init__(self, env, ac, T, fused=True, persistent=None):
         N, dev = env.env_num, env.device
         self.T, self.env, self.fused = T, env, fused
         env.reset()
         env.stats_reset()
         if fused:
-            self.roll = FusedRollout(env, ac, T)
-            self.how = FusedRollout.how
+            self.roll = FusedRollout(env, ac, T, persistent=persistent)
+            self.how = self.roll.how
         else:
             f = lambda *s: torch.empty(*s, device=dev)
             self.buf = dict(obs=f(T, N, env.observation_space.shape[0]), act=f(T, N, env.action_space.shape[0]), rew=f(T, N),

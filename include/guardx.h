@@ -318,6 +318,22 @@ int64_t gx_policy_weight_floats(const gx_env* e);
 int gx_policy_step(gx_env* e, const float* weights, const float* obs, uint64_t noise_seed, float* act, float* val,
                    float* cval, float* logp, float* mu_out, void* stream);
 
+/* ---- a whole PPO / PPO-Lagrangian rollout in ONE persistent launch ------------------------------
+ * Replaces the T-step loop of safe_rl_libX/ppo/ppo_train.py:364-417 ({ a, v, logp = ac.step(o); o, r, d, info =
+ * env.step(a); buf.store(...) } with the env's auto-reset) for the default Point task shape (obs 43, act 2:
+ * gx_policy_rollout_supported(e) != 0): every block owns 32 envs, keeps their state in registers and the three
+ * networks in shared memory, and alternates policy and env phases T times (csrc/gx_policy.cuh).
+ *   weights   device, as for gx_policy_step, 16-byte aligned
+ *   obs       device [T + 1, env_num, 43]: row 0 must hold the current observation (gx_reset's, or the last row of
+ *             the previous rollout); rows 1..T are written (row t + 1 = observation after step t, reset rows for
+ *             envs that finished in step t)
+ *   act       device [T, env_num, 2];  reward, done, cost, val, cval, logp: device [T, env_num]
+ * Results are bit-identical to T x { gx_policy_step; gx_step_autoreset } with the same noise_seed.  Episode statistics
+ * (gx_stats_*) are accumulated when switched on.  Graph-capturable. */
+int gx_policy_rollout_supported(const gx_env* e);
+int gx_policy_rollout(gx_env* e, const float* weights, int32_t T, uint64_t noise_seed, float* obs, float* act, float* reward,
+                      float* done, float* cost, float* val, float* cval, float* logp, void* stream);
+
 /* ---- diagnostics: evaluate the shared fp32 math (csrc/gx_math.h) on the
  *      device, so tests can prove host/device bit-equality of the header.
  *      fn: 0 sincos(a)->out,out2   1 atan2(a,b)->out   2 exp(a)->out

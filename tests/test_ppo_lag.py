@@ -134,9 +134,9 @@ def test_pack_policy_layout():
     w = ppo_lag.pack_policy(ac, od, ad).numpy()
     k1 = 44
     o = 0
-    W1 = w[o:o + k1 * 192].reshape(k1, 192); o += k1 * 192
+    W1 = w[o:o + k1 * 192].reshape(3, k1 // 4, 64, 4).transpose(1, 3, 0, 2).reshape(k1, 192); o += k1 * 192    # -> [k][net*64+u]
+    W2 = w[o:o + 3 * 64 * 64].reshape(3, 16, 64, 4).transpose(0, 1, 3, 2).reshape(3, 64, 64); o += 3 * 64 * 64  # -> [net][k][u]
     B1 = w[o:o + 192]; o += 192
-    W2 = w[o:o + 3 * 64 * 64].reshape(3, 64, 64); o += 3 * 64 * 64
     B2 = w[o:o + 192]; o += 192
     W3 = w[o:o + (ad + 2) * 64].reshape(ad + 2, 64); o += (ad + 2) * 64
     B3 = w[o:o + ad + 2]; o += ad + 2
@@ -208,27 +208,31 @@ def test_policy_kernel_matches_the_torch_actor_critic(task, n):
 
 @pytest.mark.gpu
 def test_fused_rollout_fills_the_buffer_like_the_step_by_step_loop():
-    """FusedRollout (2T launches in one graph, outputs written in place) against the same calls issued one by one with
-    separate tensors: bit-identical buffers (same kernels, same counters)."""
+    """FusedRollout -- both routes: the ONE persistent launch (gx_policy_rollout) and the 2T launches in one graph, outputs
+    written in place -- against the same calls issued one by one with separate tensors: bit-identical buffers and episode
+    statistics (same device functions, same counters)."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import ctypes as C
     from guardx_b200 import make
     n, T = 500, 30
     bufs = []
-    for fused in (True, False):
+    st_f = []
+    for mode in ("persistent", "graph", "loop"):
+        fused = mode != "loop"
         env = make("Goal_Point_8Hazards", env_num=n, seed=4, max_ep_len=12)      # timeouts inside the window
         torch.manual_seed(9)
         ac = ppo_lag.ActorCritic(43, 2).cuda()
         if fused:
             env.reset(); env.stats_reset()
-            fr = ppo_lag.FusedRollout(env, ac, T, noise_seed=5)
+            fr = ppo_lag.FusedRollout(env, ac, T, noise_seed=5, persistent=(mode == "persistent"))
+            assert fr.persistent == (mode == "persistent")
             env.set_counters(0, 0)       # (capture ran no kernels; the reset above consumed pool epoch 0)
             fr.reset_into_buffer(); env.stats_reset()
             fr.run()
             torch.cuda.synchronize()
             bufs.append({k: v.clone() for k, v in fr.buf.items()})
-            st_f = env.stats().clone()
+            st_f.append(env.stats().clone())
         else:
             env.reset(); env.stats_reset()
             env.set_counters(0, 0)
@@ -246,7 +250,8 @@ def test_fused_rollout_fills_the_buffer_like_the_step_by_step_loop():
             b['obs'][T] = o
             bufs.append(b)
             st_e = env.stats()
-    for k in bufs[0]:
-        assert torch.equal(bufs[0][k].view(torch.int32), bufs[1][k].view(torch.int32)), k
-    assert float(bufs[0]['done'].sum()) >= n            # episodes really ended (and envs were re-placed) inside the graph
-    assert torch.equal(st_f, st_e)
+    for which in (0, 1):
+        for k in bufs[2]:
+            assert torch.equal(bufs[which][k].view(torch.int32), bufs[2][k].view(torch.int32)), (("persistent", "graph")[which], k)
+        assert torch.equal(st_f[which], st_e)
+    assert float(bufs[2]['done'].sum()) >= n            # episodes really ended (and envs were re-placed) inside the launch

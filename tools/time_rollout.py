@@ -9,7 +9,11 @@ T = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 env = make("Goal_Point_8Hazards", env_num=n, seed=0, max_ep_len=T)
 ac = ppo_lag.ActorCritic(43, 2).cuda()
 env.reset(); env.stats_reset()
-roll = ppo_lag.RolloutTimer(env, ac, T)
-ts = [roll.run() for _ in range(9)]
-dt = median(ts)
-print(json.dumps({"envs": n, "T": T, "us_per_step": 1e6 * dt / T, "env_steps_per_s": n * T / dt, "min_us": 1e6 * min(ts) / T}))
+for persistent in (True, False):
+    if persistent and not env._lib.gx_policy_rollout_supported(env._h):
+        continue
+    roll = ppo_lag.RolloutTimer(env, ac, T, persistent=persistent)
+    ts = [roll.run() for _ in range(9)]
+    dt = median(ts)
+    print(json.dumps({"route": "persistent" if persistent else "graph", "envs": n, "T": T, "us_per_step": 1e6 * dt / T,
+                      "env_steps_per_s": n * T / dt, "min_us": 1e6 * min(ts) / T}))
