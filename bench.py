@@ -643,6 +643,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(n, world),
             "how": "CUDA: fused step + auto-reset (gx_step_autoreset), one kernel launch per step, replayed as CUDA graphs, "
+                   "launches chained by programmatic dependent launch (" + ("off: GX_PDL=0" if os.environ.get("GX_PDL", "1")[:1] == "0" else "on") + "), "
                    f"in-kernel episode statistics; stationary workload (random episode phases + {BURN_IN} burn-in steps per batch)",
             "timing": {"l2_batches": R, "l2_working_set_mb": working_set / 1e6, "l2_flush_between_regions": FLUSH,
                        "window_steps": K, "settle_seconds": SETTLE_SECONDS,
