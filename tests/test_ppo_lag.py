@@ -255,3 +255,65 @@ def test_fused_rollout_fills_the_buffer_like_the_step_by_step_loop():
             assert torch.equal(bufs[which][k].view(torch.int32), bufs[2][k].view(torch.int32)), (("persistent", "graph")[which], k)
         assert torch.equal(st_f[which], st_e)
     assert float(bufs[2]['done'].sum()) >= n            # episodes really ended (and envs were re-placed) inside the launch
+
+
+@pytest.mark.gpu
+def test_policy_rollout_in_two_calls_equals_one_call():
+    """gx_policy_rollout keeps the env state on the device between calls and takes row 0 of the observation buffer as its
+    input: T = 24 steps in one launch == 10 + 14 steps in two launches, bit for bit (buffers and episode statistics)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    from guardx_b200 import make
+    n, T, T1 = 333, 24, 10
+    res = []
+    for split in (False, True):
+        env = make("Goal_Point_8Hazards", env_num=n, seed=11, max_ep_len=9)
+        torch.manual_seed(3)
+        ac = ppo_lag.ActorCritic(43, 2).cuda()
+        L, h = env._lib, env._h
+        assert L.gx_policy_rollout_supported(h) == 1
+        w = ppo_lag.pack_policy(ac, 43, 2)
+        f = lambda *s: torch.empty(*s, device='cuda')
+        b = dict(obs=f(T + 1, n, 43), act=f(T, n, 2), rew=f(T, n), done=f(T, n), cost=f(T, n), val=f(T, n), cval=f(T, n), logp=f(T, n))
+        b['obs'][0] = env.reset(); env.stats_reset()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        for t0, steps in (((0, T1), (T1, T - T1)) if split else ((0, T),)):
+            rc = L.gx_policy_rollout(h, p(w), steps, C.c_uint64(7), p(b['obs'][t0:]), p(b['act'][t0:]), p(b['rew'][t0:]), p(b['done'][t0:]),
+                                     p(b['cost'][t0:]), p(b['val'][t0:]), p(b['cval'][t0:]), p(b['logp'][t0:]), env._stream())
+            assert rc == 0, L.gx_last_error()
+        torch.cuda.synchronize()
+        res.append((b, env.stats().clone()))
+    for k in res[0][0]:
+        assert torch.equal(res[0][0][k].view(torch.int32), res[1][0][k].view(torch.int32)), k
+    assert torch.equal(res[0][1], res[1][1])
+    assert float(res[0][0]['done'].sum()) >= n
+
+
+@pytest.mark.gpu
+def test_policy_rollout_is_refused_for_other_shapes_and_bad_arguments():
+    """The persistent rollout kernel is built for the default Point shape only; everything else gets an error code and a
+    message (and FusedRollout falls back to the two-launch graph), never a wrong answer."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ctypes as C
+    from guardx_b200 import make
+    env = make("Goal_Ant_8Hazards", env_num=64, seed=0, max_ep_len=20)
+    env.reset()
+    L, h = env._lib, env._h
+    assert L.gx_policy_rollout_supported(h) == 0
+    x = torch.zeros(1 << 16, device='cuda')
+    p = C.c_void_p(x.data_ptr())
+    assert L.gx_policy_rollout(h, p, 4, C.c_uint64(0), p, p, p, p, p, p, p, p, env._stream()) != 0
+    assert b'default Point shape' in L.gx_last_error()
+    ac = ppo_lag.ActorCritic(env.observation_space.shape[0], env.action_space.shape[0]).cuda()
+    fr = ppo_lag.FusedRollout(env, ac, 3)
+    assert not fr.persistent and fr.graph is not None
+    pt = make("Goal_Point_8Hazards", env_num=64, seed=0, max_ep_len=20)
+    L, h = pt._lib, pt._h
+    assert L.gx_policy_rollout(h, p, 4, C.c_uint64(0), p, p, p, p, p, p, p, p, pt._stream()) != 0       # before reset
+    pt.reset()
+    assert L.gx_policy_rollout(h, None, 4, C.c_uint64(0), p, p, p, p, p, p, p, p, pt._stream()) != 0    # NULL weights
+    assert L.gx_policy_rollout(h, C.c_void_p(x.data_ptr() + 4), 4, C.c_uint64(0), p, p, p, p, p, p, p, p, pt._stream()) != 0   # misaligned weights
+    assert L.gx_policy_rollout(h, p, -1, C.c_uint64(0), p, p, p, p, p, p, p, p, pt._stream()) != 0
+    assert L.gx_policy_rollout(h, p, 0, C.c_uint64(0), p, p, p, p, p, p, p, p, pt._stream()) == 0       # T = 0: nothing to do

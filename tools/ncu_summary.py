@@ -17,7 +17,8 @@ KEYS = ['gpu__time_duration.sum', 'sm__cycles_active.avg', 'smsp__cycles_active.
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed']
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed']
 
 
 def run(args):
