@@ -1488,11 +1488,8 @@ template <int K1>
 static int gx_policy_launch(gx_env* e, cudaStream_t st, const float* W, const float* obs, uint64_t noise_seed, int A, float* act,
                             float* val, float* cval, float* logp, float* mu_out) {
   const size_t sh = gx_policy_smem_floats(K1) * sizeof(float);
-  static bool attr_set = false;      // per instantiation
-  if (!attr_set) {
-    GX_CUDA(cudaFuncSetAttribute(gx_policy_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    attr_set = true;
-  }
+  // (function attributes are per device: set on every call, a process may hold handles on several devices)
+  GX_CUDA(cudaFuncSetAttribute(gx_policy_kernel<K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
   const int grid = div_up(e->p.n, GX_POL_ENVS);
   // No programmatic dependent launch on either side of this kernel (measured, 4096 envs: with it 15.8 us per rollout step, with
   // only the env kernel released early 16.1, without 15.1 -- blocks of the other kernel waiting on the SMs cost more
@@ -1550,12 +1547,8 @@ GX_API int gx_policy_rollout(gx_env* e, const float* weights, int32_t T, uint64_
   DeviceGuard guard(e->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t sh = gx_policy_rollout_smem_floats() * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    GX_CUDA(cudaFuncSetAttribute(gx_policy_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    GX_CUDA(cudaFuncSetAttribute(gx_policy_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-    attr_set = true;
-  }
+  if (e->stats_on) GX_CUDA(cudaFuncSetAttribute(gx_policy_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+  else GX_CUDA(cudaFuncSetAttribute(gx_policy_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
   const int grid = div_up(e->p.n, GX_PR_ENVS);
   float2* a2 = reinterpret_cast<float2*>(act);
   const unsigned k0 = (uint32_t)noise_seed, k1 = (uint32_t)(noise_seed >> 32);
