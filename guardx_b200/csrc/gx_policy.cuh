@@ -20,12 +20,14 @@
 //    18 k LSU cycles per 32-env block, which WAS its 9-10 us.  Hence register tiles: a thread owns an 8 unit x 4 env
 //    tile (32 accumulator pairs) and per four inputs loads 8 weight quads + 4 activation quads (12 LDS.128) for
 //    128 FMAs = 1.5 B per FMA;
-//    Six warps per 32 envs: warp = (net, half of the block's envs).  Measured alternatives: an 8 x 8 tile on three warps
-//    (1 B per FMA, 232 registers) is slower (one warp per scheduler cannot hide the LDS returns); splitting the reduction
-//    over warp PAIRS that exchange partial sums through shared memory (12 warps) is a wash (the exchange + second
-//    barrier cost what the shorter streams save).  At 12 LDS.128 per 64 FFMA2 the LSU is ~55 % and the FMA pipe ~50 %
-//    busy during the layers and the two do not overlap better without registers to prefetch into: FFMA2 issues once
-//    per 2.2 cycles per scheduler at this occupancy (tools/micro/ffma2.cu), i.e. at the scalar FMA rate;
+//    Six warps per 32 envs: warp = (net, half of the block's envs).  Measured alternatives, all within 5 %: an 8 x 8 tile
+//    on three warps (1 B per FMA, 232 registers; slower), 8 x 2 tiles on twelve warps (GX_POL_E = 2), the reduction split
+//    over warp PAIRS that exchange partial sums through shared memory (12 warps).  What the layers cost is invariant under
+//    the tiling: ~5.7 k cycles of FFMA2 issue per scheduler (FFMA2 issues once per 2.2 cycles per scheduler below 8
+//    warps per scheduler, i.e. at the scalar FMA rate: tools/micro/ffma2.cu) PLUS ~5-6 k cycles of LDS.128 returns
+//    (1.5-2 cycles each SM-wide at 6-12 warps: tools/micro/lds128.cu) -- the two add up instead of overlapping, which
+//    points at the register file's bandwidth (an FFMA2 moves eight registers per lane, an LDS.128 four) as the shared
+//    resource;
 //  * and the activations: one tanh per 54 FMAs is as many instructions as the matrix products unless it is five
 //    instructions (gx_tanh_fast).
 // Lane mapping inside a warp tile: lane = 8 unit groups x 4 env groups; unit u = i * 8 + ug, env e = i * 4 + eg, so a
@@ -57,9 +59,12 @@
 #define GX_POL_HID 64
 #define GX_POL_UNITS 192   // 3 nets x 64
 #define GX_POL_ENVS 32     // envs per block
-#define GX_POL_E 4         // envs per thread tile; a warp tile is 16 envs x 64 units
-#define GX_POL_EPW (4 * GX_POL_E)
-#define GX_POL_WARPS 6     // (net, half of the block's envs)
+#ifndef GX_POL_E
+#define GX_POL_E 4         // envs per thread tile (2 or 4); a warp tile is 4 E envs x 64 units.  4 -> 6 warps, 2 -> 12 warps: same speed (measured)
+#endif
+#define GX_POL_EPW (4 * GX_POL_E)                     // envs per warp tile
+#define GX_POL_SUB (GX_POL_ENVS / GX_POL_EPW)         // warp tiles per net
+#define GX_POL_WARPS (3 * GX_POL_SUB)                 // warp = (net, slice of the block's envs)
 #define GX_POL_THREADS (32 * GX_POL_WARPS)
 #define GX_POL_HS 72       // row stride of the hidden activations in shared memory (conflict-free tile stores)
 #define GX_POL_MAX_ACT 16
@@ -225,7 +230,7 @@ gx_policy_kernel(const float* __restrict__ W, const float* __restrict__ obs, int
   const int tail = (int)gx_policy_tail_floats(A);
   unsigned long long* bar = reinterpret_cast<unsigned long long*>(tl + ((gx_policy_tail_floats(GX_POL_MAX_ACT) + 3) & ~(size_t)3));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int net = warp >> 1, half = warp & 1;   // this warp: net `net`, envs [half * 16, half * 16 + 16) of the block
+  const int net = warp / GX_POL_SUB, half = warp % GX_POL_SUB;   // this warp: net `net`, envs [half * EPW, half * EPW + EPW) of the block
   const int e_blk = blockIdx.x * GX_POL_ENVS;
   const float* W1 = W;
   const float* W2 = W1 + (size_t)K1 * GX_POL_UNITS;
@@ -400,18 +405,21 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
     }
     // ---- policy phase ------------------------------------------------------------------------------------------------
     if (warp < GX_POL_WARPS) {
-      const int net = warp >> 1, half = warp & 1;
+      const int net = warp / GX_POL_SUB, half = warp % GX_POL_SUB;
       float* h1n = h1 + ((size_t)net * GX_PR_ENVS + half * EPW) * GX_POL_HS;
       float* h2n = h2 + ((size_t)net * GX_PR_ENVS + half * EPW) * GX_POL_HS;
+#ifndef GX_PR_SKIP_POLICY
       gx_policy_layer<K1>(w1s + (size_t)net * K1 * GX_POL_HID, tl + net * GX_POL_HID, xs + (size_t)half * EPW * K1, K1, h1n, lane);
       __syncwarp();
       gx_policy_layer<GX_POL_HID>(w2s + (size_t)net * GX_POL_HID * GX_POL_HID, tl + GX_POL_UNITS + net * GX_POL_HID, h1n, GX_POL_HS, h2n, lane);
       __syncwarp();
-      // heads: the actor warps use both half-warps (lane >> 4 = action dimension), the critic warps their first
-      const int le = half * EPW + (lane & 15), g = e_blk + le, o = lane >> 4;
-      const float4* hv = reinterpret_cast<const float4*>(h2n + (size_t)(lane & 15) * GX_POL_HS);
+#endif
+      // heads: lane = (action dimension, env of the warp's slice) for the actor warps, the first EPW lanes for the critics
+      const int ll = lane % EPW, o = lane / EPW;
+      const int le = half * EPW + ll, g = e_blk + le;
+      const float4* hv = reinterpret_cast<const float4*>(h2n + (size_t)ll * GX_POL_HS);
       if (net == 0) {
-        mu_s[2 * le + o] = gx_policy_head(W3, B3, hv, o);
+        if (o < A) mu_s[2 * le + o] = gx_policy_head(W3, B3, hv, o);
       } else if (o == 0) {
         const float v = gx_policy_head(W3, B3, hv, A + net - 1);
         if (g < n) (net == 1 ? val : cval)[row + g] = v;
@@ -453,9 +461,14 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
       const float dlt = av[a] - mu;
       lsum += -(dlt * dlt) / (2.0f * sd * sd) - ls - 0.91893853320467274f;
     }
+#ifdef GX_PR_SKIP_ENV
+    GxLaneStep r; r.obs.glidar = av[0]; r.obs.hlidar = av[1]; r.obs.cx = lsum; r.obs.cy = 0.f; r.c0 = r.c1 = r.c2 = 0.f; r.out.reward = r.out.done = r.out.cost = 0.f;
+    d.age += 1;
+#else
     const float* lay = gx_pick_layout(p, pool, nullptr, i, d.age + 1, GX_STREAM_PICK);
     const GxSpecLayout sp = gx_spec_layout(lay, sub);
     GxLaneStep r = gx_step_autoreset_lanes(p, s, i, sub, gmask, live, lay, sp, d, gx_, gy_, ox, oy, av[0], av[1], nullptr);
+#endif
     gx_store_row_lanes(xs + (size_t)el * K1, sub, r.obs, r.c0, r.c1, r.c2, d);
     if (sub == 0) { age_s[2 * el] = (unsigned)d.age; age_s[2 * el + 1] = (unsigned)(d.age >> 32); }
     if (live) {
