@@ -119,9 +119,8 @@ __device__ __forceinline__ float gx_tanh_fast(float x) {
 // no packing work.  ws: this net's weights [K / 4][64][4]; bs: its biases [64]; `in` rows have `stride` floats; out rows
 // GX_POL_HS.  K is a multiple of 4.  The tile is produced and consumed by this warp alone: callers separate the layers
 // with __syncwarp.
-template <int K>
+template <int K, int E>
 __device__ __forceinline__ void gx_policy_layer(const float* ws, const float* bs, const float* in, int stride, float* out, int lane) {
-  constexpr int E = GX_POL_E;
   const int eg = lane >> 3, ug = lane & 7;
   unsigned long long acc[E][8];
 #pragma unroll
@@ -275,9 +274,9 @@ gx_policy_kernel(const float* __restrict__ W, const float* __restrict__ obs, int
   // ---- phase 1, 2: this warp's net and envs ------------------------------------------------------------------------
   float* h1n = h1 + ((size_t)net * GX_POL_ENVS + half * GX_POL_EPW) * GX_POL_HS;
   float* h2n = h2 + ((size_t)net * GX_POL_ENVS + half * GX_POL_EPW) * GX_POL_HS;
-  gx_policy_layer<K1>(w1s + (size_t)net * K1 * GX_POL_HID, tl + net * GX_POL_HID, xs + (size_t)half * GX_POL_EPW * K1, K1, h1n, lane);
+  gx_policy_layer<K1, GX_POL_E>(w1s + (size_t)net * K1 * GX_POL_HID, tl + net * GX_POL_HID, xs + (size_t)half * GX_POL_EPW * K1, K1, h1n, lane);
   __syncwarp();
-  gx_policy_layer<GX_POL_HID>(w2s + (size_t)net * GX_POL_HID * GX_POL_HID, tl + GX_POL_UNITS + net * GX_POL_HID, h1n, GX_POL_HS, h2n, lane);
+  gx_policy_layer<GX_POL_HID, GX_POL_E>(w2s + (size_t)net * GX_POL_HID * GX_POL_HID, tl + GX_POL_UNITS + net * GX_POL_HID, h1n, GX_POL_HS, h2n, lane);
   __syncwarp();
   // ---- phase 3: lane = env; one 64-long dot product per output ---------------------------------------------------------
   if (!mine) return;
@@ -315,11 +314,13 @@ gx_policy_kernel(const float* __restrict__ W, const float* __restrict__ obs, int
 //
 // Envs are independent and the policy is evaluated per env, so a block that owns 32 envs never needs another block: it
 // keeps its envs' dynamic state in registers, the three networks' weights in shared memory (loaded ONCE, two bulk-async
-// copies), and alternates two phases per control step, each closed by one block barrier:
-//   policy  (every thread first parks its env state in shared memory) warps 0-5 evaluate the three MLPs for the 32 observation rows that sit in shared memory (gx_policy_layer)
-//           and leave the actor means in shared memory, the two value heads in the rollout buffer; meanwhile warp 6
-//           draws the step's exploration noise (Philox + Box-Muller, lane = env)
-//   env     all 16 warps, 16 lanes per env: Gaussian sample + log-prob, then gx_step_autoreset_lanes (the single-step
+// copies), and alternates two phases per control step, each closed by one barrier -- of the GROUP: the 16 warps form
+// GX_PR_GROUPS groups that own 32 / GX_PR_GROUPS envs each and run out of phase (see the main loop).  Per group:
+//   policy  (every thread first parks its env state in shared memory) the group's first three warps evaluate the three
+//           MLPs for the group's observation rows that sit in shared memory (gx_policy_layer) and leave the actor means
+//           in shared memory, the two value heads in the rollout buffer; meanwhile its fourth warp draws the step's
+//           exploration noise (Philox + Box-Muller, lane = env)
+//   env     all warps of the group, 16 lanes per env: Gaussian sample + log-prob, then gx_step_autoreset_lanes (the single-step
 //           kernel's own device function); the new observation row goes to the rollout buffer AND to shared memory, where
 //           the next policy phase reads it
 // Against the 2T-launch graph this removes, per step: two launch / drain gaps, the reload of 82 KB of weights per block, and
@@ -328,6 +329,12 @@ gx_policy_kernel(const float* __restrict__ W, const float* __restrict__ obs, int
 #define GX_PR_ENVS 32
 #define GX_PR_THREADS 512
 #define GX_PR_K1 44
+#ifndef GX_PR_GROUPS
+#define GX_PR_GROUPS 4     // groups of warps that run their envs' steps out of phase (1, 2 or 4)
+#endif
+#ifndef GX_PR_E
+#define GX_PR_E (GX_PR_GROUPS == 4 ? 2 : 4)   // envs per thread tile: a group of 8 envs is one 8-env warp tile per net
+#endif
 
 __host__ __device__ inline size_t gx_policy_rollout_smem_floats() {
   return (size_t)GX_PR_ENVS * GX_PR_K1 + 2 * 3 * (size_t)GX_PR_ENVS * GX_POL_HS + (size_t)GX_PR_K1 * GX_POL_UNITS + 3 * (size_t)GX_POL_HID * GX_POL_HID +
@@ -341,7 +348,7 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
                          unsigned k0, unsigned k1, float* __restrict__ obs, float2* __restrict__ act, float* __restrict__ reward,
                          float* __restrict__ done, float* __restrict__ cost, float* __restrict__ val, float* __restrict__ cval,
                          float* __restrict__ logp) {
-  constexpr int K1 = GX_PR_K1, A = 2, OUT = A + 2, EPW = GX_POL_EPW;
+  constexpr int K1 = GX_PR_K1, A = 2, OUT = A + 2, E = GX_PR_E, EPW = 4 * E;
   static_assert(GX_PR_ENVS == GX_POL_ENVS, "the rollout kernel uses the policy kernel's warp layout");
   extern __shared__ __align__(16) float gx_pol_smem[];
   float* xs = gx_pol_smem;                                   // [32][K1]      observation rows (column 43 stays 0)
@@ -393,6 +400,19 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
   const float* W3 = tl + 2 * GX_POL_UNITS;
   const float* B3 = W3 + OUT * GX_POL_HID;
   const float* LS = B3 + OUT;
+  // Groups: with GX_PR_GROUPS == 2 the block's warps 0-7 / 8-15 own envs 0-15 / 16-31 and run their steps HALF A STEP APART
+  // (group 1 starts when group 0 has finished its first policy phase; after that nothing couples them: each group has
+  // its own named barrier), so that one group's env phase -- latency-bound, light -- fills the issue slots that the
+  // other group's layers -- register-file-bound -- leave.
+  constexpr int NG = GX_PR_GROUPS, GW = (GX_PR_THREADS / 32) / NG, GE = GX_PR_ENVS / NG, SUBG = GE / EPW;
+  static_assert(GE % EPW == 0 && 3 * SUBG < GW, "a group needs 3 * SUBG policy warps and one noise warp");
+  const int grp = warp / GW, wl = warp % GW, e0 = grp * GE;
+  auto group_sync = [&]() {
+    if (NG == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(GW * 32) : "memory");
+  };
+  // stagger: group g starts when group g - 1 has finished its first policy phase (barrier NG + g, both groups' threads)
+  if (NG > 1 && grp > 0) asm volatile("bar.sync %0, %1;" ::"r"(NG + grp), "r"(2 * GW * 32) : "memory");
   for (int t = 0; t < T; ++t) {
     const size_t row = (size_t)t * (size_t)n;
     // the env state of this thread is dead weight during the policy phase: park it in shared memory so that the layers'
@@ -404,19 +424,19 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
       for (int k = 0; k < 17; ++k) park[k * GX_PR_THREADS] = v[k];
     }
     // ---- policy phase ------------------------------------------------------------------------------------------------
-    if (warp < GX_POL_WARPS) {
-      const int net = warp / GX_POL_SUB, half = warp % GX_POL_SUB;
-      float* h1n = h1 + ((size_t)net * GX_PR_ENVS + half * EPW) * GX_POL_HS;
-      float* h2n = h2 + ((size_t)net * GX_PR_ENVS + half * EPW) * GX_POL_HS;
+    if (wl < 3 * SUBG) {
+      const int net = wl / SUBG, r0 = e0 + (wl % SUBG) * EPW;      // this warp: net `net`, envs [r0, r0 + EPW) of the block
+      float* h1n = h1 + ((size_t)net * GX_PR_ENVS + r0) * GX_POL_HS;
+      float* h2n = h2 + ((size_t)net * GX_PR_ENVS + r0) * GX_POL_HS;
 #ifndef GX_PR_SKIP_POLICY
-      gx_policy_layer<K1>(w1s + (size_t)net * K1 * GX_POL_HID, tl + net * GX_POL_HID, xs + (size_t)half * EPW * K1, K1, h1n, lane);
+      gx_policy_layer<K1, E>(w1s + (size_t)net * K1 * GX_POL_HID, tl + net * GX_POL_HID, xs + (size_t)r0 * K1, K1, h1n, lane);
       __syncwarp();
-      gx_policy_layer<GX_POL_HID>(w2s + (size_t)net * GX_POL_HID * GX_POL_HID, tl + GX_POL_UNITS + net * GX_POL_HID, h1n, GX_POL_HS, h2n, lane);
+      gx_policy_layer<GX_POL_HID, E>(w2s + (size_t)net * GX_POL_HID * GX_POL_HID, tl + GX_POL_UNITS + net * GX_POL_HID, h1n, GX_POL_HS, h2n, lane);
       __syncwarp();
 #endif
       // heads: lane = (action dimension, env of the warp's slice) for the actor warps, the first EPW lanes for the critics
       const int ll = lane % EPW, o = lane / EPW;
-      const int le = half * EPW + ll, g = e_blk + le;
+      const int le = r0 + ll, g = e_blk + le;
       const float4* hv = reinterpret_cast<const float4*>(h2n + (size_t)ll * GX_POL_HS);
       if (net == 0) {
         if (o < A) mu_s[2 * le + o] = gx_policy_head(W3, B3, hv, o);
@@ -424,13 +444,13 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
         const float v = gx_policy_head(W3, B3, hv, A + net - 1);
         if (g < n) (net == 1 ? val : cval)[row + g] = v;
       }
-    } else if (warp == GX_POL_WARPS) {
-      // exploration noise of env `lane` for this step: the two normals of Philox words (0, 1), as gx_policy_noise draws them
-      const int g = e_blk + lane;
+    } else if (wl == 3 * SUBG && lane < GE) {
+      // exploration noise of the group's env `lane` for this step: the two normals of Philox words (0, 1), as gx_policy_noise draws them
+      const int le = e0 + lane, g = e_blk + le;
       float z0 = 0.0f, z1 = 0.0f;
       if (g < n) {
         const unsigned long long gid = p.env_id_offset + (unsigned long long)g;
-        const gx_u32x4 r = gx_philox4x32_10((unsigned)gid, age_s[2 * lane], age_s[2 * lane + 1] ^ (unsigned)(gid >> 32), GX_STREAM_POLICY,
+        const gx_u32x4 r = gx_philox4x32_10((unsigned)gid, age_s[2 * le], age_s[2 * le + 1] ^ (unsigned)(gid >> 32), GX_STREAM_POLICY,
                                             p.seed_lo ^ k0, p.seed_hi ^ k1);
         const float u1 = 1.0f - gx_u01(r.v[0]);
         const float u2 = gx_u01(r.v[1]);
@@ -439,9 +459,10 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
         sincospif(2.0f * u2, &sn, &cs);
         z0 = rad * cs; z1 = rad * sn;
       }
-      z_s[2 * lane] = z0; z_s[2 * lane + 1] = z1;
+      z_s[2 * le] = z0; z_s[2 * le + 1] = z1;
     }
-    __syncthreads();
+    group_sync();
+    if (NG > 1 && grp + 1 < NG && t == 0) asm volatile("bar.arrive %0, %1;" ::"r"(NG + grp + 1), "r"(2 * GW * 32) : "memory");   // releases the next group
     {
       float v[17];
 #pragma unroll
@@ -481,7 +502,7 @@ gx_policy_rollout_kernel(const __grid_constant__ gx_params p, const GxState s, c
       if (sub == 11) logp[k] = lsum;
       if (STATS && sub == 9) gx_stats_step(s, i, r.out.reward, r.out.cost, r.out.done);
     }
-    __syncthreads();
+    group_sync();
   }
   if (live) gx_store_dyn_lanes(s, i, sub, d);
 }

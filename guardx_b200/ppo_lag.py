@@ -246,7 +246,8 @@ class FusedRollout:
                  "outputs written in place into the rollout buffer; 2T launches replayed as one CUDA graph")
     HOW_PERSISTENT = ("gx_policy_rollout: ONE persistent launch for the T steps -- a block owns 32 envs (state in registers, the "
                       "3 fp32 MLPs' weights in shared memory) and alternates policy phases (register-tiled FFMA2, Philox Gaussian "
-                      "sample + log-prob) and env phases (gx_step_autoreset's device function); outputs in place in the rollout buffer")
+                      "sample + log-prob) and env phases (gx_step_autoreset's device function), four groups of warps out of phase; "
+                      "outputs in place in the rollout buffer")
     how = HOW_GRAPH
 
     def __init__(self, env, ac, T, noise_seed=0, persistent=None):
