@@ -232,6 +232,12 @@ __global__ void __launch_bounds__(64) gxt_step_kernel(const __grid_constant__ gx
   gx_store_tile(tile, obs + (size_t)wbase * p.obs_dim, min(32, p.n - wbase), p.obs_dim, lane);
 }
 
+// the step-pose observation pass of an env in an exotic state (non-finite / astronomically large pose or objects), out of line
+__device__ __noinline__ GxtObs gxt_obs_lanes_cold(const gxt_params& p, float* __restrict__ S, const float* ob, int i, int l, unsigned mask,
+                                                  const GxtGeom& g, float goal_button, float* row, const GxDyn* push) {
+  return gxt_obs_lanes(p, S, ob, i, l, mask, g, goal_button, row, push);
+}
+
 // ---- Engine.step (+ fused reset_done) with 8 lanes per env: 4 envs per warp, 16 per 128-thread block ----------------
 template <bool AUTORESET>
 __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_constant__ gxt_params p, float* __restrict__ S,
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
   float* row = tile + (size_t)(lane / GXT_LPE) * p.obs_dim;
   const int ob_stride = 2 * p.nobj + p.ng;
   float* ob = gxt_smem + (size_t)(blockDim.x / GXT_LPE) * p.obs_dim + (size_t)(threadIdx.x / GXT_LPE) * ob_stride;
-  gxt_stage_objects(p, S, i, l, ob);
+  const int staged_ok = gxt_stage_objects(p, S, i, l, ob);
   GxDyn d;
   float prev_box, goal_button;
   gxt_load_dyn(p, S, i, d, prev_box, goal_button);
@@ -265,9 +271,22 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
     gx_mjx_step_point(p.pt, d, c0, c1, c2, g.px, g.py, g.r00, g.r10, nullptr);
   }
   gxt_zero_lidars(p, row, l);
+  // Fused step + reset_done with ONE observation pass (as the Point kernels do it, gx_lanes.cuh): whether the env finishes is
+  // decided BEFORE the lidar -- target distance, jump and timeout need no lidar, and with sane objects and a sane pose
+  // snapshot every entry the lidar / compass pass writes is finite by construction, so the NaN / Inf guard reduces to ctrl /
+  // qpos / qvel.  A finishing env then takes its cost from a cost-only pass at the step pose, is re-placed, and the single
+  // observation pass produces its reset observation.  A launch lasts as long as its slowest warp and nearly every launch has
+  // a finishing env: this takes the second lidar pass out of that warp.  Anything exotic keeps the reference order.
+  const bool fast = AUTORESET && gxt_sum8i(staged_ok, mask) == GXT_LPE && (gx_abs(g.px) < GX_SANE_BOUND) && (gx_abs(g.py) < GX_SANE_BOUND) &&
+                    !gx_notfinite(g.r00) && !gx_notfinite(g.r10) && !gx_notfinite(g.time) &&
+                    (p.pt.use_exp ? p.pt.neg_exp_gain <= 0.0f : p.pt.lidar_max_dist > 0.0f);
   __syncwarp(mask);
   gxt_resolve_pillars(p, ob, d);
-  GxtObs o = gxt_obs_lanes(p, S, ob, i, l, mask, g, goal_button, row, live ? &d : nullptr);
+  GxtObs o;
+  o.bad = 0;
+  if (fast) gxt_task_dists(p, ob, gxt_target_index(p, goal_button), g, o);
+  else if (AUTORESET) o = gxt_obs_lanes_cold(p, S, ob, i, l, mask, g, goal_button, row, live ? &d : nullptr);   // exotic state: reference order, out of line
+  else o = gxt_obs_lanes(p, S, ob, i, l, mask, g, goal_button, row, live ? &d : nullptr);
   int bad = o.bad | gx_notfinite(c0) | gx_notfinite(c1) | gx_notfinite(c2) | gx_notfinite(d.qx) | gx_notfinite(d.qy) | gx_notfinite(d.qth) |
             gx_notfinite(d.vx) | gx_notfinite(d.vy) | gx_notfinite(d.vw);
   const float dist = o.dist_task;
@@ -290,6 +309,12 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
   if (gx_abs(d_dist) > 1.0f) { dn_flag = 1.0f; rew = 0.0f; flags |= GX_AUX_JUMP; }
   if (bad) { rew = 0.0f; dn_flag = 1.0f; flags |= GX_AUX_GUARD; }
   if (d.steps > p.num_steps) { dn_flag = 1.0f; flags |= GX_AUX_TIMEOUT; }
+  if (fast && dn_flag > 0.0f) gxt_cost_lanes(p, ob, l, mask, g, goal_button, o);
+  // the ONE inlined observation pass of the fused kernel: step pose with pushes (fast path, env goes on) or reset pose
+  // (env finished; after the re-placement below)
+  GxtGeom gg = g;
+  const GxDyn* push = live ? &d : nullptr;
+  const bool second = AUTORESET && dn_flag > 0.0f;
   d.steps = dn_flag > 0.0f ? 0.0f : d.steps + 1.0f;
   d.done = dn_flag;
   d.prev_dist = dist;
@@ -297,7 +322,8 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
   d.hc = g.r00; d.hs = g.r10;
   d.age += 1;
   if (AUTORESET && dn_flag > 0.0f) {
-    // re-place (the 8 lanes copy the layout row), then the reset observation: a second pass over the objects
+    // re-place (the 8 lanes copy the layout row), then the reset observation (the only pass over the objects' lidar on the
+    // fast path; the second one otherwise)
     __syncwarp(mask);
     const float* lay = gxt_pick_layout(p, pool, nullptr, i, d.age, GX_STREAM_PICK);
     for (int k = l; k < 2 * p.nobj; k += GXT_LPE) {
@@ -322,10 +348,15 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
     c0 = 0.0f; c1 = 0.0f; c2 = 0.0f;
     GxtGeom g2;
     g2.px = d.qx; g2.py = d.qy; g2.r00 = 1.0f; g2.r10 = 0.0f; g2.time = 0.0f;
-    gxt_zero_lidars(p, row, l);
+    if (!fast) gxt_zero_lidars(p, row, l);      // (fast path: nothing has been scattered into the row yet)
     __threadfence_block();
     __syncwarp(mask);
-    gxt_obs_lanes(p, S, ob, i, l, mask, g2, goal_button, row, nullptr);
+    gg = g2;
+    push = nullptr;
+  }
+  if (fast || second) {
+    const GxtObs f = gxt_obs_lanes(p, S, ob, i, l, mask, gg, goal_button, row, push);
+    if (fast && !second) { o.cost = f.cost; o.violations = f.violations; o.contacts = f.contacts; o.goal_bin = f.goal_bin; }
   }
   if (l == 0) {
     if (p.off_ctrl >= 0) { row[p.off_ctrl] = c0; row[p.off_ctrl + 1] = c1; if (p.nu == 3) row[p.off_ctrl + 2] = c2; }

@@ -315,6 +315,60 @@ __device__ __forceinline__ int gxt_sum8i(int x, unsigned mask) {
   return x;
 }
 
+// index of the task's target object: the goal button (button task) or the goal
+__device__ __forceinline__ int gxt_target_index(const gxt_params& p, float goal_button) {
+  return p.task == GXT_TASK_BUTTON ? p.first[GXT_BUTTON] + min(max((int)goal_button, 0), p.count[GXT_BUTTON] - 1) : p.first[GXT_GOAL];
+}
+
+// task distances (every lane, same numbers) from where target and box are in `ob`
+__device__ __forceinline__ void gxt_task_dists(const gxt_params& p, const float* ob, int tgt, const GxtGeom& g, GxtObs& o) {
+  const float tx = ob[2 * tgt], ty = ob[2 * tgt + 1];
+  const float dx = tx - g.px, dy = ty - g.py;
+  o.dist_task = gx_sqrt(dx * dx + dy * dy);
+  o.dist_box = 0.0f;
+  if (p.task == GXT_TASK_PUSH) {
+    const float bx = ob[2 * p.first[GXT_BOX]], by = ob[2 * p.first[GXT_BOX] + 1];
+    const float ex = bx - g.px, ey = by - g.py;
+    o.dist_box = gx_sqrt(ex * ex + ey * ey);
+    const float fx = tx - bx, fy = ty - by;
+    o.dist_task = gx_sqrt(fx * fx + fy * fy);       // box -> goal
+  }
+}
+
+// where object j is at the snapshot's time (a gremlin circles its centre at radius gremlins_travel, 1 rad / s)
+__device__ __forceinline__ void gxt_obj_pos(const gxt_params& p, const float* ob, int j, int cls, float time, float& ox, float& oy) {
+  ox = ob[2 * j]; oy = ob[2 * j + 1];
+  if (cls == GXT_GREMLIN) {
+    float sn, cs;
+    gx_sincos(ob[2 * p.nobj + (j - p.first[GXT_GREMLIN])] + time, &sn, &cs);
+    ox = ox + p.gremlins_travel * cs;
+    oy = oy + p.gremlins_travel * sn;
+  }
+}
+
+// cost term of object j (world-frame distance to the snapshot position, as engine.py:804-811 does for hazards)
+__device__ __forceinline__ void gxt_obj_cost(const gxt_params& p, int j, int cls, int tgt, float ox, float oy, const GxtGeom& g, float& cost,
+                                             int& viol, int& contacts) {
+  const float rr = p.size[GXT_ROBOT];
+  const float dx = ox - g.px, dy = oy - g.py;
+  const float dist = gx_sqrt(dx * dx + dy * dy);
+  if (cls == GXT_HAZARD) {
+    const float term = p.size[GXT_HAZARD] - gx_min(dist, p.size[GXT_HAZARD]);
+    if (term > 0.0f) ++viol;
+    cost = cost + p.hazards_cost_scale * term;
+  } else if (cls == GXT_BUTTON) {
+    if (!(p.task == GXT_TASK_BUTTON && j == tgt) && dist < rr + p.size[GXT_BUTTON]) { cost = cost + p.buttons_cost; ++contacts; }
+  } else if (cls == GXT_VASE) {
+    if (dist < rr + p.size[GXT_VASE]) { cost = cost + p.vases_contact_cost; ++contacts; }
+  } else if (cls == GXT_PILLAR) {
+    if (dist < rr + p.size[GXT_PILLAR]) { cost = cost + p.pillars_cost; ++contacts; }
+  } else if (cls == GXT_GREMLIN) {
+    if (dist < rr + p.size[GXT_GREMLIN]) { cost = cost + p.gremlins_contact_cost; ++contacts; }
+    const float gap = dist - p.size[GXT_GREMLIN];
+    if (gap < p.gremlins_dist_threshold) cost = cost + p.gremlins_dist_cost * (p.gremlins_dist_threshold - gap);
+  }
+}
+
 // One observation / cost pass of an env by its 8 lanes from the pose snapshot `g`.  `row`: the env's row in shared memory
 // (lidar ranges must be zero on entry, see gxt_zero_lidars).  `push` (may be null): the post-step robot state; vases and
 // the box that overlap it are pushed out (written back to S) AFTER their ray has been cast from where they were.
@@ -326,35 +380,16 @@ __device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __re
   int bad = 0, viol = 0, contacts = 0;
   float cost = 0.0f;
   const float rr = p.size[GXT_ROBOT];
-  const int tgt = p.task == GXT_TASK_BUTTON
-                      ? p.first[GXT_BUTTON] + min(max((int)goal_button, 0), p.count[GXT_BUTTON] - 1)
-                      : p.first[GXT_GOAL];
+  const int tgt = gxt_target_index(p, goal_button);
   int goal_bin = 0;
-  // task distances (every lane, same numbers) from where target and box are NOW: the loop below may push the box
-  {
-    const float tx = ob[2 * tgt], ty = ob[2 * tgt + 1];
-    const float dx = tx - g.px, dy = ty - g.py;
-    o.dist_task = gx_sqrt(dx * dx + dy * dy);
-    o.dist_box = 0.0f;
-    if (p.task == GXT_TASK_PUSH) {
-      const float bx = ob[2 * p.first[GXT_BOX]], by = ob[2 * p.first[GXT_BOX] + 1];
-      const float ex = bx - g.px, ey = by - g.py;
-      o.dist_box = gx_sqrt(ex * ex + ey * ey);
-      const float fx = tx - bx, fy = ty - by;
-      o.dist_task = gx_sqrt(fx * fx + fy * fy);       // box -> goal
-    }
-  }
+  // task distances from where target and box are NOW: the loop below may push the box
+  gxt_task_dists(p, ob, tgt, g, o);
   __syncwarp(mask);
 #pragma unroll 1
   for (int j = l; j < p.nobj; j += GXT_LPE) {
     const int cls = gxt_class_of_obj(p, j);
-    float ox = ob[2 * j], oy = ob[2 * j + 1];
-    if (cls == GXT_GREMLIN) {      // circle of radius gremlins_travel about the centre, 1 rad / s
-      float sn, cs;
-      gx_sincos(ob[2 * p.nobj + (j - p.first[GXT_GREMLIN])] + g.time, &sn, &cs);
-      ox = ox + p.gremlins_travel * cs;
-      oy = oy + p.gremlins_travel * sn;
-    }
+    float ox, oy;
+    gxt_obj_pos(p, ob, j, cls, g.time, ox, oy);
     float ex, ey;
     gx_ego(ox, oy, g.px, g.py, g.r00, g.r10, ex, ey);
     const GxRay r = gx_lidar_ray(p.pt, ex, ey);
@@ -375,24 +410,7 @@ __device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __re
       if (p.off_goal_lidar >= 0) gxt_scatter_atomic(p.pt, r, row + p.off_goal_lidar, bad);
     }
     if (cls == GXT_BOX && p.off_box_compass >= 0) { row[p.off_box_compass] = ex; row[p.off_box_compass + 1] = ey; bad |= gx_notfinite(ex) | gx_notfinite(ey); }
-    // cost term of this object (world-frame distance to the snapshot position, as engine.py:804-811 does for hazards)
-    const float dx = ox - g.px, dy = oy - g.py;
-    const float dist = gx_sqrt(dx * dx + dy * dy);
-    if (cls == GXT_HAZARD) {
-      const float term = p.size[GXT_HAZARD] - gx_min(dist, p.size[GXT_HAZARD]);
-      if (term > 0.0f) ++viol;
-      cost = cost + p.hazards_cost_scale * term;
-    } else if (cls == GXT_BUTTON) {
-      if (!(p.task == GXT_TASK_BUTTON && j == tgt) && dist < rr + p.size[GXT_BUTTON]) { cost = cost + p.buttons_cost; ++contacts; }
-    } else if (cls == GXT_VASE) {
-      if (dist < rr + p.size[GXT_VASE]) { cost = cost + p.vases_contact_cost; ++contacts; }
-    } else if (cls == GXT_PILLAR) {
-      if (dist < rr + p.size[GXT_PILLAR]) { cost = cost + p.pillars_cost; ++contacts; }
-    } else if (cls == GXT_GREMLIN) {
-      if (dist < rr + p.size[GXT_GREMLIN]) { cost = cost + p.gremlins_contact_cost; ++contacts; }
-      const float gap = dist - p.size[GXT_GREMLIN];
-      if (gap < p.gremlins_dist_threshold) cost = cost + p.gremlins_dist_cost * (p.gremlins_dist_threshold - gap);
-    }
+    gxt_obj_cost(p, j, cls, tgt, ox, oy, g, cost, viol, contacts);
     // quasi-static push by the post-step robot
     if (push && (cls == GXT_VASE || cls == GXT_BOX)) {
       const float qx = ox - push->qx, qy = oy - push->qy;
@@ -411,6 +429,32 @@ __device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __re
   o.bad = gxt_sum8i(bad, mask) != 0;
   o.goal_bin = gxt_sum8i(goal_bin, mask);          // exactly one lane owns the target
   return o;
+}
+
+// The cost half of gxt_obs_lanes alone (no lidar, no row, no pushes): cost / violations / contacts from the pose snapshot,
+// with the same per-lane object order and the same butterfly, so the sums are the same bits; plus the target's lidar bin
+// (aux).  For an env that finishes in this step: its observation is the reset observation, only these leave the step pose.
+__device__ __forceinline__ void gxt_cost_lanes(const gxt_params& p, const float* ob, int l, unsigned mask, const GxtGeom& g, float goal_button,
+                                               GxtObs& o) {
+  int viol = 0, contacts = 0, goal_bin = 0;
+  float cost = 0.0f;
+  const int tgt = gxt_target_index(p, goal_button);
+#pragma unroll 1
+  for (int j = l; j < p.nobj; j += GXT_LPE) {
+    const int cls = gxt_class_of_obj(p, j);
+    float ox, oy;
+    gxt_obj_pos(p, ob, j, cls, g.time, ox, oy);
+    if (j == tgt) {
+      float ex, ey;
+      gx_ego(ox, oy, g.px, g.py, g.r00, g.r10, ex, ey);
+      goal_bin = gx_lidar_ray(p.pt, ex, ey).bin;
+    }
+    gxt_obj_cost(p, j, cls, tgt, ox, oy, g, cost, viol, contacts);
+  }
+  o.cost = gxt_sum8(cost, mask);
+  o.violations = gxt_sum8i(viol, mask);
+  o.contacts = gxt_sum8i(contacts, mask);
+  o.goal_bin = gxt_sum8i(goal_bin, mask);
 }
 
 // the robot against the pillars (sequential: each projection moves the robot), every lane computes the same numbers
@@ -433,9 +477,17 @@ __device__ __forceinline__ void gxt_resolve_pillars(const gxt_params& p, const f
 
 // stage the env's object coordinates and gremlin phases in shared memory: the 8 lanes issue their loads together, every
 // later access (lidar loop, pillars, target, box) is a shared-memory read instead of a dependent global load
-__device__ __forceinline__ void gxt_stage_objects(const gxt_params& p, const float* __restrict__ S, int i, int l, float* ob) {
+// Returns 1 when every staged value of this lane is finite and of sane magnitude (then, with a sane pose, every ego vector,
+// distance, angle and sensor reading of the observation is finite by construction: the NaN / Inf guard cannot fire on them).
+__device__ __forceinline__ int gxt_stage_objects(const gxt_params& p, const float* __restrict__ S, int i, int l, float* ob) {
   const int cnt = 2 * p.nobj + p.ng;
-  for (int k = l; k < cnt; k += GXT_LPE) ob[k] = S[(size_t)(GXT_SLOT_OBJ + k) * p.cap + i];
+  int ok = 1;
+  for (int k = l; k < cnt; k += GXT_LPE) {
+    const float v = S[(size_t)(GXT_SLOT_OBJ + k) * p.cap + i];
+    ob[k] = v;
+    ok &= gx_abs(v) < GX_SANE_BOUND;
+  }
+  return ok;
 }
 
 // zero the lidar ranges of the env's row (its 8 lanes stride over the row)
