@@ -296,7 +296,16 @@ __device__ __forceinline__ GxObsOut gx_obs_row(const gx_params& p, const GxState
     cost = cost + term;
   };
   if constexpr (NH_CT != 0) {
+    // NOT unrolled over the hazard pairs: two copies of the ray code instead of one per hazard.  Unrolled, this kernel was
+    // 9184 instructions (147 KB: more than the instruction cache holds; ncu: 2 cycles of `no_instruction` stall per issued
+    // instruction); rolled, the hazards are indexed in a 64-byte per-thread array that lives in local memory (L1 hits).
+    // Fresh batches, us per step at 16 384 / 65 536 / 262 144 / 2^20 envs: unrolled 8.1 / 11.2 / 29.5 / 99.3, rolled
+    // 7.7 / 10.9 / 28.1 / 87.9 (one hazard per iteration: 8.1 / 11.3 / 29.1 / 90.9).  -DGX_HZ_UNROLLED restores the old loop.
+#if defined(GX_HZ_UNROLLED)
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int k = 0; k < (NH_CT + 1) / 2; ++k) {
       const float4 h = hz_regs[k];
       hazard(h.x, h.y, 2 * k);
