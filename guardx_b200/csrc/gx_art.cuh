@@ -167,11 +167,7 @@ struct GxArtSegWork {
 // the last body.
 template <int K, int NB>
 GX_HD void gx_art_seg_kin(const GxArtSeg& sg, const float* q, float* pp, float* pq, GxArtSegWork<K, NB>& w) {
-#ifdef GX_ART_ROLL
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
   for (int b = 0; b < NB; ++b) {
     if (b < sg.nb) {
       const GxArtBody& B = sg.body[b];
@@ -223,11 +219,7 @@ GX_HD void gx_art_seg_kin(const GxArtSeg& sg, const float* q, float* pp, float* 
 template <int K, int NB>
 GX_HD void gx_art_seg_dyn(const GxArtSeg& sg, const float* c, const float* v, float* cvel, float* cacc,
                           GxArtSegWork<K, NB>& w) {
-#ifdef GX_ART_ROLL
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
   for (int b = 0; b < NB; ++b) {
     if (b < sg.nb) {
       const GxArtBody& B = sg.body[b];
