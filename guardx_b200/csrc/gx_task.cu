@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_consta
                                                              const float* __restrict__ pool, const float* __restrict__ action,
                                                              float* __restrict__ obs, float* __restrict__ reward, float* __restrict__ done,
                                                              float* __restrict__ cost, int32_t* __restrict__ aux) {
+  gx_pdl_sync();      // programmatic dependent launch (gx_device.cuh): before the first access to global memory
   const int l = threadIdx.x & (GXT_LPE - 1), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int env = (blockIdx.x * blockDim.x + threadIdx.x) / GXT_LPE;
   const int wenv0 = (blockIdx.x * blockDim.x + (threadIdx.x & ~31)) / GXT_LPE;     // first env of this warp
@@ -617,8 +618,18 @@ GXT_API int gxt_step(gxt_env* e, const float* action, float* obs, float* reward,
   if (lanes) {
     const int block = 128, epb = block / GXT_LPE;
     const size_t sh = sizeof(float) * epb * (p.obs_dim + 2 * p.nobj + p.ng);     // observation rows + staged object coordinates
-    if (autoreset) gxt_step_lanes_kernel<true><<<gxt_div_up(p.n, epb), block, sh, st>>>(p, e->S, e->pool, action, obs, reward, done, cost, aux);
-    else gxt_step_lanes_kernel<false><<<gxt_div_up(p.n, epb), block, sh, st>>>(p, e->S, e->pool, action, obs, reward, done, cost, aux);
+    // chained by programmatic dependent launch, as the Point step kernels are (guardx.cu: gx_launch; GX_PDL=0 switches it off)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gxt_div_up(p.n, epb)); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = sh; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    static const bool pdl = [] { const char* v = getenv("GX_PDL"); return !(v && v[0] == '0'); }();
+    cfg.numAttrs = pdl ? 1 : 0;
+    float* S_ = e->S; const float* pool_ = e->pool;
+    if (autoreset) cudaLaunchKernelEx(&cfg, gxt_step_lanes_kernel<true>, p, S_, pool_, action, obs, reward, done, cost, aux);
+    else cudaLaunchKernelEx(&cfg, gxt_step_lanes_kernel<false>, p, S_, pool_, action, obs, reward, done, cost, aux);
     GXT_LAUNCH_CHECK("gxt_step_lanes_kernel");
     return GX_OK;
   }
