@@ -124,6 +124,7 @@ __device__ __forceinline__ void gx_store_row_lanes(float* row, int sub, const Gx
                                                    float c1, float c2, const GxDyn& d) {
   row[5 + sub] = o.glidar;
   row[21 + sub] = o.hlidar;
+#ifdef GX_ROW_SWITCH
   float v;
   switch (sub) {
     case 0: v = c0; break;
@@ -138,6 +139,21 @@ __device__ __forceinline__ void gx_store_row_lanes(float* row, int sub, const Gx
     case 9: v = d.vy; break;
     default: v = d.vw; break;
   }
+#else
+  // a chain of selects, not a switch: the 16 lanes of an env all take different cases, and a divergent 11-way switch is
+  // executed case by case
+  float v = d.vw;
+  v = sub == 9 ? d.vy : v;
+  v = sub == 8 ? d.vx : v;
+  v = sub == 7 ? d.qth : v;
+  v = sub == 6 ? d.qy : v;
+  v = sub == 5 ? d.qx : v;
+  v = sub == 4 ? o.cy : v;
+  v = sub == 3 ? o.cx : v;
+  v = sub == 2 ? c2 : v;
+  v = sub == 1 ? c1 : v;
+  v = sub == 0 ? c0 : v;
+#endif
   if (sub < 11) row[sub < 5 ? sub : 32 + sub] = v;
 }
 
