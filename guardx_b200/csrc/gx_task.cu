@@ -239,8 +239,10 @@ __device__ __noinline__ GxtObs gxt_obs_lanes_cold(const gxt_params& p, float* __
 }
 
 // ---- Engine.step (+ fused reset_done) with 8 lanes per env: 4 envs per warp, 16 per 128-thread block ----------------
+// Seven resident blocks per SM (<= 72 registers): the 16 384-env launch of BASELINE.json configs[2] is 1024 blocks, one wave on
+// 148 SMs only if seven fit -- at 80 registers it is 1.15 waves and 25 % slower (measured twice by accident).
 template <bool AUTORESET>
-__global__ void __launch_bounds__(128) gxt_step_lanes_kernel(const __grid_constant__ gxt_params p, float* __restrict__ S,
+__global__ void __launch_bounds__(128, 7) gxt_step_lanes_kernel(const __grid_constant__ gxt_params p, float* __restrict__ S,
                                                              const float* __restrict__ pool, const float* __restrict__ action,
                                                              float* __restrict__ obs, float* __restrict__ reward, float* __restrict__ done,
                                                              float* __restrict__ cost, int32_t* __restrict__ aux) {

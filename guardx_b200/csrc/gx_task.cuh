@@ -352,21 +352,25 @@ __device__ __forceinline__ void gxt_obj_cost(const gxt_params& p, int j, int cls
   const float rr = p.size[GXT_ROBOT];
   const float dx = ox - g.px, dy = oy - g.py;
   const float dist = gx_sqrt(dx * dx + dy * dy);
-  if (cls == GXT_HAZARD) {
-    const float term = p.size[GXT_HAZARD] - gx_min(dist, p.size[GXT_HAZARD]);
-    if (term > 0.0f) ++viol;
-    cost = cost + p.hazards_cost_scale * term;
-  } else if (cls == GXT_BUTTON) {
-    if (!(p.task == GXT_TASK_BUTTON && j == tgt) && dist < rr + p.size[GXT_BUTTON]) { cost = cost + p.buttons_cost; ++contacts; }
-  } else if (cls == GXT_VASE) {
-    if (dist < rr + p.size[GXT_VASE]) { cost = cost + p.vases_contact_cost; ++contacts; }
-  } else if (cls == GXT_PILLAR) {
-    if (dist < rr + p.size[GXT_PILLAR]) { cost = cost + p.pillars_cost; ++contacts; }
-  } else if (cls == GXT_GREMLIN) {
-    if (dist < rr + p.size[GXT_GREMLIN]) { cost = cost + p.gremlins_contact_cost; ++contacts; }
-    const float gap = dist - p.size[GXT_GREMLIN];
-    if (gap < p.gremlins_dist_threshold) cost = cost + p.gremlins_dist_cost * (p.gremlins_dist_threshold - gap);
-  }
+  // Branch-free over the classes (the lanes of an env hold objects of different classes: an if-chain would run class by
+  // class).  Every `cost = cost + x` below adds exactly what the chain added, or nothing: `cost` is updated through selects,
+  // never by adding a zero, so the bits are the same.
+  const float hterm = p.size[GXT_HAZARD] - gx_min(dist, p.size[GXT_HAZARD]);
+  const bool is_h = cls == GXT_HAZARD;
+  viol += (is_h && hterm > 0.0f) ? 1 : 0;
+  cost = is_h ? cost + p.hazards_cost_scale * hterm : cost;
+  const bool touch_b = cls == GXT_BUTTON && !(p.task == GXT_TASK_BUTTON && j == tgt) && dist < rr + p.size[GXT_BUTTON];
+  const bool touch_v = cls == GXT_VASE && dist < rr + p.size[GXT_VASE];
+  const bool touch_p = cls == GXT_PILLAR && dist < rr + p.size[GXT_PILLAR];
+  const bool is_g = cls == GXT_GREMLIN;
+  const bool touch_g = is_g && dist < rr + p.size[GXT_GREMLIN];
+  cost = touch_b ? cost + p.buttons_cost : cost;
+  cost = touch_v ? cost + p.vases_contact_cost : cost;
+  cost = touch_p ? cost + p.pillars_cost : cost;
+  cost = touch_g ? cost + p.gremlins_contact_cost : cost;
+  contacts += (touch_b || touch_v || touch_p || touch_g) ? 1 : 0;
+  const float gap = dist - p.size[GXT_GREMLIN];
+  cost = (is_g && gap < p.gremlins_dist_threshold) ? cost + p.gremlins_dist_cost * (p.gremlins_dist_threshold - gap) : cost;
 }
 
 // One observation / cost pass of an env by its 8 lanes from the pose snapshot `g`.  `row`: the env's row in shared memory
@@ -393,16 +397,14 @@ __device__ __forceinline__ GxtObs gxt_obs_lanes(const gxt_params& p, float* __re
     float ex, ey;
     gx_ego(ox, oy, g.px, g.py, g.r00, g.r10, ex, ey);
     const GxRay r = gx_lidar_ray(p.pt, ex, ey);
+    // (selects, not a switch: the lanes of an env hold objects of different classes, and a divergent switch runs case by case)
     int off = -1;
-    switch (cls) {
-      case GXT_BOX: off = p.off_box_lidar; break;
-      case GXT_BUTTON: off = p.off_buttons_lidar; break;
-      case GXT_HAZARD: off = p.off_hazards_lidar; break;
-      case GXT_VASE: off = p.off_vases_lidar; break;
-      case GXT_PILLAR: off = p.off_pillars_lidar; break;
-      case GXT_GREMLIN: off = p.off_gremlins_lidar; break;
-      default: break;
-    }
+    off = cls == GXT_BOX ? p.off_box_lidar : off;
+    off = cls == GXT_BUTTON ? p.off_buttons_lidar : off;
+    off = cls == GXT_HAZARD ? p.off_hazards_lidar : off;
+    off = cls == GXT_VASE ? p.off_vases_lidar : off;
+    off = cls == GXT_PILLAR ? p.off_pillars_lidar : off;
+    off = cls == GXT_GREMLIN ? p.off_gremlins_lidar : off;
     if (off >= 0) gxt_scatter_atomic(p.pt, r, row + off, bad);
     if (j == tgt) {
       goal_bin = r.bin;
