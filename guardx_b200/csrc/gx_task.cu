@@ -259,6 +259,15 @@ __global__ void __launch_bounds__(128, 7) gxt_step_lanes_kernel(const __grid_con
   const int ob_stride = 2 * p.nobj + p.ng;
   float* ob = gxt_smem + (size_t)(blockDim.x / GXT_LPE) * p.obs_dim + (size_t)(threadIdx.x / GXT_LPE) * ob_stride;
   const int staged_ok = gxt_stage_objects(p, S, i, l, ob);
+  // zero the warp's whole observation tile with 128-bit stores (everything that is not a lidar range is overwritten below;
+  // zeroing the seven lidars one by one was 9 % of the kernel's instructions); issued after the state loads
+  {
+    const int cnt = (32 / GXT_LPE) * p.obs_dim;      // the tile is 16-byte aligned: a warp's tile starts at a multiple of 4 rows
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    for (int k = lane; k < (cnt >> 2); k += 32) t4[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (int k = (cnt & ~3) + lane; k < cnt; k += 32) tile[k] = 0.0f;
+    __syncwarp();      // a row is zeroed by lanes of every env of the warp
+  }
   GxDyn d;
   float prev_box, goal_button;
   gxt_load_dyn(p, S, i, d, prev_box, goal_button);
@@ -273,7 +282,6 @@ __global__ void __launch_bounds__(128, 7) gxt_step_lanes_kernel(const __grid_con
     c0 = d.hc * a0; c1 = d.hs * a0; c2 = a1;
     gx_mjx_step_point(p.pt, d, c0, c1, c2, g.px, g.py, g.r00, g.r10, nullptr);
   }
-  gxt_zero_lidars(p, row, l);
   // Fused step + reset_done with ONE observation pass (as the Point kernels do it, gx_lanes.cuh): whether the env finishes is
   // decided BEFORE the lidar -- target distance, jump and timeout need no lidar, and with sane objects and a sane pose
   // snapshot every entry the lidar / compass pass writes is finite by construction, so the NaN / Inf guard reduces to ctrl /
