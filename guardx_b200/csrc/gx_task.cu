@@ -383,7 +383,14 @@ __global__ void __launch_bounds__(128, 7) gxt_step_lanes_kernel(const __grid_con
   // the warp's 4 rows are contiguous in shared memory and in the output
   const int rows = min(32 / GXT_LPE, p.n - wenv0);
   float* dst = obs + (size_t)wenv0 * p.obs_dim;
-  for (int k = lane; k < rows * p.obs_dim; k += 32) dst[k] = tile[k];
+  const int total = rows * p.obs_dim;
+  if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(tile)) & 15u) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(tile);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int k = lane; k < (total >> 2); k += 32) d4[k] = s4[k];     // a full warp's four rows are 16-byte aligned at both ends
+  } else {
+    for (int k = lane; k < total; k += 32) dst[k] = tile[k];
+  }
 }
 
 __global__ void gxt_reset_done_kernel(const __grid_constant__ gxt_params p, float* __restrict__ S, const float* __restrict__ pool,
