@@ -23,6 +23,26 @@ __device__ __forceinline__ unsigned gx_art_mask() {
 
 struct GxArtObs { float dist_goal, cost; int bad, violations; };
 
+// One ray into the env's shared lidar row by atomic max on the float's bit pattern (readings are >= +0, for which the integer
+// order is the float order; NaN is written as the canonical quiet NaN, which is larger than every finite pattern, and
+// flagged).  Same index semantics as gx_lidar_scatter (gather clamps, out-of-bounds scatter is dropped).
+__device__ __forceinline__ int gx_art_scatter_atomic(const gx_params& p, const GxRay& r, float* bins) {
+  const int nb = p.nb;
+  int bad = 0;
+  auto put = [&](int b, float v) {
+    bad |= gx_notfinite(v);
+    atomicMax(reinterpret_cast<int*>(bins + b), (v != v) ? 0x7fc00000 : __float_as_int(v));
+  };
+  if (r.bin < nb) put(r.bin, r.sensor);
+  if (p.alias) {
+    int bp = r.bin + 1; if (bp >= nb) bp -= nb; if (bp >= nb) bp -= nb;
+    int bm = r.bin - 1; if (bm < 0) bm += nb;
+    put(bp, r.up);
+    put(bm, r.down);
+  }
+  return bad;
+}
+
 // Observation row of one env, written by its LANES lanes into `row` (shared memory):
 // geometry from the pose snapshot (engine.py:754-758, 817-900), qpos / qvel = (q, v) given
 // (post-step values on a step, engine.py:759-762), ctrl = the unclipped action.
@@ -79,30 +99,27 @@ __device__ __forceinline__ GxArtObs gx_art_obs_row(const gx_params& p, const GxS
     if (aux_row) aux_row[2] = gr.bin;
     if (p.off_glidar >= 0) bad |= gx_lidar_scatter(p, gr, row + p.off_glidar);
   }
-  // hazards: lane l takes hazards l, l + LANES, ...; the scatters into the shared row are
-  // serialised lane by lane (all updates are max, so the order cannot change the result)
+  // hazards: lane l takes hazards l, l + LANES, ...; all lanes cast their rays at the same time and scatter into the shared
+  // row with atomic max (the updates are max, so their order cannot change the result).  The scatters used to be
+  // serialised lane by lane, i.e. the lidar ran with one lane in LANES active: 14 % of the ant's step.
   float cost = 0.0f, viol = 0.0f;
 #pragma unroll 1
-  for (int ph = 0; ph < LANES; ++ph) {
-    if (lane == ph) {
-      for (int h = lane; h < p.nh; h += LANES) {
-        float hx, hy, ex, ey;
-        gx_art_hazard(s, lay, i, h, hx, hy);
-        gx_ego(hx, hy, sn.px, sn.py, sn.r00, sn.r10, ex, ey);
-        if (p.off_hlidar >= 0 || aux_row) {
-          const GxRay r = gx_lidar_ray(p, ex, ey);
-          if (aux_row) aux_row[3 + h] = r.bin;
-          if (p.off_hlidar >= 0) bad |= gx_lidar_scatter(p, r, row + p.off_hlidar);
-        }
-        const float dx = hx - sn.px, dy = hy - sn.py;
-        const float dist = gx_sqrt(dx * dx + dy * dy);
-        const float term = p.hazards_size - gx_min(dist, p.hazards_size);
-        if (term > 0.0f) viol += 1.0f;
-        cost = cost + term;
-      }
+  for (int h = lane; h < p.nh; h += LANES) {
+    float hx, hy, ex, ey;
+    gx_art_hazard(s, lay, i, h, hx, hy);
+    gx_ego(hx, hy, sn.px, sn.py, sn.r00, sn.r10, ex, ey);
+    if (p.off_hlidar >= 0 || aux_row) {
+      const GxRay r = gx_lidar_ray(p, ex, ey);
+      if (aux_row) aux_row[3 + h] = r.bin;
+      if (p.off_hlidar >= 0) bad |= gx_art_scatter_atomic(p, r, row + p.off_hlidar);
     }
-    __syncwarp(mask);
+    const float dx = hx - sn.px, dy = hy - sn.py;
+    const float dist = gx_sqrt(dx * dx + dy * dy);
+    const float term = p.hazards_size - gx_min(dist, p.hazards_size);
+    if (term > 0.0f) viol += 1.0f;
+    cost = cost + term;
   }
+  __syncwarp(mask);
   o.cost = gx_art_sum<LANES>(cost, mask);
   o.violations = (int)gx_art_sum<LANES>(viol, mask);
   o.bad = gx_art_or<LANES>(bad, mask);
