@@ -490,6 +490,9 @@ static const char* gxt_lower(const gxt_config* c, gxt_params* p) {
   if (c->task == GXT_TASK_PUSH && (c->count[GXT_GOAL] != 1 || c->count[GXT_BOX] != 1)) return "push task: one goal and one box";
   if (c->task != GXT_TASK_PUSH && c->count[GXT_BOX] != 0) return "a box only exists in the push task";
   p->nobj = nobj; p->ng = c->count[GXT_GREMLIN];
+  static_assert(GXT_MAX_OBJECTS == 64 && GXT_NCLASS <= 16, "cls_bits packs 64 objects x 4 bits");
+  for (int w = 0; w < GXT_MAX_OBJECTS / 16; ++w) p->cls_bits[w] = 0;
+  for (int o = 0; o < nobj; ++o) p->cls_bits[o >> 4] |= (uint64_t)gxt_class_scan(*p, o) << (4 * (o & 15));
   p->nu = c->robot == GXT_ROBOT_CAR ? 2 : 3;
   for (int k = 0; k < GXT_NCLASS; ++k) {
     p->size[k] = (float)c->size[k]; p->keep[k] = (float)c->keepout[k];

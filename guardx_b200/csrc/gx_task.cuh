@@ -34,13 +34,18 @@ struct gxt_params {
   int32_t off_box_compass, off_box_lidar, off_buttons_lidar, off_ctrl, off_goal_compass, off_goal_lidar, off_gremlins_lidar,
       off_hazards_lidar, off_pillars_lidar, off_qpos, off_qvel, off_vases_lidar;
   float car_mass, car_inertia, car_wheel_r, car_half_track, car_gear, car_mh_lin, car_mh_ang;
+  uint64_t cls_bits[GXT_MAX_OBJECTS / 16];   // class of object o in 4 bits: (cls_bits[o >> 4] >> (4 * (o & 15))) & 15 (filled by gxt_lower)
 };
 
-__device__ __forceinline__ int gxt_class_of_obj(const gxt_params& p, int o) {
+__host__ __device__ inline int gxt_class_scan(const gxt_params& p, int o) {
   int c = 0;
-#pragma unroll
   for (int k = 1; k < GXT_ROBOT; ++k) c = (o >= p.first[k] && p.count[k] > 0) ? k : c;
   return c;
+}
+// class of object o: a table lookup (the scan over the classes was 4 % of the lanes kernel's instructions)
+__device__ __forceinline__ int gxt_class_of_obj(const gxt_params& p, int o) {
+  const uint64_t w = (o >> 4) == 0 ? p.cls_bits[0] : ((o >> 4) == 1 ? p.cls_bits[1] : ((o >> 4) == 2 ? p.cls_bits[2] : p.cls_bits[3]));
+  return (int)((w >> (4 * (o & 15))) & 15u);
 }
 
 // ---- robots ----------------------------------------------------------------------------------------------------
