@@ -22,6 +22,7 @@ if [ "$G" = "b" ] || [ "$G" = "all" ]; then
 run art_ant_65536 gx_art_kernel 31 1 python tools/prof_target.py 65536 3 0 xmls/ant.xml
 run tree_doggo_4096 gx_tree_kernel 31 1 python tools/prof_target.py 4096 3 0 xmls/doggo.xml
 run policy_4096 gx_policy_kernel 25 2 python tools/prof_policy.py 4096 20 graph
+run task_button_car_16384 gxt_step_lanes_kernel 25 1 python tools/prof_task.py Button_Car 16384 30
 # launch list of the bench command (cold-cache, serialised: shares, not absolutes)
 python bench.py --steps 20 --warmup 5 --no-sweep --no-legged --no-ppo > $O/r2_bench_plain.json 2> $O/r2_bench_plain.err && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $O/r2_launches.csv \
