@@ -635,7 +635,7 @@ def main():
                     "single_thread": rate1}
 
     if rank == 0:
-        kname = "gx_step_lanes_kernel" if n <= 12288 else "gx_step_kernel"
+        kname = "gx_step_lanes_kernel" if n <= 9216 else "gx_step_kernel"
         traffic, traffic_src = load_traffic(kname, n)
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
@@ -663,7 +663,7 @@ def main():
             "gpu_launches": S,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": kname + "<true,true>" if n <= 12288 else kname,
+                         "kernel": kname + "<true,true>" if n <= 9216 else kname,
                          "alg_bytes_per_env_step": ALG_BYTES_STEP, "envs_per_launch": n,
                          "us_per_launch": step_us, "peak_source": peak_src,
                          "note": "latency-bound at 4096 envs (1.4 MB per launch, one dependent chain per env); "

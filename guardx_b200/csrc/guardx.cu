@@ -832,7 +832,8 @@ static int gx_create_impl(const gx_config* h_cfg, const GxArtModel* h_model, int
   e->stage = nullptr;
   e->tree_host = nullptr; e->tree.m = nullptr; e->tree.tq = nullptr; e->tree.tw = nullptr; e->tree.scratch = nullptr;
   e->art_host = nullptr; e->art.m = nullptr; e->art.aq = nullptr; e->art.nv = 0; e->art.nu = 0; e->art_shape = 0;
-  e->lanes_max_envs = 12288;  // measured crossover with the one-thread kernel: 8192 -> 5.7 vs 8.8 us, 16384 -> 9.7 vs 9.1 us
+  e->lanes_max_envs = 9216;   // measured crossover with the one-thread kernel (us per step, lanes vs thread-per-env, after the latter's hazard
+                              // loop was rolled): 8192 -> 6.5 vs 7.2, 10 240 -> 8.4 vs 7.4, 12 288 -> 9.0 vs 7.5, 16 384 -> 10.3 vs 7.7
   if (const char* v = getenv("GX_LANES_MAX_ENVS")) e->lanes_max_envs = atoi(v);
   const int cap = div_up(p.n, 32) * 32;
   GxState& s = e->s;
